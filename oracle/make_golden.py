@@ -1,0 +1,258 @@
+"""Generate ``tests/golden/*.json`` by running the UNMODIFIED scBONITA2 reference.
+
+Run in the build container only (``python -m oracle.make_golden``): it imports the reference
+from ``/root/reference/code`` through ``oracle/ref_loader.py``.  The committed JSON files carry
+inputs AND reference outputs, so the parity tests need neither this script nor the reference.
+
+Cases
+-----
+templates.json   ``Node.possibilities`` for 0..4 parents               (node_class.py:45-107)
+rules_*.json     chunked matrix, ordered candidate lists, (difference, count) per candidate,
+                 ``infer_ruleset()`` result and node side effects   (rule_determination.py)
+sweep_*.json     seeded ``CalculateImportanceScore`` runs: sampled columns, RAW integer totals
+                 (captured by shadowing ``max`` inside the reference module — the reference
+                 only returns the normalised values), normalised scores, attractor lengths per
+                 condition and cell                                  (importance_scores.py)
+traj_*.json      ``attractor_analysis.vectorized_run_simulation`` for selected cells
+"""
+from __future__ import annotations
+
+import builtins
+import json
+import logging
+import os
+import pickle
+import random
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import ref_loader  # noqa: E402
+from tools import synth  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def rows_to_text(mat) -> list:
+    return ["".join("1" if v else "0" for v in row) for row in np.asarray(mat)]
+
+
+def spec_to_json(s) -> dict:
+    return {"name": s.name, "index": s.index,
+            "predecessors": [[int(k), v] for k, v in s.predecessors.items()],
+            "inversions": [[int(k), bool(v)] for k, v in s.inversions.items()],
+            "logic": s.logic}
+
+
+def make_ref_nodes(ns, specs):
+    return [ns.node_class.Node(s.name, s.index, dict(s.predecessors), dict(s.inversions))
+            for s in specs]
+
+
+def dump(name, obj):
+    path = os.path.join(OUT, name)
+    with open(path, "w") as fh:
+        json.dump(obj, fh, separators=(",", ":"))
+    print(f"wrote {path} ({os.path.getsize(path)} bytes)")
+
+
+# ------------------------------------------------------------------------------------------
+def golden_templates(ns):
+    out = {}
+    for k in range(5):
+        node = ns.node_class.Node("X", 9, {i: f"P{i}" for i in range(k)},
+                                  {i: False for i in range(k)})
+        out[str(k)] = [str(x) for x in node.possibilities]
+    dump("templates.json", out)
+
+
+def golden_rules(ns, tag, n_nodes, n_cells, seed, flip, **net_kw):
+    specs, planes = synth.synthetic_dataset(n_nodes, n_cells, seed, flip=flip, **net_kw)
+    dense = synth.planes_to_dense(planes, n_cells)
+    csr = sp.csr_matrix(dense.astype(float))
+    RD = ns.rule_determination.RuleDetermination
+
+    # candidates + per-candidate errors on fresh nodes (calculate_refined_errors mutates them)
+    probe_nodes = make_ref_nodes(ns, specs)
+    rd = RD(None, f"net_{tag}", f"ds_{tag}", csr, probe_nodes, {s.name: s.index for s in specs})
+    chunked = np.asarray(rd.chunked_data_numpy)
+    cands, errors = [], []
+    for node in probe_nodes:
+        node.find_all_rule_predictions()
+    for node in probe_nodes:
+        # same list growth as calculate_refined_errors (:459-475), by calling its building blocks
+        rules = node.node_rules
+        combos = [RD.generate_not_combinations(r[2]) for r in rules]
+        for combo in combos:
+            for logic in combo:
+                parents = [p for p in node.predecessors]
+                if [node.name, parents, logic] not in rules:
+                    rules.append([node.name, parents, logic])
+        cands.append([r[2] for r in rules])
+        errors.append([[int(d), int(c)] for d, c in
+                       (RD.calculate_error(node, r[2], chunked) for r in rules)])
+
+    # the end-to-end inference on another fresh set of nodes
+    nodes = make_ref_nodes(ns, specs)
+    rd2 = RD(None, f"net_{tag}", f"ds_{tag}", csr, nodes, {s.name: s.index for s in specs})
+    ruleset = rd2.infer_ruleset()
+    out_rules = [[r[0][0], [int(i) for i in r[0][1]], r[0][2], int(r[1]), float(r[2])]
+                 for r in ruleset]
+    after = [{"predecessors": [[int(k), v] for k, v in n.predecessors.items()],
+              "inversions": [[int(k), bool(v)] for k, v in n.inversions.items()],
+              "n_node_rules": len(n.node_rules),
+              "flat_node_rules": not isinstance(n.node_rules[0], list),
+              "best_rule_index": int(n.best_rule_index)} for n in nodes]
+    rules_txt = open(os.path.join(
+        ns.file_paths.file_paths["rules_output"], f"ds_{tag}_rules",
+        f"net_{tag}_ds_{tag}_rules.txt")).read()
+    dump(f"rules_{tag}.json", {
+        "n_cells": n_cells, "specs": [spec_to_json(s) for s in specs],
+        "matrix": rows_to_text(dense), "num_chunks": int(rd.num_chunks),
+        "chunked": rows_to_text(chunked), "candidates": cands, "errors": errors,
+        "ruleset": out_rules, "nodes_after": after, "rules_txt": rules_txt})
+
+
+def golden_chunk_widths(ns):
+    """Chunk widths whose ties round differently: drive chunk_data directly."""
+    RD = ns.rule_determination.RuleDetermination
+    out = []
+    rng = np.random.default_rng(5)
+    for n_cells, num_chunks in [(240, 20), (280, 20), (300, 15), (247, 19), (100, 10),
+                                (90, 10), (64, 64), (50, 80), (2095, 210)]:
+        dense = (rng.random((5, n_cells)) < 0.5).astype(np.uint8)
+        rd = RD.__new__(RD)
+        rd.binarized_matrix = sp.csr_matrix(dense.astype(float))
+        chunked = np.asarray(rd.chunk_data(num_chunks=num_chunks))
+        out.append({"n_cells": n_cells, "num_chunks": num_chunks, "matrix": rows_to_text(dense),
+                    "chunked": rows_to_text(chunked)})
+    dump("chunk_widths.json", out)
+
+
+class _CaptureMax:
+    def __init__(self):
+        self.values = None
+
+    def __call__(self, *args, **kw):
+        if len(args) == 1 and not kw:
+            seq = list(args[0])
+            self.values = seq
+            return builtins.max(seq)
+        return builtins.max(*args, **kw)
+
+
+def golden_sweep(ns, tag, specs, dense, seed, logics=None):
+    """``specs[i].logic`` (or ``logics[i]``) becomes ``best_rule[2]`` of node i."""
+    nodes = make_ref_nodes(ns, specs)
+    for i, node in enumerate(nodes):
+        logic = logics[i] if logics else specs[i].logic
+        node.best_rule = [node.name, [p for p in node.predecessors], logic]
+    csr = sp.csr_matrix(dense.astype(float))
+    random.seed(seed)
+    mod = ns.importance_scores
+    calc = mod.CalculateImportanceScore(nodes, csr.astype(bool), f"net_{tag}", f"ds_{tag}")
+    cap = _CaptureMax()
+    mod.max = cap
+    result = {"n_cells": int(dense.shape[1]), "seed": seed,
+              "specs": [spec_to_json(s) for s in specs],
+              "logics": [n.best_rule[2] for n in nodes], "matrix": rows_to_text(dense),
+              "sample": [int(i) for i in calc.cell_sample_indices]}
+    try:
+        scores = calc.calculate_importance_scores()
+        result["raw"] = [int(v) for v in cap.values]
+        result["scores"] = [float(scores[n.name]) for n in nodes]
+        result["error"] = None
+    except (KeyError, ZeroDivisionError) as exc:
+        result["raw"] = [int(v) for v in cap.values] if cap.values is not None else None
+        result["scores"] = None
+        result["error"] = type(exc).__name__
+    finally:
+        del mod.max
+    # attractor lengths (lambda+1; 0 = no repeat) per condition, from the reference's pickles
+    n_cells = len(calc.cell_sample_indices)
+
+    def lengths(path):
+        found = pickle.load(open(path, "rb"))
+        return [int(np.asarray(found[c]).shape[1]) if c in found else 0 for c in range(n_cells)]
+
+    d = calc.intermediate_dir
+    result["len_normal"] = lengths(f"{d}/normal_signaling.pkl")
+    result["len_ko"] = [lengths(f"{d}/knockout_results_{n.name}.pkl") for n in nodes]
+    result["len_ki"] = [lengths(f"{d}/knockin_results_{n.name}.pkl") for n in nodes]
+    dump(f"sweep_{tag}.json", result)
+
+
+def golden_traj(ns, tag, specs, dense, cells):
+    nodes = make_ref_nodes(ns, specs)
+    for node, s in zip(nodes, specs):
+        node.calculation_function = s.logic
+    out = {"specs": [spec_to_json(s) for s in specs], "matrix": rows_to_text(dense),
+           "cells": cells,
+           "trajectories": [ns.attractor_analysis.vectorized_run_simulation(
+               nodes, [int(v) for v in dense[:, c]]) for c in cells]}
+    dump(f"traj_{tag}.json", out)
+
+
+def ring_network(n, twist=True):
+    """Shift ring G_i <- G_{i-1}; with ``twist`` G_0 <- not G_{n-1} (period 2n Johnson ring)."""
+    specs = []
+    for i in range(n):
+        p = (i - 1) % n
+        inv = bool(twist and i == 0)
+        specs.append(synth.NodeSpec(f"G{i}", i, {p: f"G{p}"}, {p: inv},
+                                    "not A" if inv else "A"))
+    return specs
+
+
+def main():
+    logging.disable(logging.CRITICAL)
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load()
+    golden_templates(ns)
+    golden_chunk_widths(ns)
+
+    # rule inference: small unchunked, noisy, and chunked (>2000 cells; widths 10 and 9)
+    golden_rules(ns, "small", 12, 150, seed=1, flip=0.05)
+    golden_rules(ns, "noisy", 16, 97, seed=2, flip=0.25)
+    golden_rules(ns, "selfloops", 10, 64, seed=3, flip=0.10, p_source=0.4, allow_self=True)
+    golden_rules(ns, "chunk10", 8, 2250, seed=4, flip=0.10)
+    golden_rules(ns, "chunk9", 6, 2095, seed=5, flip=0.15)
+
+    # KO/KI sweeps: planted random networks (mostly fixed points / short cycles) ...
+    for tag, n_nodes, n_cells, seed in [("rand_a", 10, 40, 11), ("rand_b", 14, 70, 12),
+                                        ("rand_c", 20, 33, 13)]:
+        specs, planes = synth.synthetic_dataset(n_nodes, n_cells, seed, flip=0.2, relax_steps=2)
+        golden_sweep(ns, tag, specs, synth.planes_to_dense(planes, n_cells), seed)
+    # ... more cells than the 500-cell sample
+    specs, planes = synth.synthetic_dataset(6, 620, 21, flip=0.2, relax_steps=1)
+    golden_sweep(ns, "sampled", specs, synth.planes_to_dense(planes, 620), 21)
+    # ... long cycles: plain 5-ring (period | 5), Johnson rings with period 12 and 2*30 > 50
+    rng = np.random.default_rng(31)
+    for tag, n, twist in [("ring5", 5, False), ("twist6", 6, True), ("twist30", 30, True)]:
+        specs = ring_network(n, twist)
+        dense = (rng.random((n, 24)) < 0.5).astype(np.uint8)
+        golden_sweep(ns, tag, specs, dense, 31)
+    # ... mixed: a random network feeding from a 2-cycle and a 3-ring
+    specs, planes = synth.synthetic_dataset(9, 48, 41, flip=0.3, relax_steps=0)
+    logics = [s.logic for s in specs]
+    specs[0].predecessors, specs[0].inversions, logics[0] = {1: "G1"}, {1: True}, "not A"
+    specs[1].predecessors, specs[1].inversions, logics[1] = {0: "G0"}, {0: False}, "A"
+    specs[2].predecessors, specs[2].inversions, logics[2] = {4: "G4"}, {4: False}, "A"
+    specs[3].predecessors, specs[3].inversions, logics[3] = {2: "G2"}, {2: False}, "A"
+    specs[4].predecessors, specs[4].inversions, logics[4] = {3: "G3"}, {3: True}, "not A"
+    for s, lg in zip(specs, logics):
+        s.logic = lg
+    golden_sweep(ns, "mixed", specs, synth.planes_to_dense(planes, 48), 41)
+
+    # trajectories
+    specs, planes = synth.synthetic_dataset(12, 30, 51, flip=0.3, relax_steps=0)
+    golden_traj(ns, "rand", specs, synth.planes_to_dense(planes, 30), [0, 3, 7, 29])
+    specs = ring_network(7, True)
+    golden_traj(ns, "twist7", specs, (rng.random((7, 6)) < 0.5).astype(np.uint8), [0, 1, 5])
+
+
+if __name__ == "__main__":
+    main()

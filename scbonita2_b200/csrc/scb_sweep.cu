@@ -1,0 +1,463 @@
+// Knock-out / knock-in importance sweep and per-cell trajectories.
+//
+// Replaces CalculateImportanceScore (importance_scores.py:47-143,195-340) and
+// attractor_analysis.vectorized_run_simulation (attractor_analysis.py:43-99).
+//
+// Representation: bit-sliced.  One 32-bit word holds one node's state for 32 cells, so one
+// truth-table evaluation (7 LOP3) updates a node for 32 cells.  A CTA owns SLOTS words
+// ("slots"); the network state of a slot is N words in shared memory.  Thread (slot, part)
+// updates the part-th slice of the nodes for its slot; lanes of a warp are consecutive slots,
+// so every shared-memory access is bank-conflict free and every per-node constant (parent
+// rows, truth table) is warp-uniform.
+//
+// Exact first-repeat semantics with O(1) state copies (no history):
+//   phase 1  forward simulation.  lambda (cycle length) per cell: 1 if state_t == state_{t-1},
+//            otherwise Brent's scheme - compare with a checkpoint taken at t = 2^k - 1.  All
+//            per-cell integers (lambda) are kept bit-sliced too (6 bit-planes per slot).
+//   phase 2  (only if some cell in the CTA cycles with lambda > 1) restart twice from the data:
+//            P runs lambda_cell steps ahead of Q (per-cell stall masks); the first j with
+//            P == Q is mu, the first-repeat pair is (mu, mu+lambda), valid iff mu+lambda < steps
+//            (find_attractors, importance_scores.py:134-143); Q freezes at state_mu.
+//   scoring  cells frozen at their own state_mu are released together and stepped in lock-step
+//            with the stored normal-run states state_{mu_n + t}; XOR popcounts are accumulated
+//            for t <= min(lambda_x, lambda_n) (align_attractors, importance_scores.py:325-340).
+// The normal run is analysed first (MODE_NORMAL) and leaves found/lambda planes and the
+// aligned states in scratch; KO and KI of one node share a CTA (slots [0,SLOTS/2) = KO,
+// [SLOTS/2,SLOTS) = KI of the same words) because a cell only counts if BOTH repeat
+// (importance_scores.py:278).
+#include "scb_common.cuh"
+
+namespace scb {
+
+constexpr int kLamPlanes = 6;  // lambda < steps <= 64
+constexpr int kSweepThreads = 512;
+
+struct __align__(16) NodeEntry {
+    int pa, pb, pc;
+    uint32_t lut;
+};
+
+// bit-sliced "value > c" / "value >= c" for a per-lane integer held in kLamPlanes planes
+__device__ __forceinline__ uint32_t planes_gt(const uint32_t (&v)[kLamPlanes], int c) {
+    uint32_t gt = 0, eq = 0xFFFFFFFFu;
+#pragma unroll
+    for (int b = kLamPlanes - 1; b >= 0; --b) {
+        uint32_t cb = ((c >> b) & 1) ? 0xFFFFFFFFu : 0u;
+        gt |= eq & v[b] & ~cb;
+        eq &= ~(v[b] ^ cb);
+    }
+    return gt;
+}
+__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&v)[kLamPlanes], int c) {
+    return c <= 0 ? 0xFFFFFFFFu : planes_gt(v, c - 1);
+}
+__device__ __forceinline__ void planes_set(uint32_t (&v)[kLamPlanes], uint32_t lanes, int value) {
+#pragma unroll
+    for (int b = 0; b < kLamPlanes; ++b)
+        if ((value >> b) & 1) v[b] |= lanes;
+}
+
+// fold unused parent slots (-1 reads constant 0) into the table and alias them to row 0
+__device__ __forceinline__ NodeEntry make_entry(const int32_t* __restrict__ net_parent,
+                                                const uint8_t* __restrict__ net_lut, int n) {
+    NodeEntry e;
+    uint32_t lut = net_lut[n];
+    int pa = net_parent[3 * n], pb = net_parent[3 * n + 1], pc = net_parent[3 * n + 2];
+    if (pa < 0) { lut = (lut & 0x0Fu) | ((lut & 0x0Fu) << 4); pa = 0; }
+    if (pb < 0) { lut = (lut & 0x33u) | ((lut & 0x33u) << 2); pb = 0; }
+    if (pc < 0) { lut = (lut & 0x55u) | ((lut & 0x55u) << 1); pc = 0; }
+    e.pa = pa; e.pb = pb; e.pc = pc; e.lut = lut;
+    return e;
+}
+
+template <int SLOTS>
+__device__ __forceinline__ uint32_t eval_node(const NodeEntry& e, const uint32_t* __restrict__ st,
+                                              int slot) {
+    LutMasks m = expand_lut(e.lut);
+    return eval_lut(m, st[e.pa * SLOTS + slot], st[e.pb * SLOTS + slot], st[e.pc * SLOTS + slot]);
+}
+
+enum { MODE_NORMAL = 0, MODE_KOKI = 1 };
+
+template <int SLOTS, int MODE>
+__global__ void __launch_bounds__(kSweepThreads)
+sweep_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wpad, int64_t n_cells,
+             const int32_t* __restrict__ net_parent, const uint8_t* __restrict__ net_lut, int steps,
+             uint32_t* __restrict__ np_states /*[steps][N][wpad]*/,
+             uint32_t* __restrict__ np_lam /*[6][wpad]*/, uint32_t* __restrict__ np_found /*[wpad]*/,
+             unsigned long long* __restrict__ out_raw, unsigned long long* __restrict__ out_missing,
+             unsigned long long* __restrict__ out_keyerror) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int N = n_nodes;
+    const int S = blockDim.x / SLOTS;
+    uint32_t* buf0 = smem;
+    uint32_t* buf1 = buf0 + (size_t)N * SLOTS;
+    uint32_t* buf2 = buf1 + (size_t)N * SLOTS;
+    uint32_t* buf3 = buf2 + (size_t)N * SLOTS;
+    NodeEntry* tab = reinterpret_cast<NodeEntry*>(buf3 + (size_t)N * SLOTS);
+    uint32_t* partials = reinterpret_cast<uint32_t*>(tab + N);  // [2][2][S][SLOTS]
+    uint32_t* xchg = partials + 2 * 2 * S * SLOTS;              // [SLOTS]
+
+    const int tid = threadIdx.x;
+    const int slot = tid % SLOTS;
+    const int part = tid / SLOTS;
+    const int chunk = (N + S - 1) / S;
+    const int n_lo = min(N, part * chunk);
+    const int n_hi = min(N, n_lo + chunk);
+
+    // which word / condition this slot simulates
+    constexpr int HALF = SLOTS / 2;
+    int64_t word;
+    int forced_node = -1;
+    uint32_t forced_value = 0;
+    if (MODE == MODE_NORMAL) {
+        word = (int64_t)blockIdx.x * SLOTS + slot;
+    } else {
+        word = (int64_t)blockIdx.x * HALF + (slot % HALF);
+        forced_node = blockIdx.y;
+        forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
+    }
+    const bool word_ok = word < wpad;
+    const uint32_t cellmask = word_ok ? tail_mask(word, n_cells) : 0u;
+
+    for (int n = tid; n < N; n += blockDim.x) tab[n] = make_entry(net_parent, net_lut, n);
+
+    auto load_data = [&](uint32_t* dst) {
+        for (int n = n_lo; n < n_hi; ++n)
+            dst[n * SLOTS + slot] = word_ok ? __ldg(planes + (size_t)n * wpad + word) : 0u;
+    };
+    auto combine = [&](const uint32_t* p) {  // OR of the S partial words of my slot
+        uint32_t v = 0;
+        for (int s = 0; s < S; ++s) v |= p[s * SLOTS + slot];
+        return v;
+    };
+    auto step_node = [&](const uint32_t* st, int n) {
+        uint32_t f = eval_node<SLOTS>(tab[n], st, slot);
+        if (MODE == MODE_KOKI && n == forced_node) f = forced_value;
+        return f;
+    };
+
+    // ------------------------------------------------------------------ phase 1: lambda
+    uint32_t* cur = buf0;
+    uint32_t* nxt = buf1;
+    uint32_t* chk = buf2;
+    load_data(cur);
+    __syncthreads();
+
+    uint32_t resolved = ~cellmask;  // lanes whose lambda is settled (padding counts as settled)
+    uint32_t found_fp = 0;          // fixed point first seen at history index <= steps-1
+    uint32_t cyc = 0;               // lanes with a Brent-detected cycle (lambda >= 2)
+    uint32_t lam[kLamPlanes];
+#pragma unroll
+    for (int b = 0; b < kLamPlanes; ++b) lam[b] = 0;
+    int chk_time = -1;
+    int t_need = 1;
+    while (t_need - 1 < steps - 2) t_need <<= 1;  // smallest 2^k - 1 >= steps - 2
+    const int t1_max = (t_need - 1) + steps;
+
+    for (int t = 0; t < t1_max; ++t) {
+        uint32_t neq_prev = 0, neq_chk = 0;
+#pragma unroll 2
+        for (int n = n_lo; n < n_hi; ++n) {
+            uint32_t f = step_node(cur, n);
+            neq_prev |= f ^ cur[n * SLOTS + slot];
+            if (chk_time >= 0) neq_chk |= f ^ chk[n * SLOTS + slot];
+            nxt[n * SLOTS + slot] = f;
+        }
+        uint32_t* pp = partials + (size_t)(t & 1) * 2 * S * SLOTS;
+        pp[part * SLOTS + slot] = neq_prev;
+        pp[(S + part) * SLOTS + slot] = neq_chk;
+        __syncthreads();
+        neq_prev = combine(pp);
+        neq_chk = combine(pp + S * SLOTS);
+        if (t >= 1) {  // the raw data state is never compared (importance_scores.py:60-105)
+            uint32_t newly = ~neq_prev & ~resolved;
+            lam[0] |= newly;  // lambda = 1
+            resolved |= newly;
+            if (t <= steps - 1) found_fp |= newly;
+        }
+        if (chk_time >= 0) {
+            uint32_t newly = ~neq_chk & ~resolved;
+            int l = t - chk_time;
+            if (l <= steps - 1) {
+                planes_set(lam, newly, l);
+                cyc |= newly;
+            }
+            resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
+        }
+        if (((t + 1) & t) == 0) {  // t = 2^k - 1: new checkpoint = state_t (own nodes only)
+            for (int n = n_lo; n < n_hi; ++n) chk[n * SLOTS + slot] = nxt[n * SLOTS + slot];
+            chk_time = t;
+        }
+        uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+        if (__syncthreads_and(resolved == 0xFFFFFFFFu)) break;
+    }
+
+    // ------------------------------------------------------------------ phase 2: mu, freeze
+    uint32_t found;
+    uint32_t* xs;  // state frozen at state_mu for found lanes
+    uint32_t* xn;  // its scratch partner
+    if (__syncthreads_or(cyc != 0)) {
+        uint32_t* pc_ = buf0; uint32_t* pn_ = buf1;  // P: runs lambda ahead
+        uint32_t* qc_ = buf2; uint32_t* qn_ = buf3;  // Q: freezes at state_mu
+        load_data(pc_);
+        load_data(qc_);
+        __syncthreads();
+        const uint32_t has_lam = planes_ge(lam, 1) & cellmask;
+        for (int s = 0; s < steps; ++s) {
+            uint32_t adv = planes_gt(lam, s) & has_lam;  // lanes that still owe P a step
+            if (!__syncthreads_or(adv != 0)) break;
+#pragma unroll 2
+            for (int n = n_lo; n < n_hi; ++n) {
+                uint32_t f = step_node(pc_, n);
+                uint32_t old = pc_[n * SLOTS + slot];
+                pn_[n * SLOTS + slot] = (f & adv) | (old & ~adv);
+            }
+            __syncthreads();
+            uint32_t* tmp = pc_; pc_ = pn_; pn_ = tmp;
+        }
+        uint32_t done = ~has_lam;
+        found = 0;
+        for (int j = 0; j <= steps - 2; ++j) {
+            uint32_t neq = 0;
+#pragma unroll 2
+            for (int n = n_lo; n < n_hi; ++n) {
+                uint32_t fp = step_node(pc_, n);
+                uint32_t fq = step_node(qc_, n);
+                uint32_t oldq = qc_[n * SLOTS + slot];
+                neq |= fp ^ fq;
+                pn_[n * SLOTS + slot] = fp;
+                qn_[n * SLOTS + slot] = (oldq & done) | (fq & ~done);
+            }
+            uint32_t* pp = partials + (size_t)(j & 1) * 2 * S * SLOTS;
+            pp[part * SLOTS + slot] = neq;
+            __syncthreads();
+            neq = combine(pp);
+            uint32_t newly = ~neq & ~done;
+            // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
+            uint32_t eligible = ~planes_gt(lam, steps - 1 - j);
+            found |= newly & eligible;
+            done |= newly;
+            uint32_t* tmp = pc_; pc_ = pn_; pn_ = tmp;
+            tmp = qc_; qc_ = qn_; qn_ = tmp;
+            if (__syncthreads_and(done == 0xFFFFFFFFu)) break;
+        }
+        xs = qc_;
+        xn = qn_;
+    } else {
+        found = found_fp;  // every settled lane sits on its fixed point already
+        xs = cur;
+        xn = nxt;
+    }
+    found &= cellmask;
+
+    // ------------------------------------------------------------------ outputs
+    if (MODE == MODE_NORMAL) {
+        if (part == 0 && word_ok) {
+            np_found[word] = found;
+#pragma unroll
+            for (int b = 0; b < kLamPlanes; ++b) np_lam[(size_t)b * wpad + word] = lam[b];
+            uint32_t miss = __popc(~found & cellmask);
+            if (miss) atomicAdd(out_missing, (unsigned long long)miss);
+        }
+        for (int t = 0; t < steps; ++t) {
+            uint32_t need = found & planes_ge(lam, t);
+            if (!__syncthreads_or(need != 0)) break;
+            if (word_ok)
+                for (int n = n_lo; n < n_hi; ++n)
+                    np_states[((size_t)t * N + n) * wpad + word] = xs[n * SLOTS + slot];
+            uint32_t need_next = found & planes_ge(lam, t + 1);
+            if (!__syncthreads_or(need_next != 0)) break;
+#pragma unroll 2
+            for (int n = n_lo; n < n_hi; ++n) xn[n * SLOTS + slot] = step_node(xs, n);
+            __syncthreads();
+            uint32_t* tmp = xs; xs = xn; xn = tmp;
+        }
+        return;
+    }
+
+    // MODE_KOKI: a cell counts only if its KO run AND its KI run repeat (and the normal one)
+    if (part == 0) xchg[slot] = found;
+    __syncthreads();
+    const uint32_t partner = xchg[(slot + HALF) % SLOTS];
+    const uint32_t found_n = word_ok ? __ldg(np_found + word) : 0u;
+    uint32_t lamn[kLamPlanes];
+#pragma unroll
+    for (int b = 0; b < kLamPlanes; ++b) lamn[b] = word_ok ? __ldg(np_lam + (size_t)b * wpad + word) : 0u;
+    const uint32_t valid = found & partner & found_n;
+    if (part == 0) {
+        uint32_t miss = __popc(~found & cellmask);
+        if (miss) atomicAdd(out_missing + 1 + 2 * forced_node + (slot >= HALF ? 1 : 0), (unsigned long long)miss);
+        if (slot < HALF) {
+            uint32_t bad = __popc(found & partner & ~found_n);
+            if (bad) atomicAdd(out_keyerror, (unsigned long long)bad);
+        }
+    }
+    unsigned long long score = 0;
+    for (int t = 0; t < steps; ++t) {
+        uint32_t act = valid & planes_ge(lam, t) & planes_ge(lamn, t);
+        if (!__syncthreads_or(act != 0)) break;
+        if (act) {
+            uint32_t s = 0;
+            for (int n = n_lo; n < n_hi; ++n) {
+                uint32_t ref = __ldg(np_states + ((size_t)t * N + n) * wpad + word);
+                s += __popc((xs[n * SLOTS + slot] ^ ref) & act);
+            }
+            score += s;
+        }
+        if (t == 0 && !__syncthreads_or((valid & (planes_ge(lam, 2) | planes_ge(lamn, 2))) != 0)) {
+            score *= 2;  // every counted cell: fixed point vs fixed point, t = 1 repeats t = 0
+            break;
+        }
+        uint32_t act_next = valid & planes_ge(lam, t + 1) & planes_ge(lamn, t + 1);
+        if (!__syncthreads_or(act_next != 0)) break;
+#pragma unroll 2
+        for (int n = n_lo; n < n_hi; ++n) xn[n * SLOTS + slot] = step_node(xs, n);
+        __syncthreads();
+        uint32_t* tmp = xs; xs = xn; xn = tmp;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
+    if ((tid & 31) == 0 && score) atomicAdd(out_raw + forced_node, score);
+}
+
+// ---------------------------------------------------------------------------------------
+// trajectories: slot word = 32 selected cells; out[m][n][t] bytes
+// ---------------------------------------------------------------------------------------
+constexpr int kTrajSlots = 32;
+
+__global__ void __launch_bounds__(256)
+trajectories_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wpad,
+                    const int64_t* __restrict__ cell_idx, int64_t n_selected,
+                    const int32_t* __restrict__ net_parent, const uint8_t* __restrict__ net_lut,
+                    int steps, uint8_t* __restrict__ out) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int N = n_nodes;
+    const int S = blockDim.x / kTrajSlots;
+    uint32_t* cur = smem;
+    uint32_t* nxt = cur + (size_t)N * kTrajSlots;
+    NodeEntry* tab = reinterpret_cast<NodeEntry*>(nxt + (size_t)N * kTrajSlots);
+    const int tid = threadIdx.x;
+    const int slot = tid % kTrajSlots;
+    const int part = tid / kTrajSlots;
+    const int chunk = (N + S - 1) / S;
+    const int n_lo = min(N, part * chunk), n_hi = min(N, n_lo + chunk);
+    const int64_t first = ((int64_t)blockIdx.x * kTrajSlots + slot) * 32;  // first selected cell of my slot
+
+    for (int n = tid; n < N; n += blockDim.x) tab[n] = make_entry(net_parent, net_lut, n);
+    for (int n = n_lo; n < n_hi; ++n) {
+        uint32_t w = 0;
+        const uint32_t* row = planes + (size_t)n * wpad;
+        for (int b = 0; b < 32; ++b) {
+            int64_t m = first + b;
+            if (m < n_selected) {
+                int64_t c = __ldg(cell_idx + m);
+                w |= ((__ldg(row + (c >> 5)) >> (c & 31)) & 1u) << b;
+            }
+        }
+        cur[n * kTrajSlots + slot] = w;
+    }
+    __syncthreads();
+    for (int t = 0; t < steps; ++t) {
+        for (int n = n_lo; n < n_hi; ++n) {
+            uint32_t f = eval_node<kTrajSlots>(tab[n], cur, slot);
+            nxt[n * kTrajSlots + slot] = f;
+            for (int b = 0; b < 32; ++b) {
+                int64_t m = first + b;
+                if (m < n_selected) out[((size_t)m * N + n) * steps + t] = (f >> b) & 1u;
+            }
+        }
+        __syncthreads();
+        uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+    }
+}
+
+static size_t sweep_smem_bytes(int n_nodes, int slots) {
+    int S = kSweepThreads / slots;
+    return (size_t)4 * n_nodes * slots * 4 + (size_t)n_nodes * sizeof(NodeEntry) +
+           (size_t)2 * 2 * S * slots * 4 + (size_t)slots * 4;
+}
+
+constexpr size_t kMaxDynSmem = 232448;  // 227 KB
+
+template <int SLOTS>
+static int launch_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
+                        const int32_t* net_parent, const uint8_t* net_lut, int steps,
+                        uint32_t* np_states, uint32_t* np_lam, uint32_t* np_found,
+                        unsigned long long* out_raw, unsigned long long* out_missing,
+                        unsigned long long* out_keyerror, cudaStream_t stream) {
+    size_t smem = sweep_smem_bytes(n_nodes, SLOTS);
+    int64_t n_words = (n_cells + 31) / 32;
+    SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_KOKI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid_n((unsigned)((n_words + SLOTS - 1) / SLOTS));
+    sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(
+        planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found,
+        out_raw, out_missing, out_keyerror);
+    SCB_LAUNCH_CHECK("sweep_kernel<normal>");
+    constexpr int HALF = SLOTS / 2;
+    dim3 grid_k((unsigned)((n_words + HALF - 1) / HALF), (unsigned)n_nodes);
+    sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(
+        planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found,
+        out_raw, out_missing, out_keyerror);
+    SCB_LAUNCH_CHECK("sweep_kernel<koki>");
+    return SCB_OK;
+}
+
+}  // namespace scb
+
+using namespace scb;
+
+extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int steps) {
+    if (n_nodes <= 0 || wpad <= 0 || steps <= 0) return 0;
+    return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4;
+}
+
+extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
+                               const int32_t* net_parent, const uint8_t* net_lut, int steps,
+                               void* scratch, int64_t scratch_bytes, int64_t* out_raw,
+                               int64_t* out_missing, int64_t* out_keyerror, scb_stream_t stream) {
+    SCB_REQUIRE(n_nodes > 0 && n_nodes <= 65535, "ko_ki_sweep: n_nodes=%d out of range", n_nodes);
+    SCB_REQUIRE(steps >= 2 && steps <= 64, "ko_ki_sweep: steps=%d must be in [2, 64]", steps);
+    SCB_REQUIRE(wpad > 0 && wpad % 4 == 0 && n_cells >= 0 && wpad * 32 >= n_cells, "ko_ki_sweep: wpad must be a positive multiple of 4 covering n_cells");
+    SCB_REQUIRE(planes && net_parent && net_lut && scratch && out_raw && out_missing && out_keyerror, "ko_ki_sweep: null pointer");
+    if (n_cells == 0) return SCB_OK;
+    int64_t need = scb_ko_ki_sweep_scratch_bytes(n_nodes, wpad, steps);
+    if (scratch_bytes < need) {
+        set_error("ko_ki_sweep: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
+        return SCB_ERR_SCRATCH;
+    }
+    uint32_t* np_states = static_cast<uint32_t*>(scratch);
+    uint32_t* np_lam = np_states + (size_t)steps * n_nodes * wpad;
+    uint32_t* np_found = np_lam + (size_t)kLamPlanes * wpad;
+    auto raw = reinterpret_cast<unsigned long long*>(out_raw);
+    auto missing = reinterpret_cast<unsigned long long*>(out_missing);
+    auto keyerr = reinterpret_cast<unsigned long long*>(out_keyerror);
+    if (sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem)
+        return launch_sweep<64>(planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found, raw, missing, keyerr, as_stream(stream));
+    if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem)
+        return launch_sweep<32>(planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found, raw, missing, keyerr, as_stream(stream));
+    set_error("ko_ki_sweep: %d nodes exceed the shared-memory resident limit (%d)", n_nodes, SCB_MAX_SWEEP_NODES);
+    return SCB_ERR_UNSUPPORTED;
+}
+
+extern "C" int scb_trajectories(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
+                                const int64_t* cell_idx, int64_t n_selected,
+                                const int32_t* net_parent, const uint8_t* net_lut, int steps,
+                                uint8_t* out, scb_stream_t stream) {
+    SCB_REQUIRE(n_nodes > 0 && steps >= 1 && n_selected >= 0, "trajectories: bad size");
+    SCB_REQUIRE(wpad > 0 && wpad * 32 >= n_cells, "trajectories: wpad does not cover n_cells");
+    if (n_selected == 0) return SCB_OK;
+    SCB_REQUIRE(planes && cell_idx && net_parent && net_lut && out, "trajectories: null pointer");
+    size_t smem = (size_t)2 * n_nodes * kTrajSlots * 4 + (size_t)n_nodes * sizeof(NodeEntry);
+    if (smem > kMaxDynSmem) {
+        set_error("trajectories: %d nodes exceed the shared-memory resident limit", n_nodes);
+        return SCB_ERR_UNSUPPORTED;
+    }
+    SCB_CUDA(cudaFuncSetAttribute(trajectories_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t slots = (n_selected + 31) / 32;
+    trajectories_kernel<<<(unsigned)((slots + kTrajSlots - 1) / kTrajSlots), 256, smem, as_stream(stream)>>>(
+        planes, n_nodes, wpad, cell_idx, n_selected, net_parent, net_lut, steps, out);
+    SCB_LAUNCH_CHECK("trajectories_kernel");
+    return SCB_OK;
+}

@@ -1,0 +1,357 @@
+"""Device-side plumbing: cell bitplanes in HBM and thin typed wrappers over the C-ABI.
+
+PyTorch is used for device memory, streams and (in ``distributed.py``) NCCL only; every
+computation below is a call into ``libscbonita_b200.so``.  Tensors handed to the library are
+``torch.int32`` (bitplane words — torch has no uint32 arithmetic and none is needed),
+``torch.int64`` (counts) or ``torch.uint8`` (truth tables).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("scbonita2_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def _stream():
+    return _torch().cuda.current_stream().cuda_stream
+
+
+def padded_words(n_cells: int) -> int:
+    """Words per bitplane row: ceil(n_cells/32) rounded up to a multiple of 4 (>= 4)."""
+    return max(4, (((n_cells + 31) // 32) + 3) // 4 * 4)
+
+
+def _dev(array, dtype, device=None):
+    torch = _torch()
+    if isinstance(array, torch.Tensor):
+        return array.to(device=device or "cuda", dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(array), dtype=dtype).to(device or "cuda")
+
+
+class BitPlanes:
+    """uint32 cell bitplanes ``[n_rows][wpad]`` resident on one GPU.
+
+    Row r is the gene with ``Node.index == r``; bit b of word w is cell ``32*w + b``; bits at
+    and beyond ``n_cells`` are zero.
+    """
+
+    def __init__(self, words, n_rows: int, n_cells: int):
+        self.words = words            # torch.int32 [n_rows, wpad], cuda
+        self.n_rows = int(n_rows)
+        self.n_cells = int(n_cells)
+        self.wpad = int(words.shape[1])
+
+    # ---- constructors ---------------------------------------------------------------
+    @classmethod
+    def from_dense(cls, matrix, device=None) -> "BitPlanes":
+        """From a (rows x cells) 0/1 matrix: NumPy array or scipy sparse (any dtype)."""
+        torch = _torch()
+        if hasattr(matrix, "toarray"):
+            matrix = matrix.toarray()
+        dense = np.ascontiguousarray(np.asarray(matrix) != 0, dtype=np.uint8)
+        if dense.ndim != 2:
+            raise ValueError("expected a 2-D (genes x cells) matrix")
+        n_rows, n_cells = dense.shape
+        wpad = padded_words(n_cells)
+        d_dense = torch.from_numpy(dense).to(device or "cuda")
+        words = torch.empty((n_rows, wpad), dtype=torch.int32, device=d_dense.device)
+        with torch.cuda.device(d_dense.device):
+            _lib.check(_lib.lib().scb_pack_bitplanes(
+                d_dense.data_ptr(), n_rows, n_cells, n_cells, words.data_ptr(), wpad, _stream()),
+                "scb_pack_bitplanes")
+        return cls(words, n_rows, n_cells)
+
+    @classmethod
+    def from_packed(cls, packed: np.ndarray, n_cells: int, device=None) -> "BitPlanes":
+        """From host uint32 words ``[n_rows][>= ceil(n_cells/32)]`` (tail bits must be zero)."""
+        torch = _torch()
+        packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        n_rows, have = packed.shape
+        n_words = (n_cells + 31) // 32
+        if have < n_words:
+            raise ValueError("packed rows are shorter than ceil(n_cells/32) words")
+        wpad = padded_words(n_cells)
+        host = np.zeros((n_rows, wpad), dtype=np.uint32)
+        host[:, :n_words] = packed[:, :n_words]
+        words = torch.from_numpy(host.view(np.int32)).to(device or "cuda")
+        return cls(words, n_rows, n_cells)
+
+    # ---- views ----------------------------------------------------------------------
+    def to_dense(self) -> np.ndarray:
+        torch = _torch()
+        out = torch.empty((self.n_rows, self.n_cells), dtype=torch.uint8, device=self.words.device)
+        with torch.cuda.device(self.words.device):
+            _lib.check(_lib.lib().scb_unpack_bitplanes(
+                self.words.data_ptr(), self.n_rows, self.n_cells, self.wpad, out.data_ptr(),
+                self.n_cells, _stream()), "scb_unpack_bitplanes")
+        return out.cpu().numpy()
+
+    def to_packed(self) -> np.ndarray:
+        n_words = (self.n_cells + 31) // 32
+        return self.words.cpu().numpy().view(np.uint32)[:, :n_words].copy()
+
+    def word_slice(self, w0: int, w1: int) -> "BitPlanes":
+        """Cells [32*w0, 32*w1) as an independent BitPlanes (used for cell sharding)."""
+        torch = _torch()
+        w1 = min(w1, (self.n_cells + 31) // 32)
+        n_cells = max(0, min(self.n_cells, 32 * w1) - 32 * w0)
+        wpad = padded_words(n_cells)
+        words = torch.zeros((self.n_rows, wpad), dtype=torch.int32, device=self.words.device)
+        if w1 > w0:
+            words[:, :w1 - w0] = self.words[:, w0:w1]
+        return BitPlanes(words, self.n_rows, n_cells)
+
+    # ---- chunking -------------------------------------------------------------------
+    def chunk_majority(self, perm: np.ndarray, n_chunks: int, chunk_size: int,
+                       min_ones: int) -> "BitPlanes":
+        torch = _torch()
+        d_perm = _dev(np.asarray(perm[:n_chunks * chunk_size], dtype=np.int32), torch.int32,
+                      self.words.device)
+        wout = padded_words(n_chunks)
+        out = torch.empty((self.n_rows, wout), dtype=torch.int32, device=self.words.device)
+        with torch.cuda.device(self.words.device):
+            _lib.check(_lib.lib().scb_chunk_majority(
+                self.words.data_ptr(), self.n_rows, self.wpad, d_perm.data_ptr(), n_chunks,
+                chunk_size, min_ones, out.data_ptr(), wout, _stream()), "scb_chunk_majority")
+        return BitPlanes(out, self.n_rows, n_chunks)
+
+
+# --------------------------------------------------------------------------------------
+def rule_counts(planes: BitPlanes, target_row, parent_row):
+    """int64 ``[G, 16]`` joint counts (device tensor) for G (target, <=3 parents) groups."""
+    torch = _torch()
+    dev = planes.words.device
+    target = _dev(np.asarray(target_row, dtype=np.int32).reshape(-1), torch.int32, dev)
+    parents = _dev(np.asarray(parent_row, dtype=np.int32).reshape(-1, 3), torch.int32, dev)
+    n_groups = int(target.numel())
+    if parents.shape[0] != n_groups:
+        raise ValueError("parent_row must be [G, 3]")
+    if n_groups:
+        lo = int(min(target.min().item(), 0))
+        hi = int(max(target.max().item(), parents.max().item()))
+        if lo < 0 or hi >= planes.n_rows or int(parents.min().item()) < -1:
+            raise IndexError("rule_counts: row index out of range")
+    counts = torch.empty((n_groups, 16), dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = L.scb_rule_counts_scratch_bytes(planes.n_rows, n_groups)
+        scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+        _lib.check(L.scb_rule_counts(planes.words.data_ptr(), planes.n_rows, planes.wpad,
+                                     planes.n_cells, n_groups, target.data_ptr(),
+                                     parents.data_ptr(), scratch.data_ptr(), int(nbytes),
+                                     counts.data_ptr(), _stream()), "scb_rule_counts")
+    return counts
+
+
+def rule_error_table(counts, task_group, task_lut):
+    """int64 ``[T]`` mismatch counts (device tensor) of T (group, truth table) tasks."""
+    torch = _torch()
+    dev = counts.device
+    group = _dev(np.asarray(task_group, dtype=np.int32).reshape(-1), torch.int32, dev)
+    lut = _dev(np.asarray(task_lut, dtype=np.uint8).reshape(-1), torch.uint8, dev)
+    n_tasks = int(group.numel())
+    if lut.numel() != n_tasks:
+        raise ValueError("task_group and task_lut differ in length")
+    if n_tasks and (int(group.min().item()) < 0 or int(group.max().item()) >= counts.shape[0]):
+        raise IndexError("rule_error_table: group index out of range")
+    out = torch.empty(n_tasks, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().scb_rule_error_table(counts.data_ptr(), int(counts.shape[0]), n_tasks,
+                                                   group.data_ptr(), lut.data_ptr(),
+                                                   out.data_ptr(), _stream()),
+                   "scb_rule_error_table")
+    return out
+
+
+def rule_error_table_direct(planes: BitPlanes, target_row, parent_row, lut):
+    torch = _torch()
+    dev = planes.words.device
+    target = _dev(np.asarray(target_row, dtype=np.int32).reshape(-1), torch.int32, dev)
+    parents = _dev(np.asarray(parent_row, dtype=np.int32).reshape(-1, 3), torch.int32, dev)
+    d_lut = _dev(np.asarray(lut, dtype=np.uint8).reshape(-1), torch.uint8, dev)
+    n_tasks = int(target.numel())
+    out = torch.empty(n_tasks, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().scb_rule_error_table_direct(
+            planes.words.data_ptr(), planes.n_rows, planes.wpad, planes.n_cells, n_tasks,
+            target.data_ptr(), parents.data_ptr(), d_lut.data_ptr(), out.data_ptr(), _stream()),
+            "scb_rule_error_table_direct")
+    return out
+
+
+def population_fitness(counts, lut, active=None, per_node: bool = False):
+    """(diff[P], diff_pg[P, G] | None) device tensors for a population of truth-table rows."""
+    torch = _torch()
+    dev = counts.device
+    d_lut = lut if isinstance(lut, torch.Tensor) else _dev(np.asarray(lut, dtype=np.uint8), torch.uint8, dev)
+    d_lut = d_lut.to(device=dev, dtype=torch.uint8).contiguous()
+    n_ind, n_groups = int(d_lut.shape[0]), int(d_lut.shape[1])
+    if n_groups != counts.shape[0]:
+        raise ValueError("lut must be [P, G] with G == counts.shape[0]")
+    d_act = None
+    if active is not None:
+        d_act = _dev(active, torch.uint8, dev)
+        if tuple(d_act.shape) != (n_ind, n_groups):
+            raise ValueError("active must be [P, G]")
+    out = torch.empty(n_ind, dtype=torch.int64, device=dev)
+    out_pg = torch.empty((n_ind, n_groups), dtype=torch.int64, device=dev) if per_node else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().scb_population_fitness(
+            counts.data_ptr(), n_groups, n_ind, d_lut.data_ptr(),
+            d_act.data_ptr() if d_act is not None else None, out.data_ptr(),
+            out_pg.data_ptr() if out_pg is not None else None, _stream()),
+            "scb_population_fitness")
+    return out, out_pg
+
+
+def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=None):
+    """Run the 2N+1-condition sweep.  Returns device tensors (raw[N], missing[2N+1], keyerror[1]);
+    pass ``out`` (the same triple) to accumulate several cell shards into one result."""
+    torch = _torch()
+    dev = planes.words.device
+    n = planes.n_rows
+    parents = _dev(np.asarray(net_parent, dtype=np.int32).reshape(-1, 3), torch.int32, dev)
+    d_lut = _dev(np.asarray(net_lut, dtype=np.uint8).reshape(-1), torch.uint8, dev)
+    if parents.shape[0] != n or d_lut.numel() != n:
+        raise ValueError("the sweep needs one (parents, lut) entry per bitplane row")
+    if int(parents.min().item()) < -1 or int(parents.max().item()) >= n:
+        raise IndexError("ko_ki_sweep: parent row out of range")
+    if out is None:
+        out = (torch.zeros(n, dtype=torch.int64, device=dev),
+               torch.zeros(2 * n + 1, dtype=torch.int64, device=dev),
+               torch.zeros(1, dtype=torch.int64, device=dev))
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = int(L.scb_ko_ki_sweep_scratch_bytes(n, planes.wpad, steps))
+        scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        _lib.check(L.scb_ko_ki_sweep(planes.words.data_ptr(), n, planes.wpad, planes.n_cells,
+                                     parents.data_ptr(), d_lut.data_ptr(), steps,
+                                     scratch.data_ptr(), nbytes, out[0].data_ptr(),
+                                     out[1].data_ptr(), out[2].data_ptr(), _stream()),
+                   "scb_ko_ki_sweep")
+    return out
+
+
+def trajectories(planes: BitPlanes, cell_idx, net_parent, net_lut, steps: int = 20):
+    """uint8 ``[M, N, steps]`` device tensor of states after 1..steps updates."""
+    torch = _torch()
+    dev = planes.words.device
+    n = planes.n_rows
+    idx = _dev(np.asarray(cell_idx, dtype=np.int64).reshape(-1), torch.int64, dev)
+    if idx.numel() and (int(idx.min().item()) < 0 or int(idx.max().item()) >= planes.n_cells):
+        raise IndexError("trajectories: cell index out of range")
+    parents = _dev(np.asarray(net_parent, dtype=np.int32).reshape(-1, 3), torch.int32, dev)
+    d_lut = _dev(np.asarray(net_lut, dtype=np.uint8).reshape(-1), torch.uint8, dev)
+    out = torch.empty((int(idx.numel()), n, steps), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().scb_trajectories(planes.words.data_ptr(), n, planes.wpad,
+                                               planes.n_cells, idx.data_ptr(), int(idx.numel()),
+                                               parents.data_ptr(), d_lut.data_ptr(), steps,
+                                               out.data_ptr(), _stream()), "scb_trajectories")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+class HostWorkspace:
+    """The host-buffer ("end-to-end") entry points: NumPy in, NumPy out, no torch."""
+
+    def __init__(self):
+        import ctypes
+
+        self._ct = ctypes
+        self._L = _lib.lib()
+        handle = ctypes.c_void_p()
+        _lib.check(self._L.scb_workspace_create(ctypes.byref(handle)), "scb_workspace_create")
+        self._h = handle
+        self.n_rows = 0
+        self.n_groups = 0
+
+    def close(self):
+        if self._h is not None:
+            self._L.scb_workspace_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ptr(self, arr, ctype):
+        return arr.ctypes.data_as(self._ct.POINTER(ctype))
+
+    def load_dense(self, dense01: np.ndarray):
+        ct = self._ct
+        dense01 = np.ascontiguousarray(dense01, dtype=np.uint8)
+        _lib.check(self._L.scb_host_load_dense(self._h, self._ptr(dense01, ct.c_uint8),
+                                               dense01.shape[0], dense01.shape[1]),
+                   "scb_host_load_dense")
+        self.n_rows = dense01.shape[0]
+
+    def load_planes(self, packed: np.ndarray, n_cells: int):
+        ct = self._ct
+        n_words = (n_cells + 31) // 32
+        packed = np.ascontiguousarray(packed[:, :n_words], dtype=np.uint32)
+        _lib.check(self._L.scb_host_load_planes(self._h, self._ptr(packed, ct.c_uint32),
+                                                packed.shape[0], n_cells), "scb_host_load_planes")
+        self.n_rows = packed.shape[0]
+
+    def rule_counts(self, target_row, parent_row, want: bool = True):
+        ct = self._ct
+        target = np.ascontiguousarray(target_row, dtype=np.int32).reshape(-1)
+        parents = np.ascontiguousarray(parent_row, dtype=np.int32).reshape(-1, 3)
+        out = np.empty((target.size, 16), dtype=np.int64) if want else None
+        _lib.check(self._L.scb_host_rule_counts(
+            self._h, target.size, self._ptr(target, ct.c_int32), self._ptr(parents, ct.c_int32),
+            self._ptr(out, ct.c_int64) if want else None), "scb_host_rule_counts")
+        self.n_groups = target.size
+        return out
+
+    def rule_error_table(self, task_group, task_lut):
+        ct = self._ct
+        group = np.ascontiguousarray(task_group, dtype=np.int32).reshape(-1)
+        lut = np.ascontiguousarray(task_lut, dtype=np.uint8).reshape(-1)
+        out = np.empty(group.size, dtype=np.int64)
+        _lib.check(self._L.scb_host_rule_error_table(
+            self._h, group.size, self._ptr(group, ct.c_int32), self._ptr(lut, ct.c_uint8),
+            self._ptr(out, ct.c_int64)), "scb_host_rule_error_table")
+        return out
+
+    def population_fitness(self, lut, active=None, per_node: bool = False):
+        ct = self._ct
+        lut = np.ascontiguousarray(lut, dtype=np.uint8)
+        if lut.ndim != 2 or lut.shape[1] != self.n_groups:
+            raise ValueError("lut must be [P, G]")
+        act = np.ascontiguousarray(active, dtype=np.uint8) if active is not None else None
+        out = np.empty(lut.shape[0], dtype=np.int64)
+        out_pg = np.empty(lut.shape, dtype=np.int64) if per_node else None
+        _lib.check(self._L.scb_host_population_fitness(
+            self._h, lut.shape[0], self._ptr(lut, ct.c_uint8),
+            self._ptr(act, ct.c_uint8) if act is not None else None,
+            self._ptr(out, ct.c_int64), self._ptr(out_pg, ct.c_int64) if per_node else None),
+            "scb_host_population_fitness")
+        return out, out_pg
+
+    def ko_ki_sweep(self, net_parent, net_lut, steps: int = 50):
+        ct = self._ct
+        parents = np.ascontiguousarray(net_parent, dtype=np.int32).reshape(-1, 3)
+        lut = np.ascontiguousarray(net_lut, dtype=np.uint8).reshape(-1)
+        n = self.n_rows
+        if parents.shape[0] != n or lut.size != n:
+            raise ValueError("the sweep needs one (parents, lut) entry per matrix row")
+        raw = np.empty(n, dtype=np.int64)
+        missing = np.empty(2 * n + 1, dtype=np.int64)
+        keyerr = np.empty(1, dtype=np.int64)
+        _lib.check(self._L.scb_host_ko_ki_sweep(
+            self._h, self._ptr(parents, ct.c_int32), self._ptr(lut, ct.c_uint8), steps,
+            self._ptr(raw, ct.c_int64), self._ptr(missing, ct.c_int64),
+            self._ptr(keyerr, ct.c_int64)), "scb_host_ko_ki_sweep")
+        return raw, missing, keyerr

@@ -1,0 +1,76 @@
+"""CPU suite: rule compiler, C-ABI surface, and the no-oracle-in-product rule."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from scbonita2_b200 import _lib, rule_compiler
+from scbonita2_b200.node_class import Node
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def all_three_parent_candidates():
+    node = Node("X", 3, {0: "a", 1: "b", 2: "c"}, {0: False, 1: False, 2: False})
+    node.find_all_rule_predictions()
+    return [r[2] for r in rule_compiler.extend_with_not_variants(node)]
+
+
+def test_candidate_counts():
+    for k, n in ((1, 2), (2, 12), (3, 94)):
+        node = Node("X", 9, {i: f"p{i}" for i in range(k)}, {i: False for i in range(k)})
+        node.find_all_rule_predictions()
+        assert len(rule_compiler.extend_with_not_variants(node)) == n
+
+
+def test_94_candidates_have_94_distinct_tables():
+    cands = all_three_parent_candidates()
+    tables = [rule_compiler.compile_rule(c) for c in cands]
+    assert len(set(tables)) == 94
+    # spot values under the lop3 convention bit = (A<<2 | B<<1 | C)
+    assert rule_compiler.compile_rule("A") == 0xF0
+    assert rule_compiler.compile_rule("B") == 0xCC
+    assert rule_compiler.compile_rule("C") == 0xAA
+    assert rule_compiler.compile_rule("A and B or C") == (0xF0 & 0xCC) | 0xAA
+    assert rule_compiler.compile_rule("not A and (B or not C)") == (~0xF0 & (0xCC | ~0xAA)) & 0xFF
+
+
+def test_compile_rejects_bad_rules():
+    with pytest.raises(rule_compiler.RuleCompileError):
+        rule_compiler.compile_rule("A and D")
+    with pytest.raises(rule_compiler.RuleCompileError):
+        rule_compiler.compile_rule("A and and B")
+    with pytest.raises(rule_compiler.RuleCompileError):
+        rule_compiler.compile_for_slots("A or B", 1)
+
+
+def test_lut_support():
+    assert rule_compiler.lut_support(0xF0) == (True, False, False)
+    assert rule_compiler.lut_support(rule_compiler.compile_rule("B or C")) == (False, True, True)
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "scbonita_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(scb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert len(names) >= 20
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in include/ but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert _lib.lib().scb_abi_version() == 1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "scbonita2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "ref_port" not in text and "ref_loader" not in text, f
