@@ -1,0 +1,192 @@
+"""GPU parity: rule scoring (joint counts, error table, population fitness, inference)."""
+import logging
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_port
+from scbonita2_b200 import rule_compiler
+from tests.helpers import golden, golden_names, matrix_of, nodes_of, np_counts, np_diff
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _groups(specs):
+    targets = [s.index for s in specs]
+    parents = [synth.spec_parent_rows(s) for s in specs]
+    return targets, parents
+
+
+@pytest.mark.parametrize("n_nodes,n_cells,seed", [(1, 1, 0), (4, 31, 1), (5, 32, 2), (8, 33, 3),
+                                                  (12, 1000, 4), (59, 3621, 5), (30, 20011, 6),
+                                                  (200, 4099, 7)])
+def test_counts_match_numpy(cuda, n_nodes, n_cells, seed):
+    from scbonita2_b200 import device
+    specs, planes_np = synth.synthetic_dataset(n_nodes, n_cells, seed, flip=0.1)
+    dense = synth.planes_to_dense(planes_np, n_cells)
+    planes = device.BitPlanes.from_packed(planes_np, n_cells)
+    targets, parents = _groups(specs)
+    counts = device.rule_counts(planes, targets, parents).cpu().numpy()
+    for g in range(n_nodes):
+        assert (counts[g] == np_counts(dense, targets[g], parents[g])).all(), g
+        assert counts[g].sum() == n_cells
+
+
+def test_counts_degenerate_groups(cuda):
+    """Duplicate parents, parent == target, unused slots, more groups than rows."""
+    from scbonita2_b200 import device
+    rng = np.random.default_rng(3)
+    dense = (rng.random((5, 777)) < 0.4).astype(np.uint8)
+    planes = device.BitPlanes.from_dense(dense)
+    targets = [0, 1, 2, 3, 4, 0, 0, 2]
+    parents = [(0, 0, 0), (1, 2, -1), (-1, -1, -1), (4, -1, 4), (3, 3, 1), (1, 2, 3), (-1, 2, -1), (2, 2, 2)]
+    counts = device.rule_counts(planes, targets, parents).cpu().numpy()
+    for g, (t, p) in enumerate(zip(targets, parents)):
+        assert (counts[g] == np_counts(dense, t, p)).all(), g
+
+
+def test_many_groups_are_sliced(cuda):
+    from scbonita2_b200 import device
+    rng = np.random.default_rng(4)
+    dense = (rng.random((20, 2000)) < 0.3).astype(np.uint8)
+    planes = device.BitPlanes.from_dense(dense)
+    n_groups = 2500   # > 1024 groups per launch
+    targets = rng.integers(0, 20, n_groups)
+    parents = rng.integers(-1, 20, (n_groups, 3))
+    counts = device.rule_counts(planes, targets, parents).cpu().numpy()
+    for g in range(0, n_groups, 37):
+        assert (counts[g] == np_counts(dense, targets[g], parents[g])).all(), g
+
+
+def test_error_table_all_256_tables_and_direct_kernel(cuda):
+    from scbonita2_b200 import device
+    specs, planes_np = synth.synthetic_dataset(6, 1237, 11, flip=0.2)
+    dense = synth.planes_to_dense(planes_np, 1237)
+    planes = device.BitPlanes.from_packed(planes_np, 1237)
+    targets, parents = _groups(specs)
+    counts = device.rule_counts(planes, targets, parents)
+    group = np.repeat(np.arange(6), 256)
+    lut = np.tile(np.arange(256, dtype=np.uint8), 6)
+    diffs = device.rule_error_table(counts, group, lut).cpu().numpy()
+    direct = device.rule_error_table_direct(planes, np.asarray(targets)[group],
+                                            np.asarray(parents)[group], lut).cpu().numpy()
+    assert (diffs == direct).all()
+    c_np = counts.cpu().numpy()
+    for i in range(0, diffs.size, 5):
+        assert diffs[i] == np_diff(c_np[group[i]], int(lut[i]))
+    # every candidate text of every node against the oracle port (eval per cell)
+    nodes = nodes_of(specs)
+    for g, node in enumerate(nodes):
+        node.find_all_rule_predictions()
+        rules = rule_compiler.extend_with_not_variants(node)
+        for r in rules[::9]:
+            d, c = ref_port.calculate_error(node, r[2], dense.astype(float))
+            table = rule_compiler.compile_rule(r[2])
+            assert diffs[g * 256 + table] == d and c == 1237
+
+
+@pytest.mark.parametrize("name", golden_names("rules_"))
+def test_golden_errors_and_inference(cuda, name, tmp_path):
+    """Reference (difference, count) per candidate and the full infer_ruleset() result."""
+    from scbonita2_b200 import file_paths
+    from scbonita2_b200.rule_determination import RuleDetermination
+    logging.disable(logging.CRITICAL)
+    file_paths.set_output_root(str(tmp_path / "out"))
+    g = golden(name)
+    dense = matrix_of(g["matrix"])
+    node_dict = {s["name"]: s["index"] for s in g["specs"]}
+
+    nodes = nodes_of(g["specs"])
+    rd = RuleDetermination(None, "net", "ds", dense, nodes, node_dict)
+    assert rd.num_chunks == g["num_chunks"]
+    assert (rd.chunked_data_numpy == matrix_of(g["chunked"])).all()
+    for node in nodes:
+        node.find_all_rule_predictions()
+    for node, cands, errs in zip(nodes, g["candidates"], g["errors"]):
+        for logic, (d, c) in list(zip(cands, errs))[::5]:
+            got = RuleDetermination.calculate_error(node, logic, rd.chunked_planes)
+            assert (int(got[0]), got[1]) == (d, c)
+            assert isinstance(got[0], np.int64) and isinstance(got[1], int)
+
+    nodes = nodes_of(g["specs"])
+    rd = RuleDetermination(None, "net", "ds", dense, nodes, node_dict)
+    ruleset = rd.infer_ruleset()
+    got = [[r[0][0], [int(i) for i in r[0][1]], r[0][2], int(r[1]), float(r[2])] for r in ruleset]
+    assert got == g["ruleset"]
+    for node, after in zip(nodes, g["nodes_after"]):
+        assert [[k, v] for k, v in node.predecessors.items()] == after["predecessors"]
+        assert [[k, bool(v)] for k, v in node.inversions.items()] == after["inversions"]
+        assert len(node.node_rules) == after["n_node_rules"]
+        assert (not isinstance(node.node_rules[0], list)) == after["flat_node_rules"]
+        assert node.best_rule_index == after["best_rule_index"]
+    rules_txt = open(os.path.join(file_paths.file_paths["rules_output"], "ds_rules",
+                                  "net_ds_rules.txt")).read()
+    assert rules_txt == g["rules_txt"]
+
+
+def test_population_fitness_identity_and_host_path(cuda):
+    """fitness[p] == sum_n E[n][choice[p][n]] (A7 pinned through A4), device and host-buffer API."""
+    from scbonita2_b200 import device
+    specs, planes_np = synth.synthetic_dataset(23, 5000, 21, flip=0.1)
+    dense = synth.planes_to_dense(planes_np, 5000)
+    planes = device.BitPlanes.from_packed(planes_np, 5000)
+    targets, parents = _groups(specs)
+    counts = device.rule_counts(planes, targets, parents)
+    c_np = counts.cpu().numpy()
+    rng = np.random.default_rng(1)
+    lut = rng.integers(0, 256, (301, 23)).astype(np.uint8)
+    active = (rng.random((301, 23)) < 0.8).astype(np.uint8)
+    diff, diff_pg = device.population_fitness(counts, lut, None, per_node=True)
+    diff, diff_pg = diff.cpu().numpy(), diff_pg.cpu().numpy()
+    for p in range(0, 301, 13):
+        per = [np_diff(c_np[n], int(lut[p, n])) for n in range(23)]
+        assert list(diff_pg[p]) == per and diff[p] == sum(per)
+    diff_a, _ = device.population_fitness(counts, lut, active)
+    assert (diff_a.cpu().numpy() == (diff_pg * active).sum(axis=1)).all()
+
+    ws = device.HostWorkspace()
+    ws.load_dense(dense)
+    h_counts = ws.rule_counts(targets, parents)
+    assert (h_counts == c_np).all()
+    h_diff, h_pg = ws.population_fitness(lut, None, per_node=True)
+    assert (h_diff == diff).all() and (h_pg == diff_pg).all()
+    h_tab = ws.rule_error_table(np.arange(23), lut[0])
+    assert (h_tab == diff_pg[0]).all()
+    ws.load_planes(planes_np, 5000)
+    assert (ws.rule_counts(targets, parents) == c_np).all()
+    ws.close()
+
+
+def test_ga_wrapper_matches_oracle_formula(cuda):
+    from scbonita2_b200 import device
+    from scbonita2_b200.genetic_algorithm import PopulationFitness
+    specs, planes_np = synth.synthetic_dataset(7, 90, 31, flip=0.1)
+    dense = synth.planes_to_dense(planes_np, 90).astype(float)
+    nodes = nodes_of(specs)
+    pf = PopulationFitness(nodes, device.BitPlanes.from_packed(planes_np, 90))
+    tables = pf.candidate_tables()
+    logics = [[r[2] for r in n.node_rules] for n in nodes]
+    rng = np.random.default_rng(2)
+    choice = np.array([[rng.integers(0, len(t)) for t in tables] for _ in range(5)])
+    lut = np.array([[tables[n][choice[p, n]] for n in range(7)] for p in range(5)], dtype=np.uint8)
+    raw, fits = pf.fitness_calculation(lut, current_gen=4, max_gen=15)
+    sel = [[[int(choice[p, n])] for n in range(7)] for p in range(5)]
+    want_raw, want_fit = ref_port.population_fitness(nodes, logics, sel, dense, 4, 15)
+    assert raw == want_raw and fits == want_fit
+
+
+def test_counts_are_additive_over_cell_shards(cuda):
+    """Size-independent property used at full size: counts(all cells) == sum of shard counts."""
+    from scbonita2_b200 import device
+    specs, planes_np = synth.synthetic_dataset(40, 100_000, 41, flip=0.05, relax_steps=3)
+    planes = device.BitPlanes.from_packed(planes_np, 100_000)
+    targets, parents = _groups(specs)
+    whole = device.rule_counts(planes, targets, parents)
+    n_words = planes_np.shape[1]
+    parts = 0
+    for lo, hi in [(0, 1000), (1000, 1001), (1001, 2500), (2500, n_words)]:
+        parts = parts + device.rule_counts(planes.word_slice(lo, hi), targets, parents)
+    assert (whole == parts).all()
+    assert int(whole.sum()) == 40 * 100_000

@@ -1,0 +1,167 @@
+"""GPU parity: knock-out / knock-in importance sweep and per-cell trajectories."""
+import logging
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ref_port
+from tests.helpers import golden, golden_names, matrix_of, nodes_of
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _sweep(nodes, dense, steps=50):
+    from scbonita2_b200 import device
+    from scbonita2_b200.importance_scores import compile_network
+    for node in nodes:
+        node.calculation_function = node.best_rule[2]
+    parents, luts = compile_network(nodes)
+    planes = device.BitPlanes.from_dense(dense)
+    raw, missing, keyerr = device.ko_ki_sweep(planes, parents, luts, steps=steps)
+    return raw.cpu().numpy().tolist(), missing.cpu().numpy().tolist(), int(keyerr.item())
+
+
+@pytest.mark.parametrize("name", golden_names("sweep_"))
+def test_sweep_golden(cuda, name, tmp_path):
+    from scbonita2_b200 import file_paths
+    from scbonita2_b200.importance_scores import CalculateImportanceScore
+    logging.disable(logging.CRITICAL)
+    file_paths.set_output_root(str(tmp_path / "out"))
+    g = golden(name)
+    dense = matrix_of(g["matrix"])
+    nodes = nodes_of(g["specs"], with_logic=True)
+    for node, logic in zip(nodes, g["logics"]):
+        node.best_rule[2] = logic
+
+    # kernel-level: counts of missing attractors per condition (also for the KeyError case)
+    raw, missing, keyerr = _sweep(nodes, dense[:, g["sample"]])
+    assert missing[0] == sum(1 for v in g["len_normal"] if v == 0)
+    for i in range(len(nodes)):
+        assert missing[1 + 2 * i] == sum(1 for v in g["len_ko"][i] if v == 0), i
+        assert missing[2 + 2 * i] == sum(1 for v in g["len_ki"][i] if v == 0), i
+
+    # API-level: same seed -> same sample -> same raw totals and normalised scores
+    random.seed(g["seed"])
+    import scipy.sparse as sp
+    calc = CalculateImportanceScore(nodes, sp.csr_matrix(dense.astype(float)).astype(bool), "net", "ds")
+    assert calc.cell_sample_indices == g["sample"]
+    if g["error"] == "KeyError":
+        assert keyerr > 0
+        with pytest.raises(KeyError):
+            calc.calculate_importance_scores()
+        return
+    assert keyerr == 0 and raw == g["raw"]
+    scores = calc.calculate_importance_scores()
+    assert [calc.raw_importance_scores[n.name] for n in nodes] == g["raw"]
+    got = [float(scores[n.name]) for n in nodes]
+    assert np.allclose(got, g["scores"], rtol=0, atol=1e-6)      # north_star tolerance
+    assert got == g["scores"]                                     # and in fact bit-identical
+    assert [float(n.importance_score) for n in nodes] == g["scores"]
+
+
+def _cyclic_specs(seed, n_nodes):
+    """Random network with a high share of inhibitory edges and self-free feedback: many cycles."""
+    return synth.random_network(n_nodes, seed, p_inhibit=0.5, p_source=0.05)
+
+
+@pytest.mark.parametrize("n_nodes,n_cells,seed,steps", [
+    (3, 1, 1, 50), (6, 33, 2, 50), (12, 64, 3, 50), (17, 100, 4, 50), (25, 40, 5, 50),
+    (9, 70, 6, 7), (9, 70, 7, 2), (14, 65, 8, 50), (33, 32, 9, 50)])
+def test_sweep_random_vs_oracle(cuda, n_nodes, n_cells, seed, steps):
+    specs = _cyclic_specs(seed, n_nodes)
+    planes_np = synth.random_planes(n_nodes, n_cells, seed + 100, density=0.5)
+    dense = synth.planes_to_dense(planes_np, n_cells)
+    nodes = nodes_of(specs, with_logic=True)
+    raw, missing, keyerr = _sweep(nodes, dense, steps)
+    try:
+        want_raw, want_missing = ref_port.importance_raw_counts(nodes, dense.astype(bool), steps)
+    except KeyError:
+        assert keyerr > 0
+        return
+    assert keyerr == 0
+    assert missing == want_missing
+    assert raw == want_raw
+
+
+def test_sweep_long_cycles_and_step_window(cuda):
+    """Johnson rings: period 2n.  Found iff mu + lambda <= steps - 1."""
+    for n, steps in [(4, 50), (12, 50), (24, 50), (25, 50), (24, 49), (12, 25), (12, 24), (30, 64)]:
+        specs = []
+        for i in range(n):
+            p = (i - 1) % n
+            inv = i == 0
+            specs.append(synth.NodeSpec(f"G{i}", i, {p: f"G{p}"}, {p: inv}, "not A" if inv else "A"))
+        rng = np.random.default_rng(n)
+        dense = (rng.random((n, 37)) < 0.5).astype(np.uint8)
+        nodes = nodes_of(specs, with_logic=True)
+        raw, missing, keyerr = _sweep(nodes, dense, steps)
+        try:
+            want_raw, want_missing = ref_port.importance_raw_counts(nodes, dense.astype(bool), steps)
+        except KeyError:
+            assert keyerr > 0, (n, steps)
+            continue
+        assert (raw, missing, keyerr) == (want_raw, want_missing, 0), (n, steps)
+
+
+def test_sweep_is_additive_over_cell_shards_and_host_path(cuda):
+    from scbonita2_b200 import device
+    from scbonita2_b200.importance_scores import compile_network
+    specs, planes_np = synth.synthetic_dataset(40, 5000, 77, flip=0.3, relax_steps=1, p_inhibit=0.4)
+    nodes = nodes_of(specs, with_logic=True)
+    parents, luts = compile_network(nodes)
+    planes = device.BitPlanes.from_packed(planes_np, 5000)
+    whole = device.ko_ki_sweep(planes, parents, luts)
+    out = None
+    n_words = planes_np.shape[1]
+    for lo, hi in [(0, 7), (7, 64), (64, 65), (65, n_words)]:
+        out = device.ko_ki_sweep(planes.word_slice(lo, hi), parents, luts, out=out)
+    for a, b in zip(whole, out):
+        assert (a == b).all()
+    ws = device.HostWorkspace()
+    ws.load_planes(planes_np, 5000)
+    raw, missing, keyerr = ws.ko_ki_sweep(parents, luts)
+    assert (raw == whole[0].cpu().numpy()).all() and (missing == whole[1].cpu().numpy()).all()
+    assert keyerr[0] == int(whole[2].item())
+    ws.close()
+
+
+def test_sweep_wide_network_uses_32_slot_kernel(cuda):
+    """> 215 nodes no longer fit 64 slots of shared memory; the 32-slot instantiation runs."""
+    specs = synth.random_network(260, 5, p_inhibit=0.3)
+    planes_np = synth.random_planes(260, 48, 6, density=0.5)
+    dense = synth.planes_to_dense(planes_np, 48)
+    nodes = nodes_of(specs, with_logic=True)
+    raw, missing, keyerr = _sweep(nodes, dense, 20)
+    try:
+        want_raw, want_missing = ref_port.importance_raw_counts(nodes, dense.astype(bool), 20)
+    except KeyError:
+        assert keyerr > 0
+        return
+    assert (raw, missing, keyerr) == (want_raw, want_missing, 0)
+
+
+@pytest.mark.parametrize("name", golden_names("traj_"))
+def test_trajectories_golden(cuda, name):
+    from scbonita2_b200.attractor_analysis import simulate_trajectories, vectorized_run_simulation
+    g = golden(name)
+    dense = matrix_of(g["matrix"])
+    nodes = nodes_of(g["specs"], with_logic=True)
+    for cell, want in zip(g["cells"], g["trajectories"]):
+        assert vectorized_run_simulation(nodes, dense[:, cell]) == want
+    batch = simulate_trajectories(nodes, dense, g["cells"])
+    for m, want in enumerate(g["trajectories"]):
+        assert batch[m].T.tolist() == want
+
+
+def test_trajectories_many_cells_vs_oracle(cuda):
+    from scbonita2_b200.attractor_analysis import simulate_trajectories
+    specs = _cyclic_specs(12, 21)
+    planes_np = synth.random_planes(21, 1500, 13, density=0.4)
+    dense = synth.planes_to_dense(planes_np, 1500)
+    nodes = nodes_of(specs, with_logic=True)
+    cells = list(range(0, 1500, 7)) + [1499, 3, 3]
+    got = simulate_trajectories(nodes, dense, cells)
+    hist = ref_port.run_simulation(nodes, dense[:, cells].astype(bool), 20)   # (steps, nodes, cells)
+    assert (got == np.transpose(hist, (2, 1, 0)).astype(np.uint8)).all()
