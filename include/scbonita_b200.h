@@ -41,7 +41,7 @@ typedef struct CUstream_st* scb_stream_t; /* == cudaStream_t */
 
 #define SCB_ABI_VERSION 1
 #define SCB_COUNTS_PER_GROUP 16 /* [minterm 0..7][target 0..1] */
-#define SCB_MAX_SWEEP_NODES 443
+#define SCB_MAX_SWEEP_NODES 413
 
 int scb_abi_version(void);
 const char* scb_last_error(void);

@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(kCountThreads)
 rule_counts_kernel(const uint32_t* __restrict__ planes, int n_rows, int64_t wpad, int64_t n_words,
                    int tile_words, int64_t n_tiles, int n_groups,
                    const int32_t* __restrict__ target_row, const int32_t* __restrict__ parent_row,
-                   uint32_t* __restrict__ partial /*[grid][n_rows + 11*G]*/) {
+                   unsigned long long* __restrict__ acc /*[n_rows + 11*G], zeroed*/,
+                   unsigned int* __restrict__ ticket /*zeroed*/, int64_t n_cells,
+                   int64_t* __restrict__ out_counts /*[G][16]*/) {
     extern __shared__ __align__(16) uint32_t smem[];
     // layout: tile[(n_rows+1)][tile_words] | row_acc[n_rows] | grp_acc[G][11]
     uint32_t* tile = smem;
@@ -108,53 +110,44 @@ rule_counts_kernel(const uint32_t* __restrict__ planes, int n_rows, int64_t wpad
         }
     }
     __syncthreads();
-    uint32_t* out = partial + (size_t)blockIdx.x * (n_rows + kTermsPerGroup * n_groups);
-    for (int i = tid; i < n_rows + kTermsPerGroup * n_groups; i += blockDim.x) out[i] = row_acc[i];
-}
-
-// one warp per group: lanes add the CTA partials (int64), then lane 0 inverts the subset sums
-__global__ void __launch_bounds__(128)
-rule_counts_finalize_kernel(const uint32_t* __restrict__ partial, int n_parts, int n_rows,
-                            int n_groups, int64_t n_cells, const int32_t* __restrict__ target_row,
-                            const int32_t* __restrict__ parent_row,
-                            int64_t* __restrict__ out_counts) {
-    const int lane = threadIdx.x & 31;
-    int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= n_groups) return;
-    const size_t stride = (size_t)n_rows + (size_t)kTermsPerGroup * n_groups;
-    int ra = parent_row[3 * g], rb = parent_row[3 * g + 1], rc = parent_row[3 * g + 2];
-    int rt = target_row[g];
+    // fold this CTA's sums into the global int64 accumulators (integer adds: order-free, exact)
+    const int n_acc = n_rows + kTermsPerGroup * n_groups;
+    for (int i = tid; i < n_acc; i += blockDim.x)
+        if (row_acc[i]) atomicAdd(acc + i, (unsigned long long)row_acc[i]);
+    __threadfence();
+    __syncthreads();
+    __shared__ unsigned int s_ticket;
+    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    // last CTA: every other CTA's adds are visible; invert the subset sums per group
+    __threadfence();
     constexpr int kTermMask[kTermsPerGroup] = SCB_TERM_MASKS;
-    long long sub[16];  // sub[S] = #cells where every variable in S is 1
+    for (int g = tid; g < n_groups; g += blockDim.x) {
+        int ra = parent_row[3 * g], rb = parent_row[3 * g + 1], rc = parent_row[3 * g + 2];
+        int rt = target_row[g];
+        long long sub[16];  // sub[S] = #cells where every variable in S is 1 (T=8, A=4, B=2, C=1)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sub[i] = 0;
-    for (int p = lane; p < n_parts; p += 32) {
-        const uint32_t* blk = partial + (size_t)p * stride;
-        if (ra >= 0) sub[0x4] += blk[ra];
-        if (rb >= 0) sub[0x2] += blk[rb];
-        if (rc >= 0) sub[0x1] += blk[rc];
-        sub[0x8] += blk[rt];
-        const uint32_t* terms = blk + n_rows + (size_t)g * kTermsPerGroup;
+        for (int i = 0; i < 16; ++i) sub[i] = 0;
+        sub[0] = n_cells;
+        if (ra >= 0) sub[0x4] = (long long)__ldcg(acc + ra);
+        if (rb >= 0) sub[0x2] = (long long)__ldcg(acc + rb);
+        if (rc >= 0) sub[0x1] = (long long)__ldcg(acc + rc);
+        sub[0x8] = (long long)__ldcg(acc + rt);
+        const unsigned long long* terms = acc + n_rows + (size_t)g * kTermsPerGroup;
 #pragma unroll
-        for (int k = 0; k < kTermsPerGroup; ++k) sub[kTermMask[k]] += terms[k];
-    }
+        for (int k = 0; k < kTermsPerGroup; ++k) sub[kTermMask[k]] = (long long)__ldcg(terms + k);
+        // Moebius inversion over the 4-variable lattice: exact[S] = #cells whose set of ones is S
 #pragma unroll
-    for (int i = 1; i < 16; ++i)
+        for (int bit = 1; bit < 16; bit <<= 1)
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sub[i] += __shfl_xor_sync(0xFFFFFFFFu, sub[i], off);
-    if (lane != 0) return;
-    sub[0] = n_cells;
-    // Moebius inversion over the 4-variable lattice: exact[S] = #cells whose set of ones is S
+            for (int q = 0; q < 16; ++q)
+                if (!(q & bit)) sub[q] -= sub[q | bit];
 #pragma unroll
-    for (int bit = 1; bit < 16; bit <<= 1)
-#pragma unroll
-        for (int s = 0; s < 16; ++s)
-            if (!(s & bit)) sub[s] -= sub[s | bit];
-    // sub is indexed (T<<3 | A<<2 | B<<1 | C); output is [minterm k][target t]
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        out_counts[(size_t)g * 16 + 2 * k + 0] = sub[k];
-        out_counts[(size_t)g * 16 + 2 * k + 1] = sub[8 | k];
+        for (int k = 0; k < 8; ++k) {
+            out_counts[(size_t)g * 16 + 2 * k + 0] = sub[k];      // minterm k, target 0
+            out_counts[(size_t)g * 16 + 2 * k + 1] = sub[8 | k];  // minterm k, target 1
+        }
     }
 }
 
@@ -175,19 +168,28 @@ __global__ void error_table_kernel(const int64_t* __restrict__ counts, int64_t n
     out_diff[t] = diff_from_counts(counts + (size_t)task_group[t] * 16, task_lut[t]);
 }
 
-// one warp per individual; lanes stride over the groups; counts table staged in shared memory
-__global__ void __launch_bounds__(256)
+// One warp per individual, lanes stride over the groups.  With
+//   diff(L) = sum_k c[k][1] + sum_{k: L_k = 1} (c[k][0] - c[k][1])
+// the CTA stages base[g] and delta[k][g] in shared memory, laid out [k][g] so that lanes with
+// consecutive g read consecutive words (no bank conflicts).
+__global__ void __launch_bounds__(512)
 population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int64_t n_ind,
                           const uint8_t* __restrict__ lut, const uint8_t* __restrict__ active,
-                          int64_t* __restrict__ out_diff, int64_t* __restrict__ out_diff_pg,
-                          int counts_in_smem) {
-    extern __shared__ __align__(16) int64_t s_counts[];
-    const int64_t* table = counts;
-    if (counts_in_smem) {
-        for (int i = threadIdx.x; i < n_groups * 16; i += blockDim.x) s_counts[i] = counts[i];
-        __syncthreads();
-        table = s_counts;
+                          int64_t* __restrict__ out_diff, int64_t* __restrict__ out_diff_pg) {
+    extern __shared__ __align__(16) long long s_tab[];  // base[G] | delta[8][G]
+    long long* base = s_tab;
+    long long* delta = s_tab + n_groups;
+    for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
+        const int64_t* c = counts + (size_t)g * 16;
+        long long b = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            b += c[2 * k + 1];
+            delta[k * n_groups + g] = c[2 * k] - c[2 * k + 1];
+        }
+        base[g] = b;
     }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -197,7 +199,13 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
         long long total = 0;
         for (int g = lane; g < n_groups; g += 32) {
             long long d = 0;
-            if (!act || act[g]) d = diff_from_counts(table + (size_t)g * 16, row[g]);
+            if (!act || act[g]) {
+                const uint32_t table = row[g];
+                d = base[g];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if ((table >> k) & 1u) d += delta[k * n_groups + g];
+            }
             if (out_diff_pg) out_diff_pg[(size_t)p * n_groups + g] = d;
             total += d;
         }
@@ -284,11 +292,10 @@ using namespace scb;
 static const int kMaxGroupsPerLaunch = 1024;
 
 extern "C" int64_t scb_rule_counts_scratch_bytes(int n_rows, int n_groups) {
-    // per launch: grid <= 2*SMs partial blocks of (rows + 11*groups) uint32
+    // int64 accumulators (rows + 11 per group of one launch slice) + the CTA ticket
     if (n_rows < 0 || n_groups < 0) return 0;
-    int64_t blocks = (int64_t)2 * (sm_count() > 0 ? sm_count() : 256);
     int gn = n_groups < kMaxGroupsPerLaunch ? n_groups : kMaxGroupsPerLaunch;
-    return blocks * ((int64_t)n_rows + (int64_t)kTermsPerGroup * gn) * 4;
+    return ((int64_t)n_rows + (int64_t)kTermsPerGroup * gn) * 8 + 16;
 }
 
 extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
@@ -307,20 +314,20 @@ extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad,
         CountsPlan plan;
         int rc = plan_counts(n_rows, wpad, gn, &plan);
         if (rc != SCB_OK) return rc;
-        int64_t need = (int64_t)plan.grid * ((int64_t)n_rows + (int64_t)kTermsPerGroup * gn) * 4;
+        int64_t n_acc = (int64_t)n_rows + (int64_t)kTermsPerGroup * gn;
+        int64_t need = n_acc * 8 + 16;
         if (need > scratch_bytes) {
             set_error("rule_counts: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
             return SCB_ERR_SCRATCH;
         }
         SCB_CUDA(cudaFuncSetAttribute(rule_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        SCB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)need, as_stream(stream)));
+        auto* acc = static_cast<unsigned long long*>(scratch);
+        auto* ticket = reinterpret_cast<unsigned int*>(acc + n_acc);
         rule_counts_kernel<<<plan.grid, kCountThreads, plan.smem, as_stream(stream)>>>(
             planes, n_rows, wpad, n_words, plan.tile_words, plan.n_tiles, gn, target_row + g0,
-            parent_row + 3 * (size_t)g0, static_cast<uint32_t*>(scratch));
+            parent_row + 3 * (size_t)g0, acc, ticket, n_cells, out_counts + (size_t)g0 * 16);
         SCB_LAUNCH_CHECK("rule_counts_kernel");
-        rule_counts_finalize_kernel<<<(gn + 3) / 4, 128, 0, as_stream(stream)>>>(
-            static_cast<const uint32_t*>(scratch), plan.grid, n_rows, gn, n_cells, target_row + g0,
-            parent_row + 3 * (size_t)g0, out_counts + (size_t)g0 * 16);
-        SCB_LAUNCH_CHECK("rule_counts_finalize_kernel");
     }
     return SCB_OK;
 }
@@ -343,16 +350,18 @@ extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64
     SCB_REQUIRE(n_groups > 0 && n_individuals >= 0, "population_fitness: bad size");
     if (n_individuals == 0) return SCB_OK;
     SCB_REQUIRE(counts && lut && out_diff, "population_fitness: null pointer");
-    size_t smem = (size_t)n_groups * 16 * sizeof(int64_t);
-    int in_smem = smem <= 96 * 1024;
-    if (in_smem && smem > 48 * 1024)
+    size_t smem = (size_t)n_groups * 9 * sizeof(long long);
+    if (smem > 200 * 1024) {
+        set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 72));
+        return SCB_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
         SCB_CUDA(cudaFuncSetAttribute(population_fitness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t warps = n_individuals;
-    int64_t blocks = (warps + 7) / 8;
-    int64_t cap = (int64_t)sm_count() * 8;
+    int64_t blocks = (n_individuals + 15) / 16;  // 16 warps per CTA, one individual per warp
+    int64_t cap = (int64_t)sm_count() * 2;
     if (blocks > cap) blocks = cap;
-    population_fitness_kernel<<<(unsigned)blocks, 256, in_smem ? smem : 0, as_stream(stream)>>>(
-        counts, n_groups, n_individuals, lut, active, out_diff, out_diff_pg, in_smem);
+    population_fitness_kernel<<<(unsigned)blocks, 512, smem, as_stream(stream)>>>(
+        counts, n_groups, n_individuals, lut, active, out_diff, out_diff_pg);
     SCB_LAUNCH_CHECK("population_fitness_kernel");
     return SCB_OK;
 }

@@ -77,7 +77,15 @@ __device__ __forceinline__ uint32_t eval_node(const NodeEntry& e, const uint32_t
     return eval_lut(m, st[e.pa * SLOTS + slot], st[e.pb * SLOTS + slot], st[e.pc * SLOTS + slot]);
 }
 
+// Per-node constants as the sweep kernel keeps them in shared memory: element offsets of the
+// three parent rows inside a state buffer and the truth table expanded to 8 full-word masks.
+// Everything is warp-uniform, so each load is a single broadcast wavefront.
+struct __align__(16) NodeOffsets {
+    int pa, pb, pc, pad;
+};
+
 enum { MODE_NORMAL = 0, MODE_KOKI = 1 };
+constexpr int kRing = 4;  // fast path detects cycle lengths 1..kRing online
 
 template <int SLOTS, int MODE>
 __global__ void __launch_bounds__(kSweepThreads)
@@ -86,17 +94,16 @@ sweep_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wpad, int
              uint32_t* __restrict__ np_states /*[steps][N][wpad]*/,
              uint32_t* __restrict__ np_lam /*[6][wpad]*/, uint32_t* __restrict__ np_found /*[wpad]*/,
              unsigned long long* __restrict__ out_raw, unsigned long long* __restrict__ out_missing,
-             unsigned long long* __restrict__ out_keyerror) {
+             unsigned long long* __restrict__ out_keyerror, unsigned long long* __restrict__ out_stats) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = n_nodes;
     const int S = blockDim.x / SLOTS;
-    uint32_t* buf0 = smem;
-    uint32_t* buf1 = buf0 + (size_t)N * SLOTS;
-    uint32_t* buf2 = buf1 + (size_t)N * SLOTS;
-    uint32_t* buf3 = buf2 + (size_t)N * SLOTS;
-    NodeEntry* tab = reinterpret_cast<NodeEntry*>(buf3 + (size_t)N * SLOTS);
-    uint32_t* partials = reinterpret_cast<uint32_t*>(tab + N);  // [2][2][S][SLOTS]
-    uint32_t* xchg = partials + 2 * 2 * S * SLOTS;              // [SLOTS]
+    const int buf_words = N * SLOTS;
+    auto buf = [&](int i) { return smem + i * buf_words; };  // four state buffers [N][SLOTS]
+    NodeOffsets* offs = reinterpret_cast<NodeOffsets*>(smem + 4 * (size_t)buf_words);  // [N]
+    LutMasks* masks = reinterpret_cast<LutMasks*>(offs + N);                         // [N]
+    uint32_t* votes = reinterpret_cast<uint32_t*>(masks + N);  // [2][kRing][SLOTS] OR-accumulators
+    uint32_t* xchg = votes + 2 * kRing * SLOTS;                // [SLOTS]
 
     const int tid = threadIdx.x;
     const int slot = tid % SLOTS;
@@ -120,136 +127,208 @@ sweep_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wpad, int
     const bool word_ok = word < wpad;
     const uint32_t cellmask = word_ok ? tail_mask(word, n_cells) : 0u;
 
-    for (int n = tid; n < N; n += blockDim.x) tab[n] = make_entry(net_parent, net_lut, n);
+    for (int n = tid; n < N; n += blockDim.x) {
+        NodeEntry e = make_entry(net_parent, net_lut, n);
+        NodeOffsets o;
+        o.pa = e.pa * SLOTS; o.pb = e.pb * SLOTS; o.pc = e.pc * SLOTS; o.pad = 0;
+        offs[n] = o;
+        masks[n] = expand_lut(e.lut);
+    }
+    for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
 
     auto load_data = [&](uint32_t* dst) {
         for (int n = n_lo; n < n_hi; ++n)
             dst[n * SLOTS + slot] = word_ok ? __ldg(planes + (size_t)n * wpad + word) : 0u;
     };
-    auto combine = [&](const uint32_t* p) {  // OR of the S partial words of my slot
-        uint32_t v = 0;
-        for (int s = 0; s < S; ++s) v |= p[s * SLOTS + slot];
-        return v;
-    };
+    // next value of node n for my slot, reading the state in `st`
     auto step_node = [&](const uint32_t* st, int n) {
-        uint32_t f = eval_node<SLOTS>(tab[n], st, slot);
+        const NodeOffsets o = offs[n];
+        const uint4 lo = *reinterpret_cast<const uint4*>(&masks[n].m[0]);
+        const uint4 hi = *reinterpret_cast<const uint4*>(&masks[n].m[4]);
+        const uint32_t a = st[o.pa + slot], b = st[o.pb + slot], c = st[o.pc + slot];
+        uint32_t g0 = lop3<0xCA>(c, lo.y, lo.x), g1 = lop3<0xCA>(c, lo.w, lo.z);
+        uint32_t g2 = lop3<0xCA>(c, hi.y, hi.x), g3 = lop3<0xCA>(c, hi.w, hi.z);
+        uint32_t f = lop3<0xCA>(a, lop3<0xCA>(b, g3, g2), lop3<0xCA>(b, g1, g0));
         if (MODE == MODE_KOKI && n == forced_node) f = forced_value;
         return f;
     };
 
-    // ------------------------------------------------------------------ phase 1: lambda
-    uint32_t* cur = buf0;
-    uint32_t* nxt = buf1;
-    uint32_t* chk = buf2;
-    load_data(cur);
-    __syncthreads();
-
-    uint32_t resolved = ~cellmask;  // lanes whose lambda is settled (padding counts as settled)
-    uint32_t found_fp = 0;          // fixed point first seen at history index <= steps-1
-    uint32_t cyc = 0;               // lanes with a Brent-detected cycle (lambda >= 2)
-    uint32_t lam[kLamPlanes];
+    uint32_t found = 0;            // lanes with a first repeat inside the window
+    uint32_t lam[kLamPlanes];      // its cycle length, bit-sliced
 #pragma unroll
     for (int b = 0; b < kLamPlanes; ++b) lam[b] = 0;
-    int chk_time = -1;
-    int t_need = 1;
-    while (t_need - 1 < steps - 2) t_need <<= 1;  // smallest 2^k - 1 >= steps - 2
-    const int t1_max = (t_need - 1) + steps;
+    uint32_t* xs;                  // state frozen at state_mu for found lanes
+    uint32_t* xn;                  // scratch partner of xs
 
-    for (int t = 0; t < t1_max; ++t) {
-        uint32_t neq_prev = 0, neq_chk = 0;
+    // ------------------------------------------------------------------ fast path
+    // Ring of the last kRing states: the new state is compared with all of them while it is
+    // computed; the oldest one lives in the very buffer that is being overwritten.  A lane
+    // whose state equals state_{t-d} (smallest d) has its first repeat at (t-d, t): it is at
+    // state_mu right now and is frozen there.  Exact for cycle lengths <= kRing.
+    load_data(buf(kRing - 1));
+    __syncthreads();
+    uint32_t frozen = ~cellmask;
+    int last = kRing - 1;
+    for (int t = 0; t < steps; ++t) {
+        const uint32_t* src = buf((t + kRing - 1) % kRing);
+        uint32_t* dst = buf(t % kRing);
+        const uint32_t* r2 = buf((t + kRing - 2) % kRing);
+        const uint32_t* r3 = buf((t + kRing - 3) % kRing);
+        uint32_t neq1 = 0, neq2 = 0, neq3 = 0, neq4 = 0;
 #pragma unroll 2
         for (int n = n_lo; n < n_hi; ++n) {
-            uint32_t f = step_node(cur, n);
-            neq_prev |= f ^ cur[n * SLOTS + slot];
-            if (chk_time >= 0) neq_chk |= f ^ chk[n * SLOTS + slot];
-            nxt[n * SLOTS + slot] = f;
+            const uint32_t f = step_node(src, n);
+            const int i = n * SLOTS + slot;
+            const uint32_t old1 = src[i];
+            neq1 |= f ^ old1;
+            neq2 |= f ^ r2[i];
+            neq3 |= f ^ r3[i];
+            neq4 |= f ^ dst[i];
+            dst[i] = (f & ~frozen) | (old1 & frozen);
         }
-        uint32_t* pp = partials + (size_t)(t & 1) * 2 * S * SLOTS;
-        pp[part * SLOTS + slot] = neq_prev;
-        pp[(S + part) * SLOTS + slot] = neq_chk;
+        uint32_t* v = votes + (t & 1) * kRing * SLOTS;
+        if (neq1) atomicOr(v + 0 * SLOTS + slot, neq1);
+        if (neq2) atomicOr(v + 1 * SLOTS + slot, neq2);
+        if (neq3) atomicOr(v + 2 * SLOTS + slot, neq3);
+        if (neq4) atomicOr(v + 3 * SLOTS + slot, neq4);
         __syncthreads();
-        neq_prev = combine(pp);
-        neq_chk = combine(pp + S * SLOTS);
-        if (t >= 1) {  // the raw data state is never compared (importance_scores.py:60-105)
-            uint32_t newly = ~neq_prev & ~resolved;
-            lam[0] |= newly;  // lambda = 1
-            resolved |= newly;
-            if (t <= steps - 1) found_fp |= newly;
-        }
-        if (chk_time >= 0) {
-            uint32_t newly = ~neq_chk & ~resolved;
-            int l = t - chk_time;
-            if (l <= steps - 1) {
-                planes_set(lam, newly, l);
-                cyc |= newly;
-            }
-            resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
-        }
-        if (((t + 1) & t) == 0) {  // t = 2^k - 1: new checkpoint = state_t (own nodes only)
-            for (int n = n_lo; n < n_hi; ++n) chk[n * SLOTS + slot] = nxt[n * SLOTS + slot];
-            chk_time = t;
-        }
-        uint32_t* tmp = cur; cur = nxt; nxt = tmp;
-        if (__syncthreads_and(resolved == 0xFFFFFFFFu)) break;
+        uint32_t open = ~frozen;
+        // state_{t-d} exists for t >= d only (the raw data state is never compared)
+        uint32_t e1 = t >= 1 ? ~v[0 * SLOTS + slot] & open : 0u;
+        open &= ~e1;
+        uint32_t e2 = t >= 2 ? ~v[1 * SLOTS + slot] & open : 0u;
+        open &= ~e2;
+        uint32_t e3 = t >= 3 ? ~v[2 * SLOTS + slot] & open : 0u;
+        open &= ~e3;
+        uint32_t e4 = t >= 4 ? ~v[3 * SLOTS + slot] & open : 0u;
+        lam[0] |= e1 | e3;
+        lam[1] |= e2 | e3;
+        lam[2] |= e4;
+        frozen |= e1 | e2 | e3 | e4;
+        // the other accumulator set is idle between the two barriers: clear it for step t+1
+        if (part < kRing) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
+        last = t % kRing;
+        if (__syncthreads_and(frozen == 0xFFFFFFFFu)) break;
     }
+    found = frozen & cellmask;
+    xs = buf(last);
+    xn = buf((last + 1) % kRing);
 
-    // ------------------------------------------------------------------ phase 2: mu, freeze
-    uint32_t found;
-    uint32_t* xs;  // state frozen at state_mu for found lanes
-    uint32_t* xn;  // its scratch partner
-    if (__syncthreads_or(cyc != 0)) {
-        uint32_t* pc_ = buf0; uint32_t* pn_ = buf1;  // P: runs lambda ahead
-        uint32_t* qc_ = buf2; uint32_t* qn_ = buf3;  // Q: freezes at state_mu
-        load_data(pc_);
-        load_data(qc_);
+    // ------------------------------------------------------------------ slow path
+    // Some lane did not repeat with a cycle length <= kRing inside the window: redo the CTA
+    // with the general scheme (Brent for lambda, two-pointer replay for mu).
+    if (__syncthreads_or((~frozen) != 0)) {
+        if (out_stats && tid == 0) atomicAdd(out_stats, 1ull);
+        uint32_t* cur = buf(0);
+        uint32_t* nxt = buf(1);
+        uint32_t* chk = buf(2);
+        load_data(cur);
         __syncthreads();
-        const uint32_t has_lam = planes_ge(lam, 1) & cellmask;
-        for (int s = 0; s < steps; ++s) {
-            uint32_t adv = planes_gt(lam, s) & has_lam;  // lanes that still owe P a step
-            if (!__syncthreads_or(adv != 0)) break;
+        uint32_t resolved = ~cellmask;
+#pragma unroll
+        for (int b = 0; b < kLamPlanes; ++b) lam[b] = 0;
+        uint32_t cyc = 0, found_fp = 0;
+        int chk_time = -1;
+        int t_need = 1;
+        while (t_need - 1 < steps - 2) t_need <<= 1;  // smallest 2^k - 1 >= steps - 2
+        const int t1_max = (t_need - 1) + steps;
+        for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
+        __syncthreads();
+        for (int t = 0; t < t1_max; ++t) {
+            uint32_t neq_prev = 0, neq_chk = 0;
 #pragma unroll 2
             for (int n = n_lo; n < n_hi; ++n) {
-                uint32_t f = step_node(pc_, n);
-                uint32_t old = pc_[n * SLOTS + slot];
-                pn_[n * SLOTS + slot] = (f & adv) | (old & ~adv);
+                const uint32_t f = step_node(cur, n);
+                const int i = n * SLOTS + slot;
+                neq_prev |= f ^ cur[i];
+                if (chk_time >= 0) neq_chk |= f ^ chk[i];
+                nxt[i] = f;
             }
+            uint32_t* v = votes + (t & 1) * kRing * SLOTS;
+            if (neq_prev) atomicOr(v + slot, neq_prev);
+            if (neq_chk) atomicOr(v + SLOTS + slot, neq_chk);
             __syncthreads();
-            uint32_t* tmp = pc_; pc_ = pn_; pn_ = tmp;
+            neq_prev = v[slot];
+            neq_chk = v[SLOTS + slot];
+            if (t >= 1) {
+                uint32_t newly = ~neq_prev & ~resolved;
+                lam[0] |= newly;  // lambda = 1
+                resolved |= newly;
+                if (t <= steps - 1) found_fp |= newly;
+            }
+            if (chk_time >= 0) {
+                uint32_t newly = ~neq_chk & ~resolved;
+                int l = t - chk_time;
+                if (l <= steps - 1) {
+                    planes_set(lam, newly, l);
+                    cyc |= newly;
+                }
+                resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
+            }
+            if (((t + 1) & t) == 0) {  // t = 2^k - 1: new checkpoint = state_t (own nodes only)
+                for (int n = n_lo; n < n_hi; ++n) chk[n * SLOTS + slot] = nxt[n * SLOTS + slot];
+                chk_time = t;
+            }
+            if (part < 2) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
+            uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+            if (__syncthreads_and(resolved == 0xFFFFFFFFu)) break;
         }
-        uint32_t done = ~has_lam;
-        found = 0;
-        for (int j = 0; j <= steps - 2; ++j) {
-            uint32_t neq = 0;
+        if (__syncthreads_or(cyc != 0)) {
+            uint32_t* pc_ = buf(0); uint32_t* pn_ = buf(1);  // P: runs lambda ahead
+            uint32_t* qc_ = buf(2); uint32_t* qn_ = buf(3);  // Q: freezes at state_mu
+            load_data(pc_);
+            load_data(qc_);
+            for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
+            __syncthreads();
+            const uint32_t has_lam = planes_ge(lam, 1) & cellmask;
+            for (int s = 0; s < steps; ++s) {
+                uint32_t adv = planes_gt(lam, s) & has_lam;  // lanes that still owe P a step
+                if (!__syncthreads_or(adv != 0)) break;
 #pragma unroll 2
-            for (int n = n_lo; n < n_hi; ++n) {
-                uint32_t fp = step_node(pc_, n);
-                uint32_t fq = step_node(qc_, n);
-                uint32_t oldq = qc_[n * SLOTS + slot];
-                neq |= fp ^ fq;
-                pn_[n * SLOTS + slot] = fp;
-                qn_[n * SLOTS + slot] = (oldq & done) | (fq & ~done);
+                for (int n = n_lo; n < n_hi; ++n) {
+                    const uint32_t f = step_node(pc_, n);
+                    const int i = n * SLOTS + slot;
+                    pn_[i] = (f & adv) | (pc_[i] & ~adv);
+                }
+                __syncthreads();
+                uint32_t* tmp = pc_; pc_ = pn_; pn_ = tmp;
             }
-            uint32_t* pp = partials + (size_t)(j & 1) * 2 * S * SLOTS;
-            pp[part * SLOTS + slot] = neq;
-            __syncthreads();
-            neq = combine(pp);
-            uint32_t newly = ~neq & ~done;
-            // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
-            uint32_t eligible = ~planes_gt(lam, steps - 1 - j);
-            found |= newly & eligible;
-            done |= newly;
-            uint32_t* tmp = pc_; pc_ = pn_; pn_ = tmp;
-            tmp = qc_; qc_ = qn_; qn_ = tmp;
-            if (__syncthreads_and(done == 0xFFFFFFFFu)) break;
+            uint32_t done = ~has_lam;
+            found = 0;
+            for (int j = 0; j <= steps - 2; ++j) {
+                uint32_t neq = 0;
+#pragma unroll 2
+                for (int n = n_lo; n < n_hi; ++n) {
+                    const uint32_t fp = step_node(pc_, n);
+                    const uint32_t fq = step_node(qc_, n);
+                    const int i = n * SLOTS + slot;
+                    neq |= fp ^ fq;
+                    pn_[i] = fp;
+                    qn_[i] = (qc_[i] & done) | (fq & ~done);
+                }
+                uint32_t* v = votes + (j & 1) * kRing * SLOTS;
+                if (neq) atomicOr(v + slot, neq);
+                __syncthreads();
+                neq = v[slot];
+                uint32_t newly = ~neq & ~done;
+                // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
+                uint32_t eligible = ~planes_gt(lam, steps - 1 - j);
+                found |= newly & eligible;
+                done |= newly;
+                if (part == 0) votes[((j + 1) & 1) * kRing * SLOTS + slot] = 0;
+                uint32_t* tmp = pc_; pc_ = pn_; pn_ = tmp;
+                tmp = qc_; qc_ = qn_; qn_ = tmp;
+                if (__syncthreads_and(done == 0xFFFFFFFFu)) break;
+            }
+            xs = qc_;
+            xn = qn_;
+        } else {
+            found = found_fp;  // every settled lane sits on its fixed point already
+            xs = cur;
+            xn = nxt;
         }
-        xs = qc_;
-        xn = qn_;
-    } else {
-        found = found_fp;  // every settled lane sits on its fixed point already
-        xs = cur;
-        xn = nxt;
+        found &= cellmask;
     }
-    found &= cellmask;
 
     // ------------------------------------------------------------------ outputs
     if (MODE == MODE_NORMAL) {
@@ -373,9 +452,8 @@ trajectories_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wp
 }
 
 static size_t sweep_smem_bytes(int n_nodes, int slots) {
-    int S = kSweepThreads / slots;
-    return (size_t)4 * n_nodes * slots * 4 + (size_t)n_nodes * sizeof(NodeEntry) +
-           (size_t)2 * 2 * S * slots * 4 + (size_t)slots * 4;
+    return (size_t)4 * n_nodes * slots * 4 + (size_t)n_nodes * (sizeof(NodeOffsets) + sizeof(LutMasks)) +
+           (size_t)2 * kRing * slots * 4 + (size_t)slots * 4;
 }
 
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB
@@ -385,7 +463,8 @@ static int launch_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64
                         const int32_t* net_parent, const uint8_t* net_lut, int steps,
                         uint32_t* np_states, uint32_t* np_lam, uint32_t* np_found,
                         unsigned long long* out_raw, unsigned long long* out_missing,
-                        unsigned long long* out_keyerror, cudaStream_t stream) {
+                        unsigned long long* out_keyerror, unsigned long long* out_stats,
+                        cudaStream_t stream) {
     size_t smem = sweep_smem_bytes(n_nodes, SLOTS);
     int64_t n_words = (n_cells + 31) / 32;
     SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -393,13 +472,13 @@ static int launch_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64
     dim3 grid_n((unsigned)((n_words + SLOTS - 1) / SLOTS));
     sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(
         planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found,
-        out_raw, out_missing, out_keyerror);
+        out_raw, out_missing, out_keyerror, out_stats);
     SCB_LAUNCH_CHECK("sweep_kernel<normal>");
     constexpr int HALF = SLOTS / 2;
     dim3 grid_k((unsigned)((n_words + HALF - 1) / HALF), (unsigned)n_nodes);
     sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(
         planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found,
-        out_raw, out_missing, out_keyerror);
+        out_raw, out_missing, out_keyerror, out_stats ? out_stats + 1 : nullptr);
     SCB_LAUNCH_CHECK("sweep_kernel<koki>");
     return SCB_OK;
 }
@@ -434,9 +513,9 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     auto missing = reinterpret_cast<unsigned long long*>(out_missing);
     auto keyerr = reinterpret_cast<unsigned long long*>(out_keyerror);
     if (sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem)
-        return launch_sweep<64>(planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found, raw, missing, keyerr, as_stream(stream));
+        return launch_sweep<64>(planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found, raw, missing, keyerr, nullptr, as_stream(stream));
     if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem)
-        return launch_sweep<32>(planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found, raw, missing, keyerr, as_stream(stream));
+        return launch_sweep<32>(planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found, raw, missing, keyerr, nullptr, as_stream(stream));
     set_error("ko_ki_sweep: %d nodes exceed the shared-memory resident limit (%d)", n_nodes, SCB_MAX_SWEEP_NODES);
     return SCB_ERR_UNSUPPORTED;
 }

@@ -125,43 +125,68 @@ class BitPlanes:
 
 
 # --------------------------------------------------------------------------------------
+def _host_i32(values, shape):
+    torch = _torch()
+    if isinstance(values, torch.Tensor):
+        values = values.cpu().numpy()
+    return np.ascontiguousarray(np.asarray(values, dtype=np.int32).reshape(shape))
+
+
+class RuleCountsPlan:
+    """Device-resident metadata, scratch and output of ``scb_rule_counts`` for a fixed set of
+    groups, so that repeated passes (GA generations, benchmark steps) enqueue two kernels and
+    nothing else: no host->device copies, no allocation, no synchronisation."""
+
+    def __init__(self, n_rows: int, target_row, parent_row, device=None):
+        torch = _torch()
+        target = _host_i32(target_row, (-1,))
+        parents = _host_i32(parent_row, (-1, 3))
+        if parents.shape[0] != target.size:
+            raise ValueError("parent_row must be [G, 3]")
+        if target.size and (target.min() < 0 or target.max() >= n_rows or parents.min() < -1
+                            or parents.max() >= n_rows):
+            raise IndexError("rule_counts: row index out of range")
+        dev = torch.device(device or "cuda")
+        self.n_rows = int(n_rows)
+        self.n_groups = int(target.size)
+        self.target = torch.from_numpy(target).to(dev)
+        self.parents = torch.from_numpy(parents).to(dev)
+        with torch.cuda.device(dev):
+            self.scratch_bytes = int(_lib.lib().scb_rule_counts_scratch_bytes(self.n_rows, self.n_groups))
+        self.scratch = torch.empty(max(self.scratch_bytes, 16), dtype=torch.uint8, device=dev)
+        self.counts = torch.empty((self.n_groups, 16), dtype=torch.int64, device=dev)
+
+    def run(self, planes: BitPlanes):
+        """Enqueue the pass on the current stream; returns the (reused) int64 [G, 16] tensor."""
+        torch = _torch()
+        if planes.n_rows != self.n_rows:
+            raise ValueError("plan was built for a different number of rows")
+        with torch.cuda.device(self.counts.device):
+            _lib.check(_lib.lib().scb_rule_counts(
+                planes.words.data_ptr(), planes.n_rows, planes.wpad, planes.n_cells, self.n_groups,
+                self.target.data_ptr(), self.parents.data_ptr(), self.scratch.data_ptr(),
+                self.scratch_bytes, self.counts.data_ptr(), _stream()), "scb_rule_counts")
+        return self.counts
+
+
 def rule_counts(planes: BitPlanes, target_row, parent_row):
     """int64 ``[G, 16]`` joint counts (device tensor) for G (target, <=3 parents) groups."""
-    torch = _torch()
-    dev = planes.words.device
-    target = _dev(np.asarray(target_row, dtype=np.int32).reshape(-1), torch.int32, dev)
-    parents = _dev(np.asarray(parent_row, dtype=np.int32).reshape(-1, 3), torch.int32, dev)
-    n_groups = int(target.numel())
-    if parents.shape[0] != n_groups:
-        raise ValueError("parent_row must be [G, 3]")
-    if n_groups:
-        lo = int(min(target.min().item(), 0))
-        hi = int(max(target.max().item(), parents.max().item()))
-        if lo < 0 or hi >= planes.n_rows or int(parents.min().item()) < -1:
-            raise IndexError("rule_counts: row index out of range")
-    counts = torch.empty((n_groups, 16), dtype=torch.int64, device=dev)
-    L = _lib.lib()
-    with torch.cuda.device(dev):
-        nbytes = L.scb_rule_counts_scratch_bytes(planes.n_rows, n_groups)
-        scratch = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
-        _lib.check(L.scb_rule_counts(planes.words.data_ptr(), planes.n_rows, planes.wpad,
-                                     planes.n_cells, n_groups, target.data_ptr(),
-                                     parents.data_ptr(), scratch.data_ptr(), int(nbytes),
-                                     counts.data_ptr(), _stream()), "scb_rule_counts")
-    return counts
+    plan = RuleCountsPlan(planes.n_rows, target_row, parent_row, planes.words.device)
+    return plan.run(planes)
 
 
 def rule_error_table(counts, task_group, task_lut):
     """int64 ``[T]`` mismatch counts (device tensor) of T (group, truth table) tasks."""
     torch = _torch()
     dev = counts.device
-    group = _dev(np.asarray(task_group, dtype=np.int32).reshape(-1), torch.int32, dev)
+    h_group = _host_i32(task_group, (-1,))
+    n_tasks = int(h_group.size)
+    if n_tasks and (h_group.min() < 0 or h_group.max() >= counts.shape[0]):
+        raise IndexError("rule_error_table: group index out of range")
+    group = torch.from_numpy(h_group).to(dev)
     lut = _dev(np.asarray(task_lut, dtype=np.uint8).reshape(-1), torch.uint8, dev)
-    n_tasks = int(group.numel())
     if lut.numel() != n_tasks:
         raise ValueError("task_group and task_lut differ in length")
-    if n_tasks and (int(group.min().item()) < 0 or int(group.max().item()) >= counts.shape[0]):
-        raise IndexError("rule_error_table: group index out of range")
     out = torch.empty(n_tasks, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().scb_rule_error_table(counts.data_ptr(), int(counts.shape[0]), n_tasks,
@@ -187,12 +212,16 @@ def rule_error_table_direct(planes: BitPlanes, target_row, parent_row, lut):
     return out
 
 
-def population_fitness(counts, lut, active=None, per_node: bool = False):
-    """(diff[P], diff_pg[P, G] | None) device tensors for a population of truth-table rows."""
+def population_fitness(counts, lut, active=None, per_node: bool = False, out=None):
+    """(diff[P], diff_pg[P, G] | None) device tensors for a population of truth-table rows.
+    With ``lut`` already a device uint8 tensor and ``out`` a preallocated int64 [P] tensor the
+    call enqueues one kernel and nothing else."""
     torch = _torch()
     dev = counts.device
-    d_lut = lut if isinstance(lut, torch.Tensor) else _dev(np.asarray(lut, dtype=np.uint8), torch.uint8, dev)
-    d_lut = d_lut.to(device=dev, dtype=torch.uint8).contiguous()
+    if isinstance(lut, torch.Tensor) and lut.dtype == torch.uint8 and lut.device == dev and lut.is_contiguous():
+        d_lut = lut
+    else:
+        d_lut = _dev(lut if isinstance(lut, torch.Tensor) else np.asarray(lut, dtype=np.uint8), torch.uint8, dev)
     n_ind, n_groups = int(d_lut.shape[0]), int(d_lut.shape[1])
     if n_groups != counts.shape[0]:
         raise ValueError("lut must be [P, G] with G == counts.shape[0]")
@@ -201,7 +230,8 @@ def population_fitness(counts, lut, active=None, per_node: bool = False):
         d_act = _dev(active, torch.uint8, dev)
         if tuple(d_act.shape) != (n_ind, n_groups):
             raise ValueError("active must be [P, G]")
-    out = torch.empty(n_ind, dtype=torch.int64, device=dev)
+    if out is None:
+        out = torch.empty(n_ind, dtype=torch.int64, device=dev)
     out_pg = torch.empty((n_ind, n_groups), dtype=torch.int64, device=dev) if per_node else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().scb_population_fitness(
@@ -218,12 +248,13 @@ def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=Non
     torch = _torch()
     dev = planes.words.device
     n = planes.n_rows
-    parents = _dev(np.asarray(net_parent, dtype=np.int32).reshape(-1, 3), torch.int32, dev)
+    h_parents = _host_i32(net_parent, (-1, 3))
     d_lut = _dev(np.asarray(net_lut, dtype=np.uint8).reshape(-1), torch.uint8, dev)
-    if parents.shape[0] != n or d_lut.numel() != n:
+    if h_parents.shape[0] != n or d_lut.numel() != n:
         raise ValueError("the sweep needs one (parents, lut) entry per bitplane row")
-    if int(parents.min().item()) < -1 or int(parents.max().item()) >= n:
+    if h_parents.min() < -1 or h_parents.max() >= n:
         raise IndexError("ko_ki_sweep: parent row out of range")
+    parents = torch.from_numpy(h_parents).to(dev)
     if out is None:
         out = (torch.zeros(n, dtype=torch.int64, device=dev),
                torch.zeros(2 * n + 1, dtype=torch.int64, device=dev),
