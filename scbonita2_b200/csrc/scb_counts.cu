@@ -327,10 +327,18 @@ extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad,
             set_error("rule_counts: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
             return SCB_ERR_SCRATCH;
         }
-        SCB_CUDA(cudaFuncSetAttribute(rule_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rule_counts_kernel, kCountThreads, smem));
-        if (per_sm < 1) per_sm = 1;
+        // attribute + occupancy are queried once per shared-memory size (keeps the enqueue path
+        // free of non-stream API calls, e.g. under CUDA-graph capture)
+        static thread_local size_t cached_smem = 0;
+        static thread_local int cached_per_sm = 0;
+        if (smem != cached_smem) {
+            SCB_CUDA(cudaFuncSetAttribute(rule_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int q = 1;
+            SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, rule_counts_kernel, kCountThreads, smem));
+            cached_per_sm = q < 1 ? 1 : q;
+            cached_smem = smem;
+        }
+        int per_sm = cached_per_sm;
         int64_t grid = (int64_t)sm_count() * per_sm;
         if (grid > n_tiles) grid = n_tiles;
         if (grid < 1) grid = 1;

@@ -155,12 +155,14 @@ class RuleDetermination:
 
     # ------------------------------------------------------------------------------
     @staticmethod
-    def score_candidates(nodes, planes: device.BitPlanes, counts_hook=None) -> dict:
+    def score_candidates(nodes, planes: device.BitPlanes, counts_hook=None,
+                         count_override=None) -> dict:
         """{id(node): [difference / count per candidate]} for ``nodes`` in one GPU pass.
 
         Grows each node's ``node_rules`` to the full ordered candidate list first
         (``rule_determination.py:459-475``).  ``counts_hook`` (optional) receives the device
-        count tensor before it is read back — the cell-sharded path all-reduces it there.
+        count tensor before it is read back — the cell-sharded path all-reduces it there and
+        passes the GLOBAL number of cells as ``count_override``.
         """
         if not nodes:
             return {}
@@ -179,7 +181,7 @@ class RuleDetermination:
         if counts_hook is not None:
             counts = counts_hook(counts)
         diffs = device.rule_error_table(counts, task_group, task_lut).cpu().numpy()
-        count = int(planes.n_cells)
+        count = int(planes.n_cells if count_override is None else count_override)
         out = {}
         for node, (lo, hi) in zip(nodes, spans):
             out[id(node)] = [np.int64(d) / count for d in diffs[lo:hi]]
