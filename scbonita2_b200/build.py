@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
-           "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+           "-std=c++17", "-diag-suppress", "128", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
            "-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH]
     if verbose:
         cmd += ["-Xptxas", "-v"]

@@ -20,6 +20,9 @@
 //  * quad partials are folded with two shuffles on 16-bit packed pairs, accumulated per CTA in
 //    shared memory, added to global int64 accumulators with atomics (integer adds: exact and
 //    order-free) and inverted by the last CTA to finish.  No second kernel.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "scb_common.cuh"
 
 namespace scb {
@@ -28,6 +31,8 @@ constexpr int kTermsPerGroup = 11;  // multi-variable AND terms
 constexpr int kTileWords = 32;      // words per row per tile (128 B)
 constexpr int kStages = 2;
 constexpr int kCountThreads = 256;
+constexpr int kMaxClasses = 15;
+constexpr int kTicketBytes = (kMaxClasses + 1) * 4;
 
 // term order (bit3=T, bit2=A, bit1=B, bit0=C): masks of the 11 multi-variable subsets
 #define SCB_TERM_MASKS {0x6 /*AB*/, 0x5 /*AC*/, 0x3 /*BC*/, 0x7 /*ABC*/, 0xC /*AT*/, 0xA /*BT*/, \
@@ -68,6 +73,17 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
         : "memory");
 }
 
+// TMA 2-D tiled copy: one instruction moves a whole [box_rows x 32 words] box; rows / words
+// outside the tensor are zero-filled by the hardware and still counted in the byte total.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* map, int x, int y,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+
 // carry-save adder: (sum, carry) of three words, 2 LOP3
 __device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
     sum = lop3<0x96>(a, b, c);
@@ -90,21 +106,121 @@ __device__ __forceinline__ uint32_t popc8(const uint32_t (&x)[8]) {
     return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
 }
 
+// number of parent slots a group binds when they are packed to the left (A, AB, ABC); any other
+// pattern takes the general three-parent path
+__device__ __forceinline__ int group_arity(int ra, int rb, int rc) {
+    if (rc >= 0) return 3;
+    if (rb >= 0) return ra >= 0 ? 2 : 3;
+    return ra >= 0 ? 1 : 0;
+}
+
+// The AND-subset popcounts of one group over one 32-word tile, taken by a quad (lane l reads the
+// eight words widx[]), folded across the quad and added to the CTA accumulators dst[0..10]
+// (term order of SCB_TERM_MASKS).  ARITY selects which terms can be non-zero.
+template <int ARITY>
+__device__ __forceinline__ void group_terms(const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pb,
+                                            const uint32_t* __restrict__ pc, const uint32_t* __restrict__ pt,
+                                            const int (&widx)[8], int l, bool live, uint32_t* dst) {
+    uint32_t a[8], t[8], x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = pa[widx[j]];
+        t[j] = pt[widx[j]];
+    }
+#define SCB_TERM(var, expr)                                      \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) x[j] = (expr); \
+    uint32_t var = popc8(x);
+    if (ARITY == 1) {
+        SCB_TERM(at, a[j] & t[j])
+        at += __shfl_xor_sync(0xFFFFFFFFu, at, 1);
+        at += __shfl_xor_sync(0xFFFFFFFFu, at, 2);
+        if (live && l == 0) dst[4] += at;
+        return;
+    }
+    uint32_t b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = pb[widx[j]];
+    if (ARITY == 2) {
+        SCB_TERM(ab, a[j] & b[j])
+        SCB_TERM(at, a[j] & t[j])
+        SCB_TERM(bt, b[j] & t[j])
+        SCB_TERM(abt, lop3<0x80>(a[j], b[j], t[j]))
+        // counts <= 256 per lane: two per register in 16-bit fields
+        uint32_t p0 = ab | (at << 16), p1 = bt | (abt << 16);
+        p0 += __shfl_xor_sync(0xFFFFFFFFu, p0, 1);
+        p1 += __shfl_xor_sync(0xFFFFFFFFu, p1, 1);
+        p0 += __shfl_xor_sync(0xFFFFFFFFu, p0, 2);
+        p1 += __shfl_xor_sync(0xFFFFFFFFu, p1, 2);
+        if (live) {  // lanes 0..3 own AB, AT, BT, ABT
+            const uint32_t v = ((l & 2) ? p1 : p0) >> ((l & 1) * 16) & 0xFFFFu;
+            const int term = l == 0 ? 0 : (l == 1 ? 4 : (l == 2 ? 5 : 7));
+            dst[term] += v;
+        }
+        return;
+    }
+    uint32_t c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = pc[widx[j]];
+    uint32_t cnt[kTermsPerGroup];
+#define SCB_TERM_I(idx, expr)                                    \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) x[j] = (expr); \
+    cnt[idx] = popc8(x);
+    SCB_TERM_I(0, a[j] & b[j])
+    SCB_TERM_I(1, a[j] & c[j])
+    SCB_TERM_I(2, b[j] & c[j])
+    SCB_TERM_I(3, lop3<0x80>(a[j], b[j], c[j]))
+    SCB_TERM_I(4, a[j] & t[j])
+    SCB_TERM_I(5, b[j] & t[j])
+    SCB_TERM_I(6, c[j] & t[j])
+    SCB_TERM_I(7, lop3<0x80>(a[j], b[j], t[j]))
+    SCB_TERM_I(8, lop3<0x80>(a[j], c[j], t[j]))
+    SCB_TERM_I(9, lop3<0x80>(b[j], c[j], t[j]))
+    SCB_TERM_I(10, lop3<0x80>(a[j], b[j], c[j]) & t[j])
+#undef SCB_TERM_I
+#undef SCB_TERM
+    uint32_t pk[6];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) pk[k] = cnt[2 * k] | (cnt[2 * k + 1] << 16);
+    pk[5] = cnt[10];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        pk[k] += __shfl_xor_sync(0xFFFFFFFFu, pk[k], 1);
+        pk[k] += __shfl_xor_sync(0xFFFFFFFFu, pk[k], 2);
+    }
+    // lane l of the quad owns terms l, l+4, l+8 (term 11 does not exist)
+    const bool hi_pair = (l >> 1) != 0;
+    const int shift = (l & 1) * 16;
+    uint32_t v0 = ((hi_pair ? pk[1] : pk[0]) >> shift) & 0xFFFFu;
+    uint32_t v1 = ((hi_pair ? pk[3] : pk[2]) >> shift) & 0xFFFFu;
+    uint32_t v2 = ((hi_pair ? pk[5] : pk[4]) >> shift) & 0xFFFFu;
+    if (live) {
+        dst[l] += v0;
+        dst[l + 4] += v1;
+        if (l < 3) dst[l + 8] += v2;
+    }
+}
+
 __global__ void __launch_bounds__(kCountThreads, 3)
-rule_counts_kernel(const uint32_t* __restrict__ planes, int n_rows, int64_t wpad, int64_t n_tiles,
+rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes,
+                   int n_rows, int64_t wpad, int64_t n_tiles,
                    int n_groups, const int32_t* __restrict__ target_row,
                    const int32_t* __restrict__ parent_row,
                    unsigned long long* __restrict__ acc /*[n_rows + 11*G], zeroed*/,
-                   unsigned int* __restrict__ tickets /*[2], zeroed: tile ticket, CTA ticket*/,
-                   int64_t n_cells, int64_t* __restrict__ out_counts /*[G][16]*/) {
+                   unsigned int* __restrict__ tickets /*[kMaxClasses+1], zeroed: tile ticket per class, CTA ticket*/,
+                   int n_classes, int64_t n_cells, int64_t* __restrict__ out_counts /*[G][16]*/) {
     extern __shared__ __align__(128) uint32_t smem[];
-    // layout: stage[kStages][(n_rows+1)][32] | cta_acc[n_rows + 11*G] | mbarriers | tile ids
-    const int stage_words = (n_rows + 1) * kTileWords;
+    // layout: stage[kStages][(rows_alloc+1)][32] | cta_acc[n_rows + 11*G] | mbarriers | tile ids
+    // rows_alloc = n_boxes * box_rows >= n_rows (TMA zero-fills the excess); row rows_alloc is the
+    // explicit all-zero row that unused parent slots read.
+    const int rows_alloc = n_boxes * box_rows;
+    const int stage_words = (rows_alloc + 1) * kTileWords;
     uint32_t* stages = smem;
     uint32_t* cta_acc = stages + (size_t)kStages * stage_words;
     const int n_acc = n_rows + kTermsPerGroup * n_groups;
     uint64_t* full = reinterpret_cast<uint64_t*>(cta_acc + ((n_acc + 1) & ~1));
     int* s_tile = reinterpret_cast<int*>(full + kStages);
+    unsigned short* order = reinterpret_cast<unsigned short*>(s_tile + kStages);  // groups by arity
+    __shared__ int s_arity_count[4], s_arity_fill[4];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -114,51 +230,70 @@ rule_counts_kernel(const uint32_t* __restrict__ planes, int n_rows, int64_t wpad
     const int n_quads = (blockDim.x >> 5) * 8;
 
     for (int i = tid; i < n_acc; i += blockDim.x) cta_acc[i] = 0;
+    if (tid < 4) s_arity_count[tid] = s_arity_fill[tid] = 0;
+    __syncthreads();
+    // counting sort of the groups by arity, widest first (order inside a class is irrelevant)
+    for (int g = tid; g < n_groups; g += blockDim.x)
+        atomicAdd(&s_arity_count[group_arity(parent_row[3 * g], parent_row[3 * g + 1], parent_row[3 * g + 2])], 1);
+    __syncthreads();
+    for (int g = tid; g < n_groups; g += blockDim.x) {
+        const int ar = group_arity(parent_row[3 * g], parent_row[3 * g + 1], parent_row[3 * g + 2]);
+        int base = 0;
+        for (int k = 3; k > ar; --k) base += s_arity_count[k];
+        order[base + atomicAdd(&s_arity_fill[ar], 1)] = (unsigned short)g;
+    }
     for (int s = 0; s < kStages; ++s)               // the all-zero row of every stage
         for (int i = tid; i < kTileWords; i += blockDim.x)
-            stages[(size_t)s * stage_words + (size_t)n_rows * kTileWords + i] = 0;
+            stages[(size_t)s * stage_words + (size_t)rows_alloc * kTileWords + i] = 0;
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // producer (warp 0): claim the next tile and start its copy into `stage`
-    auto produce = [&](int stage) {
-        int tile = 0;
-        if (lane == 0) tile = (int)atomicAdd(&tickets[0], 1u);
-        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    // producer (warp 0): start the copy of `tile` into `stage`.  The first kStages tiles of a CTA
+    // are static (blockIdx.x + s*gridDim.x); later ones come from the global ticket, which is
+    // claimed one tile ahead so that its L2 round trip hides behind the arithmetic.
+    // Work split: groups (and rows) are dealt round-robin into n_classes classes so that one
+    // class fits one round of the CTA's quads; CTA b belongs to class b % n_classes and walks ALL
+    // tiles for its class.  More tiles per CTA amortise the prologue and the final atomics, which
+    // dominated when every CTA carried every group (profiles/r1_counts_v2_ncu.txt).
+    const int cls = blockIdx.x % n_classes;
+    const int cta_in_cls = blockIdx.x / n_classes;
+    const int ctas_in_cls = (gridDim.x - cls + n_classes - 1) / n_classes;
+    const int first_dynamic = kStages * ctas_in_cls;
+    auto claim = [&]() {
+        int t = 0;
+        if (lane == 0) t = first_dynamic + (int)atomicAdd(&tickets[cls], 1u);
+        return t;  // valid in lane 0
+    };
+    auto produce = [&](int stage, int tile_lane0) {
+        const int tile = __shfl_sync(0xFFFFFFFFu, tile_lane0, 0);
         if (lane == 0) s_tile[stage] = tile;
         if (tile >= n_tiles) {
             if (lane == 0) mbar_arrive(&full[stage]);  // nothing to copy: just complete the phase
             return;
         }
-        const int64_t w0 = (int64_t)tile * kTileWords;
-        const int64_t left = wpad - w0;
-        const uint32_t row_bytes = (uint32_t)(left < kTileWords ? left : kTileWords) * 4u;
-        if (lane == 0) mbar_arrive_expect_tx(&full[stage], row_bytes * (uint32_t)n_rows);
-        __syncwarp();
         uint32_t* dst = stages + (size_t)stage * stage_words;
-        for (int r = lane; r < n_rows; r += 32)
-            tma_load_1d(dst + (size_t)r * kTileWords, planes + (size_t)r * wpad + w0, row_bytes, &full[stage]);
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows_alloc * kTileWords * 4));
+            for (int b = 0; b < n_boxes; ++b)
+                tma_load_2d(dst + (size_t)b * box_rows * kTileWords, &tmap, tile * kTileWords, b * box_rows,
+                            &full[stage]);
+        }
     };
     if (warp == 0)
-        for (int s = 0; s < kStages; ++s) produce(s);
+        for (int s = 0; s < kStages; ++s) produce(s, cta_in_cls + s * ctas_in_cls);
 
     for (int it = 0;; ++it) {
         const int stage = it % kStages;
         const uint32_t parity = (it / kStages) & 1;
         mbar_wait(&full[stage], parity);
         const int tile = s_tile[stage];
-        if (tile >= n_tiles) break;  // tickets are monotone: every later stage is empty too
+        if (tile >= n_tiles) break;  // tiles are claimed in increasing order: later stages are empty too
+        int next_tile = 0;
+        if (warp == 0) next_tile = claim();  // consumed after this tile's arithmetic
         uint32_t* buf = stages + (size_t)stage * stage_words;
-        const int64_t left = wpad - (int64_t)tile * kTileWords;
-        if (left < kTileWords) {  // last, partial tile: clear the words the copy did not write
-            const int valid = (int)left;
-            for (int i = tid; i < n_rows * kTileWords; i += blockDim.x)
-                if ((i & (kTileWords - 1)) >= valid) buf[i] = 0;
-            __syncthreads();
-        }
         int widx[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) widx[j] = 4 * (j ^ quad_in_warp) + l;
@@ -166,9 +301,10 @@ rule_counts_kernel(const uint32_t* __restrict__ planes, int n_rows, int64_t wpad
         // ---- single-row popcounts: one quad per row ----
         // (loops are warp-uniform: an out-of-range quad works on a clamped index and is masked out,
         //  because the quad folds below are full-warp shuffles)
-        for (int r0 = warp * 8; r0 < n_rows; r0 += n_quads) {
-            const bool live = r0 + quad_in_warp < n_rows;
-            const int r = live ? r0 + quad_in_warp : n_rows - 1;
+        for (int i0 = warp * 8; cls + n_classes * i0 < n_rows; i0 += n_quads) {
+            const int mine = cls + n_classes * (i0 + quad_in_warp);
+            const bool live = mine < n_rows;
+            const int r = live ? mine : n_rows - 1;
             const uint32_t* p = buf + (size_t)r * kTileWords;
             uint32_t x[8];
 #pragma unroll
@@ -178,65 +314,28 @@ rule_counts_kernel(const uint32_t* __restrict__ planes, int n_rows, int64_t wpad
             s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
             if (l == 0 && live) cta_acc[r] += s;
         }
-        // ---- the 11 multi-variable terms: one quad per group ----
-        for (int g0 = warp * 8; g0 < n_groups; g0 += n_quads) {
-            const bool live = g0 + quad_in_warp < n_groups;
-            const int g = live ? g0 + quad_in_warp : n_groups - 1;
+        // ---- the multi-variable terms: one quad per group, specialised by arity ----
+        // groups are visited in arity order (3, 2, 1, 0 parents), so a warp's eight groups almost
+        // always share one code path; a mixed round runs the widest path (missing parents read the
+        // all-zero row, their terms come out 0).
+        for (int i0 = warp * 8; cls + n_classes * i0 < n_groups; i0 += n_quads) {
+            const int mine = cls + n_classes * (i0 + quad_in_warp);
+            const bool live = mine < n_groups;
+            const int g = live ? (int)order[mine] : 0;
             int ra = __ldg(parent_row + 3 * g + 0), rb = __ldg(parent_row + 3 * g + 1),
                 rc = __ldg(parent_row + 3 * g + 2), rt = __ldg(target_row + g);
-            const uint32_t* pa = buf + (size_t)(ra < 0 ? n_rows : ra) * kTileWords;
-            const uint32_t* pb = buf + (size_t)(rb < 0 ? n_rows : rb) * kTileWords;
-            const uint32_t* pc = buf + (size_t)(rc < 0 ? n_rows : rc) * kTileWords;
+            const int arity = __reduce_max_sync(0xFFFFFFFFu, live ? group_arity(ra, rb, rc) : 0);
+            const uint32_t* pa = buf + (size_t)(ra < 0 ? rows_alloc : ra) * kTileWords;
+            const uint32_t* pb = buf + (size_t)(rb < 0 ? rows_alloc : rb) * kTileWords;
+            const uint32_t* pc = buf + (size_t)(rc < 0 ? rows_alloc : rc) * kTileWords;
             const uint32_t* pt = buf + (size_t)rt * kTileWords;
-            uint32_t a[8], b[8], c[8], t[8], x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a[j] = pa[widx[j]];
-                b[j] = pb[widx[j]];
-                c[j] = pc[widx[j]];
-                t[j] = pt[widx[j]];
-            }
-            uint32_t cnt[kTermsPerGroup];
-#define SCB_TERM(idx, expr)                  \
-    _Pragma("unroll") for (int j = 0; j < 8; ++j) x[j] = (expr); \
-    cnt[idx] = popc8(x);
-            SCB_TERM(0, a[j] & b[j])
-            SCB_TERM(1, a[j] & c[j])
-            SCB_TERM(2, b[j] & c[j])
-            SCB_TERM(3, lop3<0x80>(a[j], b[j], c[j]))
-            SCB_TERM(4, a[j] & t[j])
-            SCB_TERM(5, b[j] & t[j])
-            SCB_TERM(6, c[j] & t[j])
-            SCB_TERM(7, lop3<0x80>(a[j], b[j], t[j]))
-            SCB_TERM(8, lop3<0x80>(a[j], c[j], t[j]))
-            SCB_TERM(9, lop3<0x80>(b[j], c[j], t[j]))
-            SCB_TERM(10, lop3<0x80>(a[j], b[j], c[j]) & t[j])
-#undef SCB_TERM
-            // fold the quad: counts <= 256 per lane, packed two per register (16-bit fields)
-            uint32_t pk[6];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) pk[k] = cnt[2 * k] | (cnt[2 * k + 1] << 16);
-            pk[5] = cnt[10];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                pk[k] += __shfl_xor_sync(0xFFFFFFFFu, pk[k], 1);
-                pk[k] += __shfl_xor_sync(0xFFFFFFFFu, pk[k], 2);
-            }
-            // lane l of the quad owns terms l, l+4, l+8 (term 11 does not exist)
-            const bool hi_pair = (l >> 1) != 0;
-            const int shift = (l & 1) * 16;
-            uint32_t v0 = ((hi_pair ? pk[1] : pk[0]) >> shift) & 0xFFFFu;
-            uint32_t v1 = ((hi_pair ? pk[3] : pk[2]) >> shift) & 0xFFFFu;
-            uint32_t v2 = ((hi_pair ? pk[5] : pk[4]) >> shift) & 0xFFFFu;
-            if (live) {
-                uint32_t* dst = cta_acc + n_rows + (size_t)g * kTermsPerGroup;
-                dst[l] += v0;
-                dst[l + 4] += v1;
-                if (l < 3) dst[l + 8] += v2;
-            }
+            uint32_t* dst = cta_acc + n_rows + (size_t)g * kTermsPerGroup;
+            if (arity >= 3) group_terms<3>(pa, pb, pc, pt, widx, l, live, dst);
+            else if (arity == 2) group_terms<2>(pa, pb, pc, pt, widx, l, live, dst);
+            else if (arity == 1) group_terms<1>(pa, pb, pc, pt, widx, l, live, dst);
         }
         __syncthreads();  // every reader is done with this stage
-        if (warp == 0) produce(stage);
+        if (warp == 0) produce(stage, next_tile);
     }
     __syncthreads();
 
@@ -246,7 +345,7 @@ rule_counts_kernel(const uint32_t* __restrict__ planes, int n_rows, int64_t wpad
     __threadfence();
     __syncthreads();
     __shared__ unsigned int s_ticket;
-    if (tid == 0) s_ticket = atomicAdd(&tickets[1], 1u);
+    if (tid == 0) s_ticket = atomicAdd(&tickets[kMaxClasses], 1u);
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     // last CTA: every other CTA's adds are visible; invert the subset sums per group
@@ -280,10 +379,49 @@ rule_counts_kernel(const uint32_t* __restrict__ planes, int n_rows, int64_t wpad
     }
 }
 
+static void box_shape(int n_rows, int* box_rows, int* n_boxes) {
+    *n_boxes = (n_rows + 255) / 256;            // a TMA box is at most 256 elements per dimension
+    *box_rows = (n_rows + *n_boxes - 1) / *n_boxes;
+}
+
 static size_t counts_smem_bytes(int n_rows, int n_groups) {
+    int box_rows, n_boxes;
+    box_shape(n_rows, &box_rows, &n_boxes);
     size_t n_acc = (size_t)n_rows + (size_t)kTermsPerGroup * n_groups;
-    return (size_t)kStages * (n_rows + 1) * kTileWords * 4 + ((n_acc + 1) & ~(size_t)1) * 4 +
-           kStages * 8 + kStages * 4 + 16;
+    return (size_t)kStages * ((size_t)box_rows * n_boxes + 1) * kTileWords * 4 + ((n_acc + 1) & ~(size_t)1) * 4 +
+           kStages * 8 + kStages * 4 + ((size_t)n_groups * 2 + 16);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+// [n_rows][wpad] uint32 bitplanes as a 2-D tensor, box = [box_rows][32 words]
+static int make_tensor_map(const uint32_t* planes, int n_rows, int64_t wpad, int box_rows, CUtensorMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+            set_error("rule_counts: cuTensorMapEncodeTiled is not available from this driver");
+            return SCB_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)wpad, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)wpad * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kTileWords, (cuuint32_t)box_rows};
+    cuuint32_t elem[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(planes), dims, strides, box,
+                        elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("rule_counts: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        return SCB_ERR_CUDA;
+    }
+    return SCB_OK;
 }
 
 }  // namespace scb
@@ -297,7 +435,7 @@ extern "C" int64_t scb_rule_counts_scratch_bytes(int n_rows, int n_groups) {
     // int64 accumulators (rows + 11 per group of one launch slice) + the two tickets
     if (n_rows < 0 || n_groups < 0) return 0;
     int gn = n_groups < kMaxGroupsPerLaunch ? n_groups : kMaxGroupsPerLaunch;
-    return ((int64_t)n_rows + (int64_t)kTermsPerGroup * gn) * 8 + 16;
+    return ((int64_t)n_rows + (int64_t)kTermsPerGroup * gn) * 8 + kTicketBytes;
 }
 
 extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
@@ -314,6 +452,13 @@ extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad,
     SCB_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 8 == 0, "rule_counts: scratch must be 8-byte aligned");
     const int64_t n_tiles = (wpad + kTileWords - 1) / kTileWords;
     SCB_REQUIRE(n_tiles < ((int64_t)1 << 30), "rule_counts: too many tiles");
+    int box_rows, n_boxes;
+    box_shape(n_rows, &box_rows, &n_boxes);
+    CUtensorMap tmap;
+    {
+        int rc = make_tensor_map(planes, n_rows, wpad, box_rows, &tmap);
+        if (rc != SCB_OK) return rc;
+    }
     for (int g0 = 0; g0 < n_groups; g0 += kMaxGroupsPerLaunch) {
         int gn = n_groups - g0 < kMaxGroupsPerLaunch ? n_groups - g0 : kMaxGroupsPerLaunch;
         size_t smem = counts_smem_bytes(n_rows, gn);
@@ -322,7 +467,7 @@ extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad,
             return SCB_ERR_UNSUPPORTED;
         }
         int64_t n_acc = (int64_t)n_rows + (int64_t)kTermsPerGroup * gn;
-        int64_t need = n_acc * 8 + 16;
+        int64_t need = n_acc * 8 + kTicketBytes;
         if (need > scratch_bytes) {
             set_error("rule_counts: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
             return SCB_ERR_SCRATCH;
@@ -339,15 +484,30 @@ extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad,
             cached_smem = smem;
         }
         int per_sm = cached_per_sm;
+        if (const char* cap = getenv("SCB_COUNTS_CTAS_PER_SM")) {
+            int c = atoi(cap);
+            if (c >= 1 && c < per_sm) per_sm = c;
+        }
+        // one class = at most one round of the CTA's quads (8 per warp)
+        const int quads = (kCountThreads / 32) * 8;
+        int n_classes = 1;
+        (void)quads;
+        if (const char* cap = getenv("SCB_COUNTS_CLASSES")) {
+            int c = atoi(cap);
+            if (c >= 1) n_classes = c;
+        }
+        if (n_classes > kMaxClasses) n_classes = kMaxClasses;
+        if (n_classes < 1) n_classes = 1;
         int64_t grid = (int64_t)sm_count() * per_sm;
-        if (grid > n_tiles) grid = n_tiles;
-        if (grid < 1) grid = 1;
+        if (grid > n_tiles * n_classes) grid = n_tiles * n_classes;
+        grid -= grid % n_classes;
+        if (grid < n_classes) grid = n_classes;
         SCB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)need, as_stream(stream)));
         auto* acc = static_cast<unsigned long long*>(scratch);
         auto* tickets = reinterpret_cast<unsigned int*>(acc + n_acc);
         rule_counts_kernel<<<(unsigned)grid, kCountThreads, smem, as_stream(stream)>>>(
-            planes, n_rows, wpad, n_tiles, gn, target_row + g0, parent_row + 3 * (size_t)g0, acc,
-            tickets, n_cells, out_counts + (size_t)g0 * 16);
+            tmap, box_rows, n_boxes, n_rows, wpad, n_tiles, gn, target_row + g0, parent_row + 3 * (size_t)g0, acc,
+            tickets, n_classes, n_cells, out_counts + (size_t)g0 * 16);
         SCB_LAUNCH_CHECK("rule_counts_kernel");
     }
     return SCB_OK;
