@@ -25,6 +25,8 @@
 // aligned states in scratch; KO and KI of one node share a CTA (slots [0,SLOTS/2) = KO,
 // [SLOTS/2,SLOTS) = KI of the same words) because a cell only counts if BOTH repeat
 // (importance_scores.py:278).
+#include <stdlib.h>
+
 #include "scb_common.cuh"
 
 namespace scb {
@@ -78,32 +80,54 @@ __device__ __forceinline__ uint32_t eval_node(const NodeEntry& e, const uint32_t
 }
 
 // Per-node constants as the sweep kernel keeps them in shared memory: element offsets of the
-// three parent rows inside a state buffer and the truth table expanded to 8 full-word masks.
-// Everything is warp-uniform, so each load is a single broadcast wavefront.
+// three parent rows inside the state array and the truth table expanded to 8 full-word masks.
+// Everything is warp-uniform, so each load is a broadcast.
 struct __align__(16) NodeOffsets {
     int pa, pb, pc, pad;
 };
 
-enum { MODE_NORMAL = 0, MODE_KOKI = 1 };
-constexpr int kRing = 4;  // fast path detects cycle lengths 1..kRing online
+// a (word, node) pair whose KO or KI run has cells the fast path could not settle
+struct __align__(16) SweepItem {
+    int word, node;
+    uint32_t lanes;
+    int pad;
+};
 
+struct SweepArgs {
+    const uint32_t* planes;
+    int n_nodes;
+    int64_t wpad, n_cells;
+    const int32_t* net_parent;
+    const uint8_t* net_lut;
+    int steps;
+    uint32_t* np_states;            // [steps][N][wpad]  normal-run states from each cell's own mu
+    uint32_t* np_lam;               // [6][wpad]         lambda of the normal run, bit-sliced
+    uint32_t* np_found;             // [wpad]
+    SweepItem* items;               // deferred (word, node) pairs
+    unsigned int* counters;         // [0] number of items, [1] flags (bit 0: normal run has lambda >= 3)
+    unsigned long long* out_raw;
+    unsigned long long* out_missing;
+    unsigned long long* out_keyerror;
+};
+
+enum { MODE_NORMAL = 0, MODE_KOKI = 1, MODE_CLEANUP = 2 };
+constexpr int kRing = 4;  // state copies per slot: ring of the fast path, P/Q pairs of the slow path
+
+// State layout in shared memory: word (node n, copy k, slot s) lives at ((n*4 + k)*SLOTS + s), so
+// the four copies of a node sit at compile-time offsets from each other.
 template <int SLOTS, int MODE>
 __global__ void __launch_bounds__(kSweepThreads)
-sweep_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wpad, int64_t n_cells,
-             const int32_t* __restrict__ net_parent, const uint8_t* __restrict__ net_lut, int steps,
-             uint32_t* __restrict__ np_states /*[steps][N][wpad]*/,
-             uint32_t* __restrict__ np_lam /*[6][wpad]*/, uint32_t* __restrict__ np_found /*[wpad]*/,
-             unsigned long long* __restrict__ out_raw, unsigned long long* __restrict__ out_missing,
-             unsigned long long* __restrict__ out_keyerror, unsigned long long* __restrict__ out_stats) {
+sweep_kernel(const SweepArgs args) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int N = n_nodes;
+    const int N = args.n_nodes;
+    const int steps = args.steps;
+    const int64_t wpad = args.wpad;
     const int S = blockDim.x / SLOTS;
-    const int buf_words = N * SLOTS;
-    auto buf = [&](int i) { return smem + i * buf_words; };  // four state buffers [N][SLOTS]
-    NodeOffsets* offs = reinterpret_cast<NodeOffsets*>(smem + 4 * (size_t)buf_words);  // [N]
-    LutMasks* masks = reinterpret_cast<LutMasks*>(offs + N);                         // [N]
+    uint32_t* state = smem;                                                            // [N][4][SLOTS]
+    NodeOffsets* offs = reinterpret_cast<NodeOffsets*>(smem + (size_t)4 * N * SLOTS);  // [N]
+    LutMasks* masks = reinterpret_cast<LutMasks*>(offs + N);                           // [N]
     uint32_t* votes = reinterpret_cast<uint32_t*>(masks + N);  // [2][kRing][SLOTS] OR-accumulators
-    uint32_t* xchg = votes + 2 * kRing * SLOTS;                // [SLOTS]
+    uint32_t* xchg = votes + 2 * kRing * SLOTS;                // [2][SLOTS]
 
     const int tid = threadIdx.x;
     const int slot = tid % SLOTS;
@@ -111,293 +135,347 @@ sweep_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wpad, int
     const int chunk = (N + S - 1) / S;
     const int n_lo = min(N, part * chunk);
     const int n_hi = min(N, n_lo + chunk);
-
-    // which word / condition this slot simulates
     constexpr int HALF = SLOTS / 2;
-    int64_t word;
-    int forced_node = -1;
-    uint32_t forced_value = 0;
-    if (MODE == MODE_NORMAL) {
-        word = (int64_t)blockIdx.x * SLOTS + slot;
-    } else {
-        word = (int64_t)blockIdx.x * HALF + (slot % HALF);
-        forced_node = blockIdx.y;
-        forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
-    }
-    const bool word_ok = word < wpad;
-    const uint32_t cellmask = word_ok ? tail_mask(word, n_cells) : 0u;
+    constexpr int NODE_STRIDE = 4 * SLOTS;
 
     for (int n = tid; n < N; n += blockDim.x) {
-        NodeEntry e = make_entry(net_parent, net_lut, n);
+        NodeEntry e = make_entry(args.net_parent, args.net_lut, n);
         NodeOffsets o;
-        o.pa = e.pa * SLOTS; o.pb = e.pb * SLOTS; o.pc = e.pc * SLOTS; o.pad = 0;
+        o.pa = e.pa * NODE_STRIDE; o.pb = e.pb * NODE_STRIDE; o.pc = e.pc * NODE_STRIDE; o.pad = 0;
         offs[n] = o;
         masks[n] = expand_lut(e.lut);
     }
-    for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
+    unsigned int n_items = 0;
+    if (MODE == MODE_CLEANUP) n_items = args.counters[0];
+    const bool deep_ring = MODE == MODE_KOKI ? (args.counters[1] & 1u) != 0 : true;
 
-    auto load_data = [&](uint32_t* dst) {
-        for (int n = n_lo; n < n_hi; ++n)
-            dst[n * SLOTS + slot] = word_ok ? __ldg(planes + (size_t)n * wpad + word) : 0u;
-    };
-    // next value of node n for my slot, reading the state in `st`
-    auto step_node = [&](const uint32_t* st, int n) {
-        const NodeOffsets o = offs[n];
-        const uint4 lo = *reinterpret_cast<const uint4*>(&masks[n].m[0]);
-        const uint4 hi = *reinterpret_cast<const uint4*>(&masks[n].m[4]);
-        const uint32_t a = st[o.pa + slot], b = st[o.pb + slot], c = st[o.pc + slot];
-        uint32_t g0 = lop3<0xCA>(c, lo.y, lo.x), g1 = lop3<0xCA>(c, lo.w, lo.z);
-        uint32_t g2 = lop3<0xCA>(c, hi.y, hi.x), g3 = lop3<0xCA>(c, hi.w, hi.z);
-        uint32_t f = lop3<0xCA>(a, lop3<0xCA>(b, g3, g2), lop3<0xCA>(b, g1, g0));
-        if (MODE == MODE_KOKI && n == forced_node) f = forced_value;
-        return f;
-    };
-
-    uint32_t found = 0;            // lanes with a first repeat inside the window
-    uint32_t lam[kLamPlanes];      // its cycle length, bit-sliced
-#pragma unroll
-    for (int b = 0; b < kLamPlanes; ++b) lam[b] = 0;
-    uint32_t* xs;                  // state frozen at state_mu for found lanes
-    uint32_t* xn;                  // scratch partner of xs
-
-    // ------------------------------------------------------------------ fast path
-    // Ring of the last kRing states: the new state is compared with all of them while it is
-    // computed; the oldest one lives in the very buffer that is being overwritten.  A lane
-    // whose state equals state_{t-d} (smallest d) has its first repeat at (t-d, t): it is at
-    // state_mu right now and is frozen there.  Exact for cycle lengths <= kRing.
-    load_data(buf(kRing - 1));
-    __syncthreads();
-    uint32_t frozen = ~cellmask;
-    int last = kRing - 1;
-    for (int t = 0; t < steps; ++t) {
-        const uint32_t* src = buf((t + kRing - 1) % kRing);
-        uint32_t* dst = buf(t % kRing);
-        const uint32_t* r2 = buf((t + kRing - 2) % kRing);
-        const uint32_t* r3 = buf((t + kRing - 3) % kRing);
-        uint32_t neq1 = 0, neq2 = 0, neq3 = 0, neq4 = 0;
-#pragma unroll 2
-        for (int n = n_lo; n < n_hi; ++n) {
-            const uint32_t f = step_node(src, n);
-            const int i = n * SLOTS + slot;
-            const uint32_t old1 = src[i];
-            neq1 |= f ^ old1;
-            neq2 |= f ^ r2[i];
-            neq3 |= f ^ r3[i];
-            neq4 |= f ^ dst[i];
-            dst[i] = (f & ~frozen) | (old1 & frozen);
+    int batch = blockIdx.x;
+    do {
+        // ------------------------------------------------------------ what this slot simulates
+        int64_t word;
+        int forced_node = -1;
+        uint32_t forced_value = 0;
+        uint32_t cellmask;
+        if (MODE == MODE_NORMAL) {
+            word = (int64_t)blockIdx.x * SLOTS + slot;
+            cellmask = word < wpad ? tail_mask(word, args.n_cells) : 0u;
+        } else if (MODE == MODE_KOKI) {
+            word = (int64_t)blockIdx.x * HALF + (slot % HALF);
+            forced_node = blockIdx.y;
+            forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
+            cellmask = word < wpad ? tail_mask(word, args.n_cells) : 0u;
+        } else {
+            const unsigned int idx = (unsigned int)batch * HALF + (slot % HALF);
+            SweepItem it;
+            it.word = 0; it.node = 0; it.lanes = 0; it.pad = 0;
+            if (idx < n_items) it = args.items[idx];
+            word = it.word;
+            forced_node = it.node;
+            forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
+            cellmask = it.lanes;
         }
-        uint32_t* v = votes + (t & 1) * kRing * SLOTS;
-        if (neq1) atomicOr(v + 0 * SLOTS + slot, neq1);
-        if (neq2) atomicOr(v + 1 * SLOTS + slot, neq2);
-        if (neq3) atomicOr(v + 2 * SLOTS + slot, neq3);
-        if (neq4) atomicOr(v + 3 * SLOTS + slot, neq4);
-        __syncthreads();
-        uint32_t open = ~frozen;
-        // state_{t-d} exists for t >= d only (the raw data state is never compared)
-        uint32_t e1 = t >= 1 ? ~v[0 * SLOTS + slot] & open : 0u;
-        open &= ~e1;
-        uint32_t e2 = t >= 2 ? ~v[1 * SLOTS + slot] & open : 0u;
-        open &= ~e2;
-        uint32_t e3 = t >= 3 ? ~v[2 * SLOTS + slot] & open : 0u;
-        open &= ~e3;
-        uint32_t e4 = t >= 4 ? ~v[3 * SLOTS + slot] & open : 0u;
-        lam[0] |= e1 | e3;
-        lam[1] |= e2 | e3;
-        lam[2] |= e4;
-        frozen |= e1 | e2 | e3 | e4;
-        // the other accumulator set is idle between the two barriers: clear it for step t+1
-        if (part < kRing) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
-        last = t % kRing;
-        if (__syncthreads_and(frozen == 0xFFFFFFFFu)) break;
-    }
-    found = frozen & cellmask;
-    xs = buf(last);
-    xn = buf((last + 1) % kRing);
+        const bool word_ok = word < wpad;
+        for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
 
-    // ------------------------------------------------------------------ slow path
-    // Some lane did not repeat with a cycle length <= kRing inside the window: redo the CTA
-    // with the general scheme (Brent for lambda, two-pointer replay for mu).
-    if (__syncthreads_or((~frozen) != 0)) {
-        if (out_stats && tid == 0) atomicAdd(out_stats, 1ull);
-        uint32_t* cur = buf(0);
-        uint32_t* nxt = buf(1);
-        uint32_t* chk = buf(2);
-        load_data(cur);
-        __syncthreads();
-        uint32_t resolved = ~cellmask;
+        auto at = [&](int k, int n) -> uint32_t& { return state[(n * 4 + k) * SLOTS + slot]; };
+        auto load_data = [&](int k) {
+            for (int n = n_lo; n < n_hi; ++n)
+                at(k, n) = word_ok ? __ldg(args.planes + (size_t)n * wpad + word) : 0u;
+        };
+        // next value of node n for my slot, reading state copy k
+        auto step_node = [&](int k, int n) {
+            const NodeOffsets o = offs[n];
+            const uint4 lo = *reinterpret_cast<const uint4*>(&masks[n].m[0]);
+            const uint4 hi = *reinterpret_cast<const uint4*>(&masks[n].m[4]);
+            const uint32_t* st = state + k * SLOTS + slot;
+            const uint32_t a = st[o.pa], b = st[o.pb], c = st[o.pc];
+            uint32_t g0 = lop3<0xCA>(c, lo.y, lo.x), g1 = lop3<0xCA>(c, lo.w, lo.z);
+            uint32_t g2 = lop3<0xCA>(c, hi.y, hi.x), g3 = lop3<0xCA>(c, hi.w, hi.z);
+            uint32_t f = lop3<0xCA>(a, lop3<0xCA>(b, g3, g2), lop3<0xCA>(b, g1, g0));
+            if (MODE != MODE_NORMAL && n == forced_node) f = forced_value;
+            return f;
+        };
+
+        uint32_t found = 0;        // lanes with a first repeat inside the window
+        uint32_t lam[kLamPlanes];  // its cycle length, bit-sliced
 #pragma unroll
         for (int b = 0; b < kLamPlanes; ++b) lam[b] = 0;
-        uint32_t cyc = 0, found_fp = 0;
-        int chk_time = -1;
-        int t_need = 1;
-        while (t_need - 1 < steps - 2) t_need <<= 1;  // smallest 2^k - 1 >= steps - 2
-        const int t1_max = (t_need - 1) + steps;
-        for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
-        __syncthreads();
-        for (int t = 0; t < t1_max; ++t) {
-            uint32_t neq_prev = 0, neq_chk = 0;
-#pragma unroll 2
-            for (int n = n_lo; n < n_hi; ++n) {
-                const uint32_t f = step_node(cur, n);
-                const int i = n * SLOTS + slot;
-                neq_prev |= f ^ cur[i];
-                if (chk_time >= 0) neq_chk |= f ^ chk[i];
-                nxt[i] = f;
-            }
-            uint32_t* v = votes + (t & 1) * kRing * SLOTS;
-            if (neq_prev) atomicOr(v + slot, neq_prev);
-            if (neq_chk) atomicOr(v + SLOTS + slot, neq_chk);
+        int xs = 0, xn = 1;        // state copy frozen at state_mu for found lanes / its scratch partner
+        uint32_t unresolved = cellmask;
+
+        // -------------------------------------------------------------------- fast path
+        // Ring of the last states: the new state is compared with its predecessors while it is
+        // computed (the oldest one lives in the very copy that is being overwritten).  A lane
+        // whose state equals state_{t-d} (smallest d) has its first repeat at (t-d, t): it is at
+        // state_mu right now and is frozen there.  Exact for cycle lengths <= ring depth (4, or
+        // 2 when the unperturbed run showed no longer cycles; anything else is settled later).
+        if (MODE != MODE_CLEANUP) {
+            load_data(kRing - 1);
             __syncthreads();
-            neq_prev = v[slot];
-            neq_chk = v[SLOTS + slot];
-            if (t >= 1) {
-                uint32_t newly = ~neq_prev & ~resolved;
-                lam[0] |= newly;  // lambda = 1
-                resolved |= newly;
-                if (t <= steps - 1) found_fp |= newly;
-            }
-            if (chk_time >= 0) {
-                uint32_t newly = ~neq_chk & ~resolved;
-                int l = t - chk_time;
-                if (l <= steps - 1) {
-                    planes_set(lam, newly, l);
-                    cyc |= newly;
+            uint32_t frozen = ~cellmask;
+            for (int t = 0; t < steps; ++t) {
+                const int ks = (t + 3) & 3, kd = t & 3, k2 = (t + 2) & 3, k3 = (t + 1) & 3;
+                uint32_t neq1 = 0, neq2 = 0, neq3 = 0, neq4 = 0;
+                if (deep_ring) {
+#pragma unroll 2
+                    for (int n = n_lo; n < n_hi; ++n) {
+                        const uint32_t f = step_node(ks, n);
+                        uint32_t* base = state + n * NODE_STRIDE + slot;
+                        const uint32_t old1 = base[ks * SLOTS];
+                        neq1 |= f ^ old1;
+                        neq2 |= f ^ base[k2 * SLOTS];
+                        neq3 |= f ^ base[k3 * SLOTS];
+                        neq4 |= f ^ base[kd * SLOTS];
+                        base[kd * SLOTS] = (f & ~frozen) | (old1 & frozen);
+                    }
+                } else {
+#pragma unroll 2
+                    for (int n = n_lo; n < n_hi; ++n) {
+                        const uint32_t f = step_node(ks, n);
+                        uint32_t* base = state + n * NODE_STRIDE + slot;
+                        const uint32_t old1 = base[ks * SLOTS];
+                        neq1 |= f ^ old1;
+                        neq2 |= f ^ base[k2 * SLOTS];
+                        base[kd * SLOTS] = (f & ~frozen) | (old1 & frozen);
+                    }
+                    neq3 = neq4 = 0xFFFFFFFFu;
                 }
-                resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
+                uint32_t* v = votes + (t & 1) * kRing * SLOTS;
+                if (neq1) atomicOr(v + 0 * SLOTS + slot, neq1);
+                if (neq2) atomicOr(v + 1 * SLOTS + slot, neq2);
+                if (neq3) atomicOr(v + 2 * SLOTS + slot, neq3);
+                if (neq4) atomicOr(v + 3 * SLOTS + slot, neq4);
+                __syncthreads();
+                uint32_t open = ~frozen;
+                // state_{t-d} exists for t >= d only (the raw data state is never compared)
+                uint32_t e1 = t >= 1 ? ~v[0 * SLOTS + slot] & open : 0u;
+                open &= ~e1;
+                uint32_t e2 = t >= 2 ? ~v[1 * SLOTS + slot] & open : 0u;
+                open &= ~e2;
+                uint32_t e3 = t >= 3 ? ~v[2 * SLOTS + slot] & open : 0u;
+                open &= ~e3;
+                uint32_t e4 = t >= 4 ? ~v[3 * SLOTS + slot] & open : 0u;
+                lam[0] |= e1 | e3;
+                lam[1] |= e2 | e3;
+                lam[2] |= e4;
+                frozen |= e1 | e2 | e3 | e4;
+                // the other accumulator set is idle between the two barriers: clear it for step t+1
+                if (part < kRing) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
+                xs = kd;
+                if (__syncthreads_and(frozen == 0xFFFFFFFFu)) break;
             }
-            if (((t + 1) & t) == 0) {  // t = 2^k - 1: new checkpoint = state_t (own nodes only)
-                for (int n = n_lo; n < n_hi; ++n) chk[n * SLOTS + slot] = nxt[n * SLOTS + slot];
-                chk_time = t;
-            }
-            if (part < 2) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
-            uint32_t* tmp = cur; cur = nxt; nxt = tmp;
-            if (__syncthreads_and(resolved == 0xFFFFFFFFu)) break;
+            xn = (xs + 1) & 3;
+            found = frozen & cellmask;
+            unresolved = ~frozen;
         }
-        if (__syncthreads_or(cyc != 0)) {
-            uint32_t* pc_ = buf(0); uint32_t* pn_ = buf(1);  // P: runs lambda ahead
-            uint32_t* qc_ = buf(2); uint32_t* qn_ = buf(3);  // Q: freezes at state_mu
-            load_data(pc_);
-            load_data(qc_);
+
+        // ---------------------------------------------- KO/KI: hand unsettled cells to the cleanup
+        if (MODE == MODE_KOKI) {
+            if (part == 0) xchg[slot] = unresolved;
+            __syncthreads();
+            const uint32_t both = unresolved | xchg[(slot + HALF) % SLOTS];  // KO and KI travel together
+            if (both && part == 0 && slot < HALF) {
+                const unsigned int idx = atomicAdd(&args.counters[0], 1u);
+                SweepItem it;
+                it.word = (int)word; it.node = forced_node; it.lanes = both; it.pad = 0;
+                args.items[idx] = it;
+            }
+            cellmask &= ~both;
+            found &= cellmask;
+            unresolved = 0;
+            __syncthreads();  // xchg is reused below
+        }
+
+        // -------------------------------------------------------------------- slow path
+        // General scheme for the lanes in `cellmask` that are still open: Brent checkpoints at
+        // t = 2^k - 1 give lambda, then two replays from the data (P runs lambda_cell steps ahead
+        // of Q under per-cell stall masks) give mu and leave Q frozen at state_mu.
+        if (MODE == MODE_CLEANUP || __syncthreads_or(unresolved != 0)) {
+            const int cur0 = 0, nxt0 = 1, chk = 2;
+            int cur = cur0, nxt = nxt0;
             for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
+            load_data(cur);
             __syncthreads();
-            const uint32_t has_lam = planes_ge(lam, 1) & cellmask;
-            for (int s = 0; s < steps; ++s) {
-                uint32_t adv = planes_gt(lam, s) & has_lam;  // lanes that still owe P a step
-                if (!__syncthreads_or(adv != 0)) break;
+            uint32_t resolved = ~cellmask;
+#pragma unroll
+            for (int b = 0; b < kLamPlanes; ++b) lam[b] = 0;
+            uint32_t cyc = 0, found_fp = 0;
+            int chk_time = -1;
+            int t_need = 1;
+            while (t_need - 1 < steps - 2) t_need <<= 1;  // smallest 2^k - 1 >= steps - 2
+            const int t1_max = (t_need - 1) + steps;
+            for (int t = 0; t < t1_max; ++t) {
+                uint32_t neq_prev = 0, neq_chk = 0;
 #pragma unroll 2
                 for (int n = n_lo; n < n_hi; ++n) {
-                    const uint32_t f = step_node(pc_, n);
-                    const int i = n * SLOTS + slot;
-                    pn_[i] = (f & adv) | (pc_[i] & ~adv);
+                    const uint32_t f = step_node(cur, n);
+                    neq_prev |= f ^ at(cur, n);
+                    if (chk_time >= 0) neq_chk |= f ^ at(chk, n);
+                    at(nxt, n) = f;
                 }
+                uint32_t* v = votes + (t & 1) * kRing * SLOTS;
+                if (neq_prev) atomicOr(v + slot, neq_prev);
+                if (neq_chk) atomicOr(v + SLOTS + slot, neq_chk);
                 __syncthreads();
-                uint32_t* tmp = pc_; pc_ = pn_; pn_ = tmp;
+                neq_prev = v[slot];
+                neq_chk = v[SLOTS + slot];
+                if (t >= 1) {
+                    uint32_t newly = ~neq_prev & ~resolved;
+                    lam[0] |= newly;  // lambda = 1
+                    resolved |= newly;
+                    if (t <= steps - 1) found_fp |= newly;
+                }
+                if (chk_time >= 0) {
+                    uint32_t newly = ~neq_chk & ~resolved;
+                    int l = t - chk_time;
+                    if (l <= steps - 1) {
+                        planes_set(lam, newly, l);
+                        cyc |= newly;
+                    }
+                    resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
+                }
+                if (((t + 1) & t) == 0) {  // t = 2^k - 1: new checkpoint = state_t (own nodes only)
+                    for (int n = n_lo; n < n_hi; ++n) at(chk, n) = at(nxt, n);
+                    chk_time = t;
+                }
+                if (part < 2) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
+                int tmp = cur; cur = nxt; nxt = tmp;
+                if (__syncthreads_and(resolved == 0xFFFFFFFFu)) break;
             }
-            uint32_t done = ~has_lam;
-            found = 0;
-            for (int j = 0; j <= steps - 2; ++j) {
-                uint32_t neq = 0;
+            if (__syncthreads_or(cyc != 0)) {
+                int pc_ = 0, pn_ = 1;  // P: runs lambda ahead
+                int qc_ = 2, qn_ = 3;  // Q: freezes at state_mu
+                load_data(pc_);
+                load_data(qc_);
+                for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
+                __syncthreads();
+                const uint32_t has_lam = planes_ge(lam, 1) & cellmask;
+                for (int s = 0; s < steps; ++s) {
+                    uint32_t adv = planes_gt(lam, s) & has_lam;  // lanes that still owe P a step
+                    if (!__syncthreads_or(adv != 0)) break;
 #pragma unroll 2
-                for (int n = n_lo; n < n_hi; ++n) {
-                    const uint32_t fp = step_node(pc_, n);
-                    const uint32_t fq = step_node(qc_, n);
-                    const int i = n * SLOTS + slot;
-                    neq |= fp ^ fq;
-                    pn_[i] = fp;
-                    qn_[i] = (qc_[i] & done) | (fq & ~done);
+                    for (int n = n_lo; n < n_hi; ++n) {
+                        const uint32_t f = step_node(pc_, n);
+                        at(pn_, n) = (f & adv) | (at(pc_, n) & ~adv);
+                    }
+                    __syncthreads();
+                    int tmp = pc_; pc_ = pn_; pn_ = tmp;
                 }
-                uint32_t* v = votes + (j & 1) * kRing * SLOTS;
-                if (neq) atomicOr(v + slot, neq);
-                __syncthreads();
-                neq = v[slot];
-                uint32_t newly = ~neq & ~done;
-                // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
-                uint32_t eligible = ~planes_gt(lam, steps - 1 - j);
-                found |= newly & eligible;
-                done |= newly;
-                if (part == 0) votes[((j + 1) & 1) * kRing * SLOTS + slot] = 0;
-                uint32_t* tmp = pc_; pc_ = pn_; pn_ = tmp;
-                tmp = qc_; qc_ = qn_; qn_ = tmp;
-                if (__syncthreads_and(done == 0xFFFFFFFFu)) break;
+                uint32_t done = ~has_lam;
+                found = 0;
+                for (int j = 0; j <= steps - 2; ++j) {
+                    uint32_t neq = 0;
+#pragma unroll 2
+                    for (int n = n_lo; n < n_hi; ++n) {
+                        const uint32_t fp = step_node(pc_, n);
+                        const uint32_t fq = step_node(qc_, n);
+                        neq |= fp ^ fq;
+                        at(pn_, n) = fp;
+                        at(qn_, n) = (at(qc_, n) & done) | (fq & ~done);
+                    }
+                    uint32_t* v = votes + (j & 1) * kRing * SLOTS;
+                    if (neq) atomicOr(v + slot, neq);
+                    __syncthreads();
+                    neq = v[slot];
+                    uint32_t newly = ~neq & ~done;
+                    // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
+                    uint32_t eligible = ~planes_gt(lam, steps - 1 - j);
+                    found |= newly & eligible;
+                    done |= newly;
+                    if (part == 0) votes[((j + 1) & 1) * kRing * SLOTS + slot] = 0;
+                    int tmp = pc_; pc_ = pn_; pn_ = tmp;
+                    tmp = qc_; qc_ = qn_; qn_ = tmp;
+                    if (__syncthreads_and(done == 0xFFFFFFFFu)) break;
+                }
+                xs = qc_;
+                xn = qn_;
+            } else {
+                found = found_fp;  // every settled lane sits on its fixed point already
+                xs = cur;
+                xn = nxt;
             }
-            xs = qc_;
-            xn = qn_;
+            found &= cellmask;
+        }
+
+        // -------------------------------------------------------------------- outputs
+        if (MODE == MODE_NORMAL) {
+            if (part == 0 && word_ok) {
+                args.np_found[word] = found;
+#pragma unroll
+                for (int b = 0; b < kLamPlanes; ++b) args.np_lam[(size_t)b * wpad + word] = lam[b];
+                uint32_t miss = __popc(~found & cellmask);
+                if (miss) atomicAdd(args.out_missing, (unsigned long long)miss);
+                // tell the KO/KI pass whether the short ring is enough for this data set
+                if ((~found & cellmask) || (planes_ge(lam, 3) & found)) atomicOr(&args.counters[1], 1u);
+            }
+            for (int t = 0; t < steps; ++t) {
+                uint32_t need = found & planes_ge(lam, t);
+                if (!__syncthreads_or(need != 0)) break;
+                if (word_ok)
+                    for (int n = n_lo; n < n_hi; ++n)
+                        args.np_states[((size_t)t * N + n) * wpad + word] = at(xs, n);
+                uint32_t need_next = found & planes_ge(lam, t + 1);
+                if (!__syncthreads_or(need_next != 0)) break;
+#pragma unroll 2
+                for (int n = n_lo; n < n_hi; ++n) at(xn, n) = step_node(xs, n);
+                __syncthreads();
+                int tmp = xs; xs = xn; xn = tmp;
+            }
         } else {
-            found = found_fp;  // every settled lane sits on its fixed point already
-            xs = cur;
-            xn = nxt;
-        }
-        found &= cellmask;
-    }
-
-    // ------------------------------------------------------------------ outputs
-    if (MODE == MODE_NORMAL) {
-        if (part == 0 && word_ok) {
-            np_found[word] = found;
-#pragma unroll
-            for (int b = 0; b < kLamPlanes; ++b) np_lam[(size_t)b * wpad + word] = lam[b];
-            uint32_t miss = __popc(~found & cellmask);
-            if (miss) atomicAdd(out_missing, (unsigned long long)miss);
-        }
-        for (int t = 0; t < steps; ++t) {
-            uint32_t need = found & planes_ge(lam, t);
-            if (!__syncthreads_or(need != 0)) break;
-            if (word_ok)
-                for (int n = n_lo; n < n_hi; ++n)
-                    np_states[((size_t)t * N + n) * wpad + word] = xs[n * SLOTS + slot];
-            uint32_t need_next = found & planes_ge(lam, t + 1);
-            if (!__syncthreads_or(need_next != 0)) break;
-#pragma unroll 2
-            for (int n = n_lo; n < n_hi; ++n) xn[n * SLOTS + slot] = step_node(xs, n);
+            // a cell counts only if its KO run AND its KI run repeat (and the normal one)
+            if (part == 0) xchg[slot] = found;
             __syncthreads();
-            uint32_t* tmp = xs; xs = xn; xn = tmp;
-        }
-        return;
-    }
-
-    // MODE_KOKI: a cell counts only if its KO run AND its KI run repeat (and the normal one)
-    if (part == 0) xchg[slot] = found;
-    __syncthreads();
-    const uint32_t partner = xchg[(slot + HALF) % SLOTS];
-    const uint32_t found_n = word_ok ? __ldg(np_found + word) : 0u;
-    uint32_t lamn[kLamPlanes];
+            const uint32_t partner = xchg[(slot + HALF) % SLOTS];
+            const uint32_t found_n = word_ok ? __ldg(args.np_found + word) : 0u;
+            uint32_t lamn[kLamPlanes];
 #pragma unroll
-    for (int b = 0; b < kLamPlanes; ++b) lamn[b] = word_ok ? __ldg(np_lam + (size_t)b * wpad + word) : 0u;
-    const uint32_t valid = found & partner & found_n;
-    if (part == 0) {
-        uint32_t miss = __popc(~found & cellmask);
-        if (miss) atomicAdd(out_missing + 1 + 2 * forced_node + (slot >= HALF ? 1 : 0), (unsigned long long)miss);
-        if (slot < HALF) {
-            uint32_t bad = __popc(found & partner & ~found_n);
-            if (bad) atomicAdd(out_keyerror, (unsigned long long)bad);
-        }
-    }
-    unsigned long long score = 0;
-    for (int t = 0; t < steps; ++t) {
-        uint32_t act = valid & planes_ge(lam, t) & planes_ge(lamn, t);
-        if (!__syncthreads_or(act != 0)) break;
-        if (act) {
-            uint32_t s = 0;
-            for (int n = n_lo; n < n_hi; ++n) {
-                uint32_t ref = __ldg(np_states + ((size_t)t * N + n) * wpad + word);
-                s += __popc((xs[n * SLOTS + slot] ^ ref) & act);
+            for (int b = 0; b < kLamPlanes; ++b)
+                lamn[b] = word_ok ? __ldg(args.np_lam + (size_t)b * wpad + word) : 0u;
+            const uint32_t valid = found & partner & found_n;
+            if (part == 0) {
+                uint32_t miss = __popc(~found & cellmask);
+                if (miss)
+                    atomicAdd(args.out_missing + 1 + 2 * forced_node + (slot >= HALF ? 1 : 0),
+                              (unsigned long long)miss);
+                if (slot < HALF) {
+                    uint32_t bad = __popc(found & partner & ~found_n);
+                    if (bad) atomicAdd(args.out_keyerror, (unsigned long long)bad);
+                }
             }
-            score += s;
-        }
-        if (t == 0 && !__syncthreads_or((valid & (planes_ge(lam, 2) | planes_ge(lamn, 2))) != 0)) {
-            score *= 2;  // every counted cell: fixed point vs fixed point, t = 1 repeats t = 0
-            break;
-        }
-        uint32_t act_next = valid & planes_ge(lam, t + 1) & planes_ge(lamn, t + 1);
-        if (!__syncthreads_or(act_next != 0)) break;
+            unsigned long long score = 0;
+            for (int t = 0; t < steps; ++t) {
+                uint32_t act = valid & planes_ge(lam, t) & planes_ge(lamn, t);
+                if (!__syncthreads_or(act != 0)) break;
+                if (act) {
+                    uint32_t sc = 0;
+                    for (int n = n_lo; n < n_hi; ++n) {
+                        uint32_t ref = __ldg(args.np_states + ((size_t)t * N + n) * wpad + word);
+                        sc += __popc((at(xs, n) ^ ref) & act);
+                    }
+                    score += sc;
+                }
+                if (t == 0 && !__syncthreads_or((valid & (planes_ge(lam, 2) | planes_ge(lamn, 2))) != 0)) {
+                    score *= 2;  // every counted cell: fixed point vs fixed point, t = 1 repeats t = 0
+                    break;
+                }
+                uint32_t act_next = valid & planes_ge(lam, t + 1) & planes_ge(lamn, t + 1);
+                if (!__syncthreads_or(act_next != 0)) break;
 #pragma unroll 2
-        for (int n = n_lo; n < n_hi; ++n) xn[n * SLOTS + slot] = step_node(xs, n);
-        __syncthreads();
-        uint32_t* tmp = xs; xs = xn; xn = tmp;
-    }
+                for (int n = n_lo; n < n_hi; ++n) at(xn, n) = step_node(xs, n);
+                __syncthreads();
+                int tmp = xs; xs = xn; xn = tmp;
+            }
+            if (MODE == MODE_KOKI) {  // one node per CTA: fold the warp first
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
-    if ((tid & 31) == 0 && score) atomicAdd(out_raw + forced_node, score);
+                for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
+                if ((tid & 31) == 0 && score) atomicAdd(args.out_raw + forced_node, score);
+            } else if (score) {
+                atomicAdd(args.out_raw + forced_node, score);
+            }
+        }
+        batch += gridDim.x;
+        if (MODE == MODE_CLEANUP) __syncthreads();
+    } while (MODE == MODE_CLEANUP && (unsigned int)batch * HALF < n_items);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -453,33 +531,38 @@ trajectories_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wp
 
 static size_t sweep_smem_bytes(int n_nodes, int slots) {
     return (size_t)4 * n_nodes * slots * 4 + (size_t)n_nodes * (sizeof(NodeOffsets) + sizeof(LutMasks)) +
-           (size_t)2 * kRing * slots * 4 + (size_t)slots * 4;
+           (size_t)2 * kRing * slots * 4 + (size_t)2 * slots * 4;
 }
 
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB
 
 template <int SLOTS>
-static int launch_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
-                        const int32_t* net_parent, const uint8_t* net_lut, int steps,
-                        uint32_t* np_states, uint32_t* np_lam, uint32_t* np_found,
-                        unsigned long long* out_raw, unsigned long long* out_missing,
-                        unsigned long long* out_keyerror, unsigned long long* out_stats,
-                        cudaStream_t stream) {
-    size_t smem = sweep_smem_bytes(n_nodes, SLOTS);
-    int64_t n_words = (n_cells + 31) / 32;
-    SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_KOKI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+static int launch_sweep(const SweepArgs& args, cudaStream_t stream) {
+    size_t smem = sweep_smem_bytes(args.n_nodes, SLOTS);
+    int64_t n_words = (args.n_cells + 31) / 32;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_KOKI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_CLEANUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    SCB_CUDA(cudaMemsetAsync(args.counters, 0, 16, stream));
     dim3 grid_n((unsigned)((n_words + SLOTS - 1) / SLOTS));
-    sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(
-        planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found,
-        out_raw, out_missing, out_keyerror, out_stats);
+    sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<normal>");
+    if (const char* ring = getenv("SCB_SWEEP_RING")) {  // experiments: force the KO/KI ring depth
+        if (ring[0] == '4') SCB_CUDA(cudaMemsetAsync(args.counters + 1, 1, 1, stream));
+        if (ring[0] == '2') SCB_CUDA(cudaMemsetAsync(args.counters + 1, 0, 1, stream));
+    }
     constexpr int HALF = SLOTS / 2;
-    dim3 grid_k((unsigned)((n_words + HALF - 1) / HALF), (unsigned)n_nodes);
-    sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(
-        planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found,
-        out_raw, out_missing, out_keyerror, out_stats ? out_stats + 1 : nullptr);
+    dim3 grid_k((unsigned)((n_words + HALF - 1) / HALF), (unsigned)args.n_nodes);
+    sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<koki>");
+    // stragglers, compacted: a persistent grid walks the deferred (word, node) pairs
+    int per_sm = smem <= kMaxDynSmem / 2 ? 2 : 1;
+    sweep_kernel<SLOTS, MODE_CLEANUP><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
+    SCB_LAUNCH_CHECK("sweep_kernel<cleanup>");
     return SCB_OK;
 }
 
@@ -489,7 +572,8 @@ using namespace scb;
 
 extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int steps) {
     if (n_nodes <= 0 || wpad <= 0 || steps <= 0) return 0;
-    return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4;
+    // normal-run states + lambda planes + found plane + one deferred item per (word, node) + counters
+    return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4 + (int64_t)wpad * n_nodes * (int64_t)sizeof(SweepItem) + 16;
 }
 
 extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
@@ -499,23 +583,33 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     SCB_REQUIRE(n_nodes > 0 && n_nodes <= 65535, "ko_ki_sweep: n_nodes=%d out of range", n_nodes);
     SCB_REQUIRE(steps >= 2 && steps <= 64, "ko_ki_sweep: steps=%d must be in [2, 64]", steps);
     SCB_REQUIRE(wpad > 0 && wpad % 4 == 0 && n_cells >= 0 && wpad * 32 >= n_cells, "ko_ki_sweep: wpad must be a positive multiple of 4 covering n_cells");
+    SCB_REQUIRE(wpad < ((int64_t)1 << 31), "ko_ki_sweep: too many words per row");
     SCB_REQUIRE(planes && net_parent && net_lut && scratch && out_raw && out_missing && out_keyerror, "ko_ki_sweep: null pointer");
+    SCB_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 16 == 0, "ko_ki_sweep: scratch must be 16-byte aligned");
     if (n_cells == 0) return SCB_OK;
     int64_t need = scb_ko_ki_sweep_scratch_bytes(n_nodes, wpad, steps);
     if (scratch_bytes < need) {
         set_error("ko_ki_sweep: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
         return SCB_ERR_SCRATCH;
     }
-    uint32_t* np_states = static_cast<uint32_t*>(scratch);
-    uint32_t* np_lam = np_states + (size_t)steps * n_nodes * wpad;
-    uint32_t* np_found = np_lam + (size_t)kLamPlanes * wpad;
-    auto raw = reinterpret_cast<unsigned long long*>(out_raw);
-    auto missing = reinterpret_cast<unsigned long long*>(out_missing);
-    auto keyerr = reinterpret_cast<unsigned long long*>(out_keyerror);
-    if (sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem)
-        return launch_sweep<64>(planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found, raw, missing, keyerr, nullptr, as_stream(stream));
-    if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem)
-        return launch_sweep<32>(planes, n_nodes, wpad, n_cells, net_parent, net_lut, steps, np_states, np_lam, np_found, raw, missing, keyerr, nullptr, as_stream(stream));
+    SweepArgs args;
+    args.planes = planes;
+    args.n_nodes = n_nodes;
+    args.wpad = wpad;
+    args.n_cells = n_cells;
+    args.net_parent = net_parent;
+    args.net_lut = net_lut;
+    args.steps = steps;
+    args.np_states = static_cast<uint32_t*>(scratch);
+    args.np_lam = args.np_states + (size_t)steps * n_nodes * wpad;
+    args.np_found = args.np_lam + (size_t)kLamPlanes * wpad;
+    args.items = reinterpret_cast<SweepItem*>(args.np_found + wpad);  // wpad % 4 == 0 keeps 16-byte alignment
+    args.counters = reinterpret_cast<unsigned int*>(args.items + (size_t)wpad * n_nodes);
+    args.out_raw = reinterpret_cast<unsigned long long*>(out_raw);
+    args.out_missing = reinterpret_cast<unsigned long long*>(out_missing);
+    args.out_keyerror = reinterpret_cast<unsigned long long*>(out_keyerror);
+    if (sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem) return launch_sweep<64>(args, as_stream(stream));
+    if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem) return launch_sweep<32>(args, as_stream(stream));
     set_error("ko_ki_sweep: %d nodes exceed the shared-memory resident limit (%d)", n_nodes, SCB_MAX_SWEEP_NODES);
     return SCB_ERR_UNSUPPORTED;
 }

@@ -242,7 +242,10 @@ def population_fitness(counts, lut, active=None, per_node: bool = False, out=Non
     return out, out_pg
 
 
-def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=None):
+LAST_SWEEP_STATS = {}
+
+
+def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=None, stats: bool = False):
     """Run the 2N+1-condition sweep.  Returns device tensors (raw[N], missing[2N+1], keyerror[1]);
     pass ``out`` (the same triple) to accumulate several cell shards into one result."""
     torch = _torch()
@@ -268,6 +271,10 @@ def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=Non
                                      scratch.data_ptr(), nbytes, out[0].data_ptr(),
                                      out[1].data_ptr(), out[2].data_ptr(), _stream()),
                    "scb_ko_ki_sweep")
+        if stats:  # diagnostic only (synchronises): deferred (word, node) pairs and ring-depth flag
+            tail = scratch[nbytes - 16:nbytes].view(torch.int32).cpu().numpy()
+            LAST_SWEEP_STATS.update(deferred_items=int(tail[0]), deep_ring=bool(tail[1] & 1),
+                                    word_node_pairs=int(((planes.n_cells + 31) // 32) * n))
     return out
 
 

@@ -51,8 +51,9 @@ def main():
     if "sweep" in what:
         net_parents, net_luts = compile_network(nodes)
         for _ in range(max(1, args.reps // 3)):
-            res = device.ko_ki_sweep(planes, net_parents, net_luts, steps=50)
+            res = device.ko_ki_sweep(planes, net_parents, net_luts, steps=50, stats=True)
         torch.cuda.synchronize()
+        print("sweep stats", device.LAST_SWEEP_STATS)
         print("sweep checksum", int(res[0].sum().item()), "missing normal", int(res[1][0].item()))
 
 
