@@ -108,6 +108,13 @@ int scb_population_fitness(const int64_t* counts /*[G][16]*/, int n_groups, int6
                            int64_t* out_diff /*[P]*/, int64_t* out_diff_pg /*[P][G]|NULL*/,
                            scb_stream_t stream);
 
+/* Multi-rule individuals of the historic GA: an individual is a 0/1 string over the concatenated
+ * candidate lists of all nodes; out_diff[p] = sum of task_diff[j] over its set bits, out_nsel[p] =
+ * number of set bits (the GA's complexity penalty).  task_diff is scb_rule_error_table's output. */
+int scb_bitstring_fitness(const int64_t* task_diff /*[T]*/, int64_t n_tasks, int64_t n_individuals,
+                          const uint8_t* bits /*[P][T]*/, int64_t* out_diff /*[P]*/,
+                          int32_t* out_nsel /*[P]*/, scb_stream_t stream);
+
 /* ---- (3) knock-out / knock-in importance sweep --------------------------------------------
  * CalculateImportanceScore.calculate_importance_scores (importance_scores.py:47-143,195-340):
  * synchronous update of the whole network for `steps` steps under 2N+1 conditions (normal,

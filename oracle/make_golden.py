@@ -196,6 +196,58 @@ def golden_traj(ns, tag, specs, dense, cells):
     dump(f"traj_{tag}.json", out)
 
 
+def golden_rule_inference(ns, tag, n_genes, n_cells, seed, extra_rows=3):
+    """The whole ``RuleInference`` constructor: CSV -> sampled cells -> binarised matrix ->
+    Spearman top-3 parents -> nodes -> ruleset (rule_inference.py:21-101)."""
+    import networkx as nx
+    import tempfile
+    rng = np.random.default_rng(seed)
+    specs, planes = synth.synthetic_dataset(n_genes, n_cells, seed, flip=0.08, relax_steps=3)
+    dense = synth.planes_to_dense(planes, n_cells)
+    # expression values: 0/1 pattern times a positive magnitude, plus sub-threshold noise
+    values = dense * rng.uniform(0.5, 3.0, size=dense.shape) + rng.uniform(0, 0.0005, size=dense.shape)
+    names = [f"GENE{i}" for i in range(n_genes)]
+    # a graph with up to 5 incoming edges per node so the top-3 pruning matters; node order == CSV order
+    graph = nx.DiGraph()
+    graph.add_nodes_from(names)
+    edges = []
+    for s in specs:
+        parents = set(s.predecessors)
+        while len(parents) < min(5, n_genes - 1) and rng.random() < 0.7:
+            cand = int(rng.integers(0, n_genes))
+            if cand != s.index:
+                parents.add(cand)
+        for p in sorted(parents):
+            kind = "i" if (p in s.inversions and s.inversions[p]) or rng.random() < 0.1 else "a"
+            key = "interaction" if rng.random() < 0.5 else "signal"
+            graph.add_edge(names[p], names[s.index], **{key: kind})
+            edges.append([names[p], names[s.index], key, kind])
+    lines = ["gene," + ",".join(f"cell{c}" for c in range(n_cells))]
+    for i in range(n_genes):
+        lines.append(names[i] + "," + ",".join(f"{v:.6f}" for v in values[i]))
+    for j in range(extra_rows):   # rows that are not part of the network
+        lines.append(f"OTHER{j}," + ",".join(f"{v:.6f}" for v in rng.uniform(0, 2, n_cells)))
+    csv_text = "\n".join(lines) + "\n"
+    with tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False) as fh:
+        fh.write(csv_text)
+        path = fh.name
+    np.random.seed(seed)
+    ri = ns.rule_inference.RuleInference(path, graph, f"ds_{tag}", f"net_{tag}", ",", list(range(n_genes)),
+                                         binarize_threshold=0.001, sample_cells=True)
+    os.unlink(path)
+    dump(f"ruleinf_{tag}.json", {
+        "seed": seed, "csv": csv_text, "node_names": names, "edges": edges,
+        "node_indices": list(range(n_genes)),
+        "gene_names": list(ri.gene_names), "cv_genes": list(ri.cv_genes),
+        "binarized": rows_to_text(np.asarray(ri.binarized_matrix.todense())),
+        "predecessors": [[int(x) for x in p] for p in ri.predecessors],
+        "nodes": [{"predecessors": [[int(k), v] for k, v in n.predecessors.items()],
+                   "inversions": [[int(k), bool(v)] for k, v in n.inversions.items()],
+                   "best_rule": [n.best_rule[0], [int(i) for i in n.best_rule[1]], n.best_rule[2]],
+                   "best_rule_index": int(n.best_rule_index)} for n in ri.nodes],
+        "ruleset": [[r[0][0], [int(i) for i in r[0][1]], r[0][2], int(r[1]), float(r[2])] for r in ri.ruleset]})
+
+
 def ring_network(n, twist=True):
     """Shift ring G_i <- G_{i-1}; with ``twist`` G_0 <- not G_{n-1} (period 2n Johnson ring)."""
     specs = []
@@ -246,6 +298,9 @@ def main():
     for s, lg in zip(specs, logics):
         s.logic = lg
     golden_sweep(ns, "mixed", specs, synth.planes_to_dense(planes, 48), 41)
+
+    golden_rule_inference(ns, "a", 10, 80, seed=61)
+    golden_rule_inference(ns, "b", 14, 2100, seed=62)
 
     # trajectories
     specs, planes = synth.synthetic_dataset(12, 30, 51, flip=0.3, relax_steps=0)

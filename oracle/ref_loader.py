@@ -109,7 +109,7 @@ def load() -> types.SimpleNamespace:
     sys.path.insert(0, code)
     ns = types.SimpleNamespace(root=root, code_dir=code)
     for name in ("file_paths", "node_class", "network_class", "cell_class",
-                 "rule_determination", "importance_scores"):
+                 "rule_determination", "importance_scores", "rule_inference"):
         # a product alias of the same top-level name must not shadow the reference
         sys.modules.pop(name, None)
         setattr(ns, name, importlib.import_module(name))

@@ -35,6 +35,7 @@ SIGNATURES = {
                                             c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_population_fitness": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p]),
+    "scb_bitstring_fitness": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_ko_ki_sweep_scratch_bytes": (c_int64, [c_int, c_int64, c_int]),
     "scb_ko_ki_sweep": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int,
                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -72,6 +72,35 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     }
 }
 
+// one warp per multi-rule individual: masked sum of the per-rule mismatch table
+__global__ void __launch_bounds__(256)
+bitstring_fitness_kernel(const int64_t* __restrict__ task_diff, int64_t n_tasks, int64_t n_ind,
+                         const uint8_t* __restrict__ bits, int64_t* __restrict__ out_diff,
+                         int32_t* __restrict__ out_nsel) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < n_ind; p += n_warps) {
+        const uint8_t* row = bits + (size_t)p * n_tasks;
+        long long total = 0;
+        int nsel = 0;
+        for (int64_t j = lane; j < n_tasks; j += 32)
+            if (row[j]) {
+                total += task_diff[j];
+                ++nsel;
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            total += __shfl_xor_sync(0xFFFFFFFFu, total, off);
+            nsel += __shfl_xor_sync(0xFFFFFFFFu, nsel, off);
+        }
+        if (lane == 0) {
+            out_diff[p] = total;
+            out_nsel[p] = nsel;
+        }
+    }
+}
+
 // brute force: one warp per task streams the four rows and evaluates the table per word
 __global__ void __launch_bounds__(256)
 error_table_direct_kernel(const uint32_t* __restrict__ planes, int64_t wpad, int64_t n_cells,
@@ -140,6 +169,21 @@ extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64
     population_fitness_kernel<<<(unsigned)blocks, 512, smem, as_stream(stream)>>>(
         counts, n_groups, n_individuals, lut, active, out_diff, out_diff_pg);
     SCB_LAUNCH_CHECK("population_fitness_kernel");
+    return SCB_OK;
+}
+
+extern "C" int scb_bitstring_fitness(const int64_t* task_diff, int64_t n_tasks, int64_t n_individuals,
+                                     const uint8_t* bits, int64_t* out_diff, int32_t* out_nsel,
+                                     scb_stream_t stream) {
+    SCB_REQUIRE(n_tasks >= 0 && n_individuals >= 0, "bitstring_fitness: negative size");
+    if (n_individuals == 0) return SCB_OK;
+    SCB_REQUIRE(task_diff && bits && out_diff && out_nsel, "bitstring_fitness: null pointer");
+    int64_t blocks = (n_individuals + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    bitstring_fitness_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(task_diff, n_tasks, n_individuals,
+                                                                             bits, out_diff, out_nsel);
+    SCB_LAUNCH_CHECK("bitstring_fitness_kernel");
     return SCB_OK;
 }
 

@@ -242,6 +242,23 @@ def population_fitness(counts, lut, active=None, per_node: bool = False, out=Non
     return out, out_pg
 
 
+def bitstring_fitness(task_diff, bits):
+    """(diff[P] int64, nsel[P] int32) device tensors for 0/1 strings over the task table."""
+    torch = _torch()
+    dev = task_diff.device
+    d_bits = _dev(bits if isinstance(bits, torch.Tensor) else np.asarray(bits, dtype=np.uint8), torch.uint8, dev)
+    n_ind, n_tasks = int(d_bits.shape[0]), int(d_bits.shape[1])
+    if n_tasks != task_diff.numel():
+        raise ValueError("bits must be [P, T] with T == len(task_diff)")
+    out = torch.empty(n_ind, dtype=torch.int64, device=dev)
+    nsel = torch.empty(n_ind, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().scb_bitstring_fitness(task_diff.data_ptr(), n_tasks, n_ind, d_bits.data_ptr(),
+                                                    out.data_ptr(), nsel.data_ptr(), _stream()),
+                   "scb_bitstring_fitness")
+    return out, nsel
+
+
 LAST_SWEEP_STATS = {}
 
 

@@ -51,3 +51,106 @@ class PopulationFitness:
         raw = [int(d) / (n_rules * cells) for d in diff]
         fits = [(r + 0.002 * n_rules * current_gen / max_gen,) for r in raw]
         return raw, fits
+
+
+class GeneticAlgorithm:
+    """Seeded GA over multi-rule individuals, fitness on the GPU.
+
+    The GA only survives in the reference as Python-3.6 bytecode; what is restated here are its
+    recovered constants and shapes: 15 generations, start population 50, 25 parents /
+    25 children, crossover 0.1, mutation 0.9, bit-flip 0.5, a node's segment of the bitstring
+    holds 1..5 set bits, fitness = sum(differences) / sum(counts) + 0.002 * (#rules) * gen/max_gen,
+    minimised.  PARITY UNPINNED against the historic code (no runnable source); the fitness values
+    are pinned to ``calculate_error`` through the oracle identity, and the run is a pure function
+    of ``seed`` (NumPy ``default_rng``), which is what "selected rules under a fixed seed and
+    population trajectory" can mean for a reference that no longer ships its GA.
+    """
+
+    def __init__(self, nodes, planes: device.BitPlanes, seed: int = 0, generations: int = 15,
+                 population: int = 50, parents: int = 25, children: int = 25, cx: float = 0.1,
+                 mut: float = 0.9, bit_flip: float = 0.5, max_rules_per_node: int = 5,
+                 counts_hook=None, n_cells=None):
+        self.nodes = list(nodes)
+        self.rng = np.random.default_rng(seed)
+        self.generations, self.population = generations, population
+        self.n_parents, self.n_children = parents, children
+        self.cx, self.mut, self.bit_flip = cx, mut, bit_flip
+        self.max_rules = max_rules_per_node
+        self.scorer = PopulationFitness(self.nodes, planes, counts_hook)
+        self.n_cells = int(n_cells if n_cells is not None else planes.n_cells)
+        tables = self.scorer.candidate_tables()
+        self.logics = [[r[2] for r in node.node_rules] for node in self.nodes]
+        self.offsets = np.concatenate([[0], np.cumsum([len(t) for t in tables])]).astype(np.int64)
+        task_group = np.repeat(np.arange(len(tables)), [len(t) for t in tables])
+        task_lut = np.concatenate(tables)
+        # one table of integer mismatches for every candidate rule of every node: the whole data
+        # set is read once, every generation afterwards only touches this table
+        self.task_diff = device.rule_error_table(self.scorer.counts, task_group, task_lut)
+        self.task_error = self.task_diff.cpu().numpy() / self.n_cells
+        self.history = []
+
+    # ---- individuals -------------------------------------------------------------------
+    def _repair(self, bits):
+        for n in range(len(self.nodes)):
+            seg = bits[self.offsets[n]:self.offsets[n + 1]]
+            on = np.flatnonzero(seg)
+            if on.size == 0:
+                seg[self.rng.integers(0, seg.size)] = 1
+            elif on.size > self.max_rules:
+                seg[self.rng.choice(on, on.size - self.max_rules, replace=False)] = 0
+        return bits
+
+    def _random_individual(self):
+        bits = self.rng.integers(0, 2, size=int(self.offsets[-1])).astype(np.uint8)
+        return self._repair(bits)
+
+    def evaluate(self, pop, generation):
+        diff, nsel = device.bitstring_fitness(self.task_diff, np.ascontiguousarray(pop))
+        diff, nsel = diff.cpu().numpy(), nsel.cpu().numpy()
+        raw = diff / (nsel.astype(np.int64) * self.n_cells)
+        return raw, raw + 0.002 * nsel * generation / self.generations
+
+    def _crossover(self, a, b):
+        cut = np.sort(self.rng.choice(len(self.nodes) + 1, 2, replace=False))
+        lo, hi = self.offsets[cut[0]], self.offsets[cut[1]]
+        child = a.copy()
+        child[lo:hi] = b[lo:hi]          # two-point crossover on node boundaries
+        return child
+
+    def _mutate(self, bits):
+        # nodes whose selected rules fit worst are the most likely to be rewritten
+        err = np.array([self.task_error[self.offsets[n]:self.offsets[n + 1]][
+            bits[self.offsets[n]:self.offsets[n + 1]] == 1].mean() for n in range(len(self.nodes))])
+        weight = err + 1e-9
+        node = self.rng.choice(len(self.nodes), p=weight / weight.sum())
+        seg = bits[self.offsets[node]:self.offsets[node + 1]]
+        flip = self.rng.random(seg.size) < self.bit_flip
+        seg[flip] ^= 1
+        return self._repair(bits)
+
+    def run(self):
+        pop = np.stack([self._random_individual() for _ in range(self.population)])
+        for gen in range(self.generations):
+            raw, fit = self.evaluate(pop, gen)
+            order = np.lexsort((np.arange(len(fit)), fit))     # best first, ties by position
+            keep = pop[order[:self.n_parents]]
+            self.history.append({"generation": gen, "best": float(fit[order[0]]),
+                                 "mean": float(fit.mean()), "best_raw": float(raw[order[0]])})
+            kids = []
+            for _ in range(self.n_children):
+                i, j = self.rng.integers(0, len(keep), 2)
+                child = self._crossover(keep[i], keep[j]) if self.rng.random() < self.cx else keep[i].copy()
+                if self.rng.random() < self.mut:
+                    child = self._mutate(child)
+                kids.append(child)
+            pop = np.concatenate([keep, np.stack(kids)])
+        raw, fit = self.evaluate(pop, self.generations)
+        best = pop[int(np.lexsort((np.arange(len(fit)), fit))[0])]
+        self.population_bits = pop
+        self.final_raw, self.final_fitness = raw, fit
+        rules = []
+        for n, node in enumerate(self.nodes):
+            seg = np.flatnonzero(best[self.offsets[n]:self.offsets[n + 1]])
+            pick = seg[np.argmin(self.task_error[self.offsets[n] + seg])]   # first minimum
+            rules.append((node.name, self.logics[n][int(pick)], float(self.task_error[self.offsets[n] + pick])))
+        return {"best_individual": best, "rules": rules, "history": self.history}

@@ -190,3 +190,70 @@ def test_counts_are_additive_over_cell_shards(cuda):
         parts = parts + device.rule_counts(planes.word_slice(lo, hi), targets, parents)
     assert (whole == parts).all()
     assert int(whole.sum()) == 40 * 100_000
+
+
+@pytest.mark.parametrize("name", golden_names("ruleinf_"))
+def test_rule_inference_constructor_golden(cuda, name, tmp_path):
+    """The whole RuleInference constructor (CSV -> sample -> binarise -> Spearman top-3 -> GPU rule
+    scoring) against the reference run with the same NumPy seed; then the pickle round trip."""
+    import pickle
+
+    import networkx as nx
+
+    import scbonita2_b200
+    from scbonita2_b200 import file_paths
+    from scbonita2_b200.rule_inference import RuleInference
+    logging.disable(logging.CRITICAL)
+    file_paths.set_output_root(str(tmp_path / "out"))
+    g = golden(name)
+    graph = nx.DiGraph()
+    graph.add_nodes_from(g["node_names"])
+    for src, dst, key, kind in g["edges"]:
+        graph.add_edge(src, dst, **{key: kind})
+    csv_path = tmp_path / "data.csv"
+    csv_path.write_text(g["csv"])
+    np.random.seed(g["seed"])
+    ri = RuleInference(str(csv_path), graph, "ds", "net", ",", g["node_indices"],
+                       binarize_threshold=0.001, sample_cells=True)
+    assert list(ri.gene_names) == g["gene_names"] and list(ri.cv_genes) == g["cv_genes"]
+    assert (np.asarray(ri.binarized_matrix.todense()).astype(np.uint8) == matrix_of(g["binarized"])).all()
+    assert [[int(x) for x in p] for p in ri.predecessors] == g["predecessors"]
+    for node, want in zip(ri.nodes, g["nodes"]):
+        assert [[k, v] for k, v in node.predecessors.items()] == want["predecessors"]
+        assert [[k, bool(v)] for k, v in node.inversions.items()] == want["inversions"]
+        assert [node.best_rule[0], [int(i) for i in node.best_rule[1]], node.best_rule[2]] == want["best_rule"]
+        assert node.best_rule_index == want["best_rule_index"]
+    got = [[r[0][0], [int(i) for i in r[0][1]], r[0][2], int(r[1]), float(r[2])] for r in ri.ruleset]
+    assert got == g["ruleset"]
+    # pickles carry the reference's module paths once the aliases are installed
+    scbonita2_b200.install_aliases()
+    blob = pickle.dumps(ri)
+    assert b"rule_inference" in blob and b"node_class" in blob and b"scbonita2_b200" not in blob
+    back = pickle.loads(blob)
+    assert [n.best_rule for n in back.nodes] == [n.best_rule for n in ri.nodes]
+
+
+def test_genetic_algorithm_seeded_and_fitness_pinned(cuda):
+    """GA loop (next-1): deterministic under a seed, elitist, and its GPU fitness equals the oracle
+    formula sum(calculate_error)/sum(count) + 0.002 * #rules * gen/max_gen."""
+    from scbonita2_b200 import device
+    from scbonita2_b200.genetic_algorithm import GeneticAlgorithm
+    specs, planes_np = synth.synthetic_dataset(8, 120, 71, flip=0.03, relax_steps=3)
+    dense = synth.planes_to_dense(planes_np, 120).astype(float)
+    runs = []
+    for _ in range(2):
+        ga = GeneticAlgorithm(nodes_of(specs), device.BitPlanes.from_packed(planes_np, 120), seed=5,
+                              generations=6, population=20, parents=10, children=10)
+        runs.append((ga, ga.run()))
+    (ga, res), (_, res2) = runs
+    assert res["rules"] == res2["rules"] and res["history"] == res2["history"]
+    assert (res["best_individual"] == res2["best_individual"]).all()
+    bests = [h["best_raw"] for h in res["history"]]
+    assert all(b2 <= b1 + 1e-15 for b1, b2 in zip(bests, bests[1:]))     # parents survive
+    # oracle check of three final individuals
+    logics = ga.logics
+    for p in (0, 7, 19):
+        bits = ga.population_bits[p]
+        sel = [list(np.flatnonzero(bits[ga.offsets[n]:ga.offsets[n + 1]])) for n in range(8)]
+        raw, fit = ref_port.population_fitness(ga.nodes, logics, [sel], dense, ga.generations, ga.generations)
+        assert ga.final_raw[p] == raw[0] and ga.final_fitness[p] == fit[0][0]

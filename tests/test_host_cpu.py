@@ -74,3 +74,29 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "ref_port" not in text and "ref_loader" not in text, f
+
+
+def test_aliases_make_pickles_reference_compatible():
+    import pickle
+    import sys
+
+    import scbonita2_b200
+    from scbonita2_b200.cell_class import Cell, CellPopulation
+    from scbonita2_b200.network_class import Network
+    saved = {k: sys.modules.get(k) for k in ("node_class", "network_class", "cell_class")}
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        scbonita2_b200.install_aliases()
+        net = Network("hsa04370")
+        net.nodes = [Node("G0", 0, {}, {})]
+        blob = pickle.dumps((net, CellPopulation([Cell(0)])))
+        for path in (b"network_class", b"node_class", b"cell_class"):
+            assert path in blob
+        assert b"scbonita2_b200" not in blob
+        back, cells = pickle.loads(blob)
+        assert back.nodes[0].predecessors == {0: "G0"} and cells.cells[0].index == 0
+    finally:
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
