@@ -229,6 +229,29 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     const int l = lane & 3;                         // lane in quad
     const int n_quads = (blockDim.x >> 5) * 8;
 
+    // Work split: groups (and rows) can be dealt round-robin into n_classes classes; CTA b belongs
+    // to class b % n_classes and walks ALL tiles for its class (n_classes = 1 by default).
+    const int cls = blockIdx.x % n_classes;
+    const int cta_in_cls = blockIdx.x / n_classes;
+    const int ctas_in_cls = (gridDim.x - cls + n_classes - 1) / n_classes;
+    // one thread starts the copy of `tile` into `stage` (a tile past the end just completes the phase)
+    auto issue_tile = [&](int stage, int tile) {
+        s_tile[stage] = tile;
+        if (tile >= n_tiles) {
+            mbar_arrive(&full[stage]);
+            return;
+        }
+        uint32_t* dst = stages + (size_t)stage * stage_words;
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows_alloc * kTileWords * 4));
+        for (int b = 0; b < n_boxes; ++b)
+            tma_load_2d(dst + (size_t)b * box_rows * kTileWords, &tmap, tile * kTileWords, b * box_rows, &full[stage]);
+    };
+    // the first kStages tiles of a CTA are static: get them moving before any other set-up work
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < kStages; ++s) issue_tile(s, cta_in_cls + s * ctas_in_cls);
+    }
     for (int i = tid; i < n_acc; i += blockDim.x) cta_acc[i] = 0;
     if (tid < 4) s_arity_count[tid] = s_arity_fill[tid] = 0;
     __syncthreads();
@@ -245,45 +268,16 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     for (int s = 0; s < kStages; ++s)               // the all-zero row of every stage
         for (int i = tid; i < kTileWords; i += blockDim.x)
             stages[(size_t)s * stage_words + (size_t)rows_alloc * kTileWords + i] = 0;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
 
-    // producer (warp 0): start the copy of `tile` into `stage`.  The first kStages tiles of a CTA
-    // are static (blockIdx.x + s*gridDim.x); later ones come from the global ticket, which is
-    // claimed one tile ahead so that its L2 round trip hides behind the arithmetic.
-    // Work split: groups (and rows) are dealt round-robin into n_classes classes so that one
-    // class fits one round of the CTA's quads; CTA b belongs to class b % n_classes and walks ALL
-    // tiles for its class.  More tiles per CTA amortise the prologue and the final atomics, which
-    // dominated when every CTA carried every group (profiles/r1_counts_v2_ncu.txt).
-    const int cls = blockIdx.x % n_classes;
-    const int cta_in_cls = blockIdx.x / n_classes;
-    const int ctas_in_cls = (gridDim.x - cls + n_classes - 1) / n_classes;
+    // later tiles come from the global ticket, claimed one tile ahead so that its L2 round trip
+    // hides behind the arithmetic
     const int first_dynamic = kStages * ctas_in_cls;
     auto claim = [&]() {
         int t = 0;
         if (lane == 0) t = first_dynamic + (int)atomicAdd(&tickets[cls], 1u);
         return t;  // valid in lane 0
     };
-    auto produce = [&](int stage, int tile_lane0) {
-        const int tile = __shfl_sync(0xFFFFFFFFu, tile_lane0, 0);
-        if (lane == 0) s_tile[stage] = tile;
-        if (tile >= n_tiles) {
-            if (lane == 0) mbar_arrive(&full[stage]);  // nothing to copy: just complete the phase
-            return;
-        }
-        uint32_t* dst = stages + (size_t)stage * stage_words;
-        if (lane == 0) {
-            mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows_alloc * kTileWords * 4));
-            for (int b = 0; b < n_boxes; ++b)
-                tma_load_2d(dst + (size_t)b * box_rows * kTileWords, &tmap, tile * kTileWords, b * box_rows,
-                            &full[stage]);
-        }
-    };
-    if (warp == 0)
-        for (int s = 0; s < kStages; ++s) produce(s, cta_in_cls + s * ctas_in_cls);
 
     for (int it = 0;; ++it) {
         const int stage = it % kStages;
@@ -335,7 +329,7 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
             else if (arity == 1) group_terms<1>(pa, pb, pc, pt, widx, l, live, dst);
         }
         __syncthreads();  // every reader is done with this stage
-        if (warp == 0) produce(stage, next_tile);
+        if (tid == 0) issue_tile(stage, next_tile);
     }
     __syncthreads();
 

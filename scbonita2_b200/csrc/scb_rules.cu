@@ -27,24 +27,52 @@ __global__ void error_table_kernel(const int64_t* __restrict__ counts, int64_t n
 
 // One warp per individual, lanes stride over the groups.  With
 //   diff(L) = sum_k c[k][1] + sum_{k: L_k = 1} (c[k][0] - c[k][1])
-// the CTA stages base[g] and delta[k][g] in shared memory, laid out [k][g] so that lanes with
-// consecutive g read consecutive words (no bank conflicts).
+// the CTA stages base[g] and, per table nibble, the 16 partial sums of the deltas:
+//   diff(L) = base[g] + lo[L & 15][g] + hi[L >> 4][g]            (2 shared loads per pair)
+// laid out [nibble][g] so lanes with consecutive g mostly hit distinct banks.  The nibble sums are
+// kept in int32 when every count fits (always, below 2^31 cells); otherwise the CTA falls back to
+// the eight int64 deltas.
 __global__ void __launch_bounds__(512)
 population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int64_t n_ind,
                           const uint8_t* __restrict__ lut, const uint8_t* __restrict__ active,
                           int64_t* __restrict__ out_diff, int64_t* __restrict__ out_diff_pg) {
-    extern __shared__ __align__(16) long long s_tab[];  // base[G] | delta[8][G]
+    extern __shared__ __align__(16) long long s_tab[];  // base[G] | delta[8][G] (int64)  or  lo/hi[32][G] (int32)
     long long* base = s_tab;
     long long* delta = s_tab + n_groups;
+    int* nib = reinterpret_cast<int*>(s_tab + n_groups);  // aliases delta: only one form is built
+    int wide = 0;
     for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
         const int64_t* c = counts + (size_t)g * 16;
-        long long b = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) wide |= (int)((unsigned long long)c[k] >> 31 != 0);
+    }
+    wide = __syncthreads_or(wide);
+    for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
+        const int64_t* c = counts + (size_t)g * 16;
+        long long b = 0, d[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             b += c[2 * k + 1];
-            delta[k * n_groups + g] = c[2 * k] - c[2 * k + 1];
+            d[k] = c[2 * k] - c[2 * k + 1];
         }
         base[g] = b;
+        if (wide) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) delta[k * n_groups + g] = d[k];
+        } else {
+#pragma unroll
+            for (int v = 0; v < 16; ++v) {
+                long long lo = 0, hi = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if ((v >> k) & 1) {
+                        lo += d[k];
+                        hi += d[k + 4];
+                    }
+                nib[v * n_groups + g] = (int)lo;
+                nib[(16 + v) * n_groups + g] = (int)hi;
+            }
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -59,9 +87,13 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
             if (!act || act[g]) {
                 const uint32_t table = row[g];
                 d = base[g];
+                if (wide) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if ((table >> k) & 1u) d += delta[k * n_groups + g];
+                    for (int k = 0; k < 8; ++k)
+                        if ((table >> k) & 1u) d += delta[k * n_groups + g];
+                } else {
+                    d += nib[(table & 15u) * n_groups + g] + nib[(16u + (table >> 4)) * n_groups + g];
+                }
             }
             if (out_diff_pg) out_diff_pg[(size_t)p * n_groups + g] = d;
             total += d;
@@ -156,9 +188,9 @@ extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64
     SCB_REQUIRE(n_groups > 0 && n_individuals >= 0, "population_fitness: bad size");
     if (n_individuals == 0) return SCB_OK;
     SCB_REQUIRE(counts && lut && out_diff, "population_fitness: null pointer");
-    size_t smem = (size_t)n_groups * 9 * sizeof(long long);
+    size_t smem = (size_t)n_groups * 17 * sizeof(long long);  // base + max(8 int64 deltas, 32 int32 nibble sums)
     if (smem > 200 * 1024) {
-        set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 72));
+        set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 136));
         return SCB_ERR_UNSUPPORTED;
     }
     if (smem > 48 * 1024)

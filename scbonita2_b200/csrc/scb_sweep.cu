@@ -86,12 +86,6 @@ struct __align__(16) NodeOffsets {
     int pa, pb, pc, pad;
 };
 
-// a (word, node) pair whose KO or KI run has cells the fast path could not settle
-struct __align__(16) SweepItem {
-    int word, node;
-    uint32_t lanes;
-    int pad;
-};
 
 struct SweepArgs {
     const uint32_t* planes;
@@ -103,14 +97,17 @@ struct SweepArgs {
     uint32_t* np_states;            // [steps][N][wpad]  normal-run states from each cell's own mu
     uint32_t* np_lam;               // [6][wpad]         lambda of the normal run, bit-sliced
     uint32_t* np_found;             // [wpad]
-    SweepItem* items;               // deferred (word, node) pairs
-    unsigned int* counters;         // [0] number of items, [1] flags (bit 0: normal run has lambda >= 3)
+    int32_t* cells;                 // [N][cap] deferred cells per knocked node (KO and KI travel together)
+    int64_t cap;
+    unsigned int* node_count;       // [N] entries used in each list
+    unsigned int* counters;         // [1] flags (bit 0: normal run has lambda >= 3 or an unsettled cell)
     unsigned long long* out_raw;
     unsigned long long* out_missing;
     unsigned long long* out_keyerror;
 };
 
 enum { MODE_NORMAL = 0, MODE_KOKI = 1, MODE_CLEANUP = 2 };
+
 constexpr int kRing = 4;  // state copies per slot: ring of the fast path, P/Q pairs of the slow path
 
 // State layout in shared memory: word (node n, copy k, slot s) lives at ((n*4 + k)*SLOTS + s), so
@@ -128,6 +125,13 @@ sweep_kernel(const SweepArgs args) {
     LutMasks* masks = reinterpret_cast<LutMasks*>(offs + N);                           // [N]
     uint32_t* votes = reinterpret_cast<uint32_t*>(masks + N);  // [2][kRing][SLOTS] OR-accumulators
     uint32_t* xchg = votes + 2 * kRing * SLOTS;                // [2][SLOTS]
+    // cleanup only: the 32 cell indices behind each virtual word, their normal-run planes, and
+    // the per-node batch prefix
+    constexpr int HALF = SLOTS / 2;
+    int* cellidx = reinterpret_cast<int*>(xchg + 2 * SLOTS);   // [HALF][32]
+    uint32_t* nrm = reinterpret_cast<uint32_t*>(cellidx + HALF * 32);  // [1 + kLamPlanes][HALF]
+    int* pre = reinterpret_cast<int*>(nrm + (1 + kLamPlanes) * HALF);  // [N + 1]
+    __shared__ int s_node;
 
     const int tid = threadIdx.x;
     const int slot = tid % SLOTS;
@@ -135,8 +139,8 @@ sweep_kernel(const SweepArgs args) {
     const int chunk = (N + S - 1) / S;
     const int n_lo = min(N, part * chunk);
     const int n_hi = min(N, n_lo + chunk);
-    constexpr int HALF = SLOTS / 2;
     constexpr int NODE_STRIDE = 4 * SLOTS;
+    constexpr int BATCH_CELLS = HALF * 32;  // cells of one node a cleanup batch simulates
 
     for (int n = tid; n < N; n += blockDim.x) {
         NodeEntry e = make_entry(args.net_parent, args.net_lut, n);
@@ -145,12 +149,26 @@ sweep_kernel(const SweepArgs args) {
         offs[n] = o;
         masks[n] = expand_lut(e.lut);
     }
-    unsigned int n_items = 0;
-    if (MODE == MODE_CLEANUP) n_items = args.counters[0];
+    int total_batches = 0;
+    if (MODE == MODE_CLEANUP) {
+        if (tid == 0) {
+            int acc = 0;
+            for (int k = 0; k < N; ++k) {
+                pre[k] = acc;
+                int64_t cnt = args.node_count[k];
+                if (cnt > args.cap) cnt = args.cap;
+                acc += (int)((cnt + BATCH_CELLS - 1) / BATCH_CELLS);
+            }
+            pre[N] = acc;
+        }
+        __syncthreads();
+        total_batches = pre[N];
+    }
     const bool deep_ring = MODE == MODE_KOKI ? (args.counters[1] & 1u) != 0 : true;
 
     int batch = blockIdx.x;
     do {
+        if (MODE == MODE_CLEANUP && batch >= total_batches) break;
         // ------------------------------------------------------------ what this slot simulates
         int64_t word;
         int forced_node = -1;
@@ -165,22 +183,53 @@ sweep_kernel(const SweepArgs args) {
             forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
             cellmask = word < wpad ? tail_mask(word, args.n_cells) : 0u;
         } else {
-            const unsigned int idx = (unsigned int)batch * HALF + (slot % HALF);
-            SweepItem it;
-            it.word = 0; it.node = 0; it.lanes = 0; it.pad = 0;
-            if (idx < n_items) it = args.items[idx];
-            word = it.word;
-            forced_node = it.node;
+            // a virtual word: 32 deferred cells of one node, gathered from anywhere in the data
+            if (tid == 0) {
+                int lo = 0, hi = N;  // largest k with pre[k] <= batch
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (pre[mid] <= batch) lo = mid; else hi = mid;
+                }
+                s_node = lo;
+            }
+            __syncthreads();
+            forced_node = s_node;
             forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
-            cellmask = it.lanes;
+            int64_t cnt = args.node_count[forced_node];
+            if (cnt > args.cap) cnt = args.cap;
+            const int64_t first = ((int64_t)(batch - pre[forced_node]) * HALF + (slot % HALF)) * 32;
+            if (slot < HALF)
+                for (int ln = part; ln < 32; ln += S)
+                    cellidx[slot * 32 + ln] =
+                        first + ln < cnt ? args.cells[(size_t)forced_node * args.cap + first + ln] : -1;
+            __syncthreads();
+            word = 0;
+            cellmask = 0;
+            for (int ln = 0; ln < 32; ++ln) cellmask |= (uint32_t)(cellidx[(slot % HALF) * 32 + ln] >= 0) << ln;
         }
         const bool word_ok = word < wpad;
+        // bit `ln` of the result = bit of cell cellidx[ln] in the bitplane row `row` (cleanup only)
+        auto gather_bits = [&](const uint32_t* __restrict__ row, uint32_t lanes) {
+            uint32_t w = 0;
+            const int* idx = cellidx + (slot % HALF) * 32;
+            while (lanes) {
+                const int ln = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
+                const int c = idx[ln];
+                w |= ((__ldg(row + (c >> 5)) >> (c & 31)) & 1u) << ln;
+            }
+            return w;
+        };
         for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
 
         auto at = [&](int k, int n) -> uint32_t& { return state[(n * 4 + k) * SLOTS + slot]; };
         auto load_data = [&](int k) {
-            for (int n = n_lo; n < n_hi; ++n)
-                at(k, n) = word_ok ? __ldg(args.planes + (size_t)n * wpad + word) : 0u;
+            for (int n = n_lo; n < n_hi; ++n) {
+                if (MODE == MODE_CLEANUP)
+                    at(k, n) = gather_bits(args.planes + (size_t)n * wpad, cellmask);
+                else
+                    at(k, n) = word_ok ? __ldg(args.planes + (size_t)n * wpad + word) : 0u;
+            }
         };
         // next value of node n for my slot, reading state copy k
         auto step_node = [&](int k, int n) {
@@ -210,13 +259,14 @@ sweep_kernel(const SweepArgs args) {
         // state_mu right now and is frozen there.  Exact for cycle lengths <= ring depth (4, or
         // 2 when the unperturbed run showed no longer cycles; anything else is settled later).
         if (MODE != MODE_CLEANUP) {
+            const bool deep = deep_ring;
             load_data(kRing - 1);
             __syncthreads();
             uint32_t frozen = ~cellmask;
             for (int t = 0; t < steps; ++t) {
                 const int ks = (t + 3) & 3, kd = t & 3, k2 = (t + 2) & 3, k3 = (t + 1) & 3;
                 uint32_t neq1 = 0, neq2 = 0, neq3 = 0, neq4 = 0;
-                if (deep_ring) {
+                if (deep) {
 #pragma unroll 2
                     for (int n = n_lo; n < n_hi; ++n) {
                         const uint32_t f = step_node(ks, n);
@@ -274,15 +324,26 @@ sweep_kernel(const SweepArgs args) {
             if (part == 0) xchg[slot] = unresolved;
             __syncthreads();
             const uint32_t both = unresolved | xchg[(slot + HALF) % SLOTS];  // KO and KI travel together
-            if (both && part == 0 && slot < HALF) {
-                const unsigned int idx = atomicAdd(&args.counters[0], 1u);
-                SweepItem it;
-                it.word = (int)word; it.node = forced_node; it.lanes = both; it.pad = 0;
-                args.items[idx] = it;
+            if (part == 0 && slot < HALF) {
+                uint32_t deferred = 0;
+                if (both) {  // reserve room in the node's list; a full list keeps the cells here
+                    const unsigned int k = __popc(both);
+                    const unsigned int at0 = atomicAdd(&args.node_count[forced_node], k);
+                    if ((int64_t)at0 + k <= args.cap) {
+                        int32_t* dst = args.cells + (size_t)forced_node * args.cap + at0;
+                        for (uint32_t m = both; m; m &= m - 1) *dst++ = (int32_t)(word * 32 + __ffs(m) - 1);
+                        deferred = both;
+                    } else {
+                        atomicSub(&args.node_count[forced_node], k);
+                    }
+                }
+                xchg[SLOTS + slot] = deferred;
             }
-            cellmask &= ~both;
+            __syncthreads();
+            const uint32_t deferred = xchg[SLOTS + (slot % HALF)];
+            cellmask &= ~deferred;
             found &= cellmask;
-            unresolved = 0;
+            unresolved = both & ~deferred;
             __syncthreads();  // xchg is reused below
         }
 
@@ -426,11 +487,23 @@ sweep_kernel(const SweepArgs args) {
             if (part == 0) xchg[slot] = found;
             __syncthreads();
             const uint32_t partner = xchg[(slot + HALF) % SLOTS];
-            const uint32_t found_n = word_ok ? __ldg(args.np_found + word) : 0u;
+            uint32_t found_n;
             uint32_t lamn[kLamPlanes];
+            if (MODE == MODE_CLEANUP) {
+                // thread (slot < HALF, part q) assembles plane q of the normal run for its virtual word
+                if (slot < HALF && part < 1 + kLamPlanes)
+                    nrm[part * HALF + slot] = gather_bits(
+                        part == 0 ? args.np_found : args.np_lam + (size_t)(part - 1) * wpad, cellmask);
+                __syncthreads();
+                found_n = nrm[slot % HALF];
 #pragma unroll
-            for (int b = 0; b < kLamPlanes; ++b)
-                lamn[b] = word_ok ? __ldg(args.np_lam + (size_t)b * wpad + word) : 0u;
+                for (int b = 0; b < kLamPlanes; ++b) lamn[b] = nrm[(1 + b) * HALF + (slot % HALF)];
+            } else {
+                found_n = word_ok ? __ldg(args.np_found + word) : 0u;
+#pragma unroll
+                for (int b = 0; b < kLamPlanes; ++b)
+                    lamn[b] = word_ok ? __ldg(args.np_lam + (size_t)b * wpad + word) : 0u;
+            }
             const uint32_t valid = found & partner & found_n;
             if (part == 0) {
                 uint32_t miss = __popc(~found & cellmask);
@@ -449,7 +522,8 @@ sweep_kernel(const SweepArgs args) {
                 if (act) {
                     uint32_t sc = 0;
                     for (int n = n_lo; n < n_hi; ++n) {
-                        uint32_t ref = __ldg(args.np_states + ((size_t)t * N + n) * wpad + word);
+                        const uint32_t* row = args.np_states + ((size_t)t * N + n) * wpad;
+                        uint32_t ref = MODE == MODE_CLEANUP ? gather_bits(row, act) : __ldg(row + word);
                         sc += __popc((at(xs, n) ^ ref) & act);
                     }
                     score += sc;
@@ -465,17 +539,14 @@ sweep_kernel(const SweepArgs args) {
                 __syncthreads();
                 int tmp = xs; xs = xn; xn = tmp;
             }
-            if (MODE == MODE_KOKI) {  // one node per CTA: fold the warp first
+            // one node per CTA (and per cleanup batch): fold the warp first
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
-                if ((tid & 31) == 0 && score) atomicAdd(args.out_raw + forced_node, score);
-            } else if (score) {
-                atomicAdd(args.out_raw + forced_node, score);
-            }
+            for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
+            if ((tid & 31) == 0 && score) atomicAdd(args.out_raw + forced_node, score);
         }
         batch += gridDim.x;
         if (MODE == MODE_CLEANUP) __syncthreads();
-    } while (MODE == MODE_CLEANUP && (unsigned int)batch * HALF < n_items);
+    } while (MODE == MODE_CLEANUP);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -531,7 +602,17 @@ trajectories_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wp
 
 static size_t sweep_smem_bytes(int n_nodes, int slots) {
     return (size_t)4 * n_nodes * slots * 4 + (size_t)n_nodes * (sizeof(NodeOffsets) + sizeof(LutMasks)) +
-           (size_t)2 * kRing * slots * 4 + (size_t)2 * slots * 4;
+           (size_t)2 * kRing * slots * 4 + (size_t)2 * slots * 4 +
+           (size_t)(slots / 2) * 32 * 4 + (size_t)(1 + kLamPlanes) * (slots / 2) * 4 + (size_t)(n_nodes + 1) * 4;
+}
+
+// room per node for deferred cells; a full list only means its cells are settled in place
+static int64_t sweep_list_capacity(int64_t n_cells) {
+    int64_t div = 8;
+    if (const char* e = getenv("SCB_SWEEP_CAP_DIV")) div = atoi(e) > 0 ? atoi(e) : 8;  // experiments
+    int64_t cap = n_cells / div;
+    if (cap < 65536) cap = 65536;
+    return cap < n_cells ? cap : n_cells;
 }
 
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB
@@ -547,7 +628,7 @@ static int launch_sweep(const SweepArgs& args, cudaStream_t stream) {
         SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_CLEANUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    SCB_CUDA(cudaMemsetAsync(args.counters, 0, 16, stream));
+    SCB_CUDA(cudaMemsetAsync(args.node_count, 0, (size_t)args.n_nodes * 4 + 16, stream));
     dim3 grid_n((unsigned)((n_words + SLOTS - 1) / SLOTS));
     sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<normal>");
@@ -572,8 +653,9 @@ using namespace scb;
 
 extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int steps) {
     if (n_nodes <= 0 || wpad <= 0 || steps <= 0) return 0;
-    // normal-run states + lambda planes + found plane + one deferred item per (word, node) + counters
-    return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4 + (int64_t)wpad * n_nodes * (int64_t)sizeof(SweepItem) + 16;
+    // normal-run states + lambda planes + found plane + per-node lists of deferred cells + counters
+    return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4 +
+           (int64_t)n_nodes * sweep_list_capacity(wpad * 32) * 4 + (int64_t)n_nodes * 4 + 16;
 }
 
 extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
@@ -583,7 +665,7 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     SCB_REQUIRE(n_nodes > 0 && n_nodes <= 65535, "ko_ki_sweep: n_nodes=%d out of range", n_nodes);
     SCB_REQUIRE(steps >= 2 && steps <= 64, "ko_ki_sweep: steps=%d must be in [2, 64]", steps);
     SCB_REQUIRE(wpad > 0 && wpad % 4 == 0 && n_cells >= 0 && wpad * 32 >= n_cells, "ko_ki_sweep: wpad must be a positive multiple of 4 covering n_cells");
-    SCB_REQUIRE(wpad < ((int64_t)1 << 31), "ko_ki_sweep: too many words per row");
+    SCB_REQUIRE(wpad * 32 < ((int64_t)1 << 31), "ko_ki_sweep: at most 2^31-1 cells per call (shard the cells)");
     SCB_REQUIRE(planes && net_parent && net_lut && scratch && out_raw && out_missing && out_keyerror, "ko_ki_sweep: null pointer");
     SCB_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 16 == 0, "ko_ki_sweep: scratch must be 16-byte aligned");
     if (n_cells == 0) return SCB_OK;
@@ -603,8 +685,10 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.np_states = static_cast<uint32_t*>(scratch);
     args.np_lam = args.np_states + (size_t)steps * n_nodes * wpad;
     args.np_found = args.np_lam + (size_t)kLamPlanes * wpad;
-    args.items = reinterpret_cast<SweepItem*>(args.np_found + wpad);  // wpad % 4 == 0 keeps 16-byte alignment
-    args.counters = reinterpret_cast<unsigned int*>(args.items + (size_t)wpad * n_nodes);
+    args.cap = sweep_list_capacity(wpad * 32);
+    args.cells = reinterpret_cast<int32_t*>(args.np_found + wpad);
+    args.node_count = reinterpret_cast<unsigned int*>(args.cells + (size_t)n_nodes * args.cap);
+    args.counters = args.node_count + n_nodes;  // followed by 16 spare bytes
     args.out_raw = reinterpret_cast<unsigned long long*>(out_raw);
     args.out_missing = reinterpret_cast<unsigned long long*>(out_missing);
     args.out_keyerror = reinterpret_cast<unsigned long long*>(out_keyerror);

@@ -289,9 +289,9 @@ def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=Non
                                      out[1].data_ptr(), out[2].data_ptr(), _stream()),
                    "scb_ko_ki_sweep")
         if stats:  # diagnostic only (synchronises): deferred (word, node) pairs and ring-depth flag
-            tail = scratch[nbytes - 16:nbytes].view(torch.int32).cpu().numpy()
-            LAST_SWEEP_STATS.update(deferred_items=int(tail[0]), deep_ring=bool(tail[1] & 1),
-                                    word_node_pairs=int(((planes.n_cells + 31) // 32) * n))
+            tail = scratch[nbytes - 16 - 4 * n:nbytes].view(torch.int32).cpu().numpy()
+            LAST_SWEEP_STATS.update(deferred_cells=int(tail[:n].sum()), deferred_max_per_node=int(tail[:n].max()),
+                                    deep_ring=bool(tail[n + 1] & 1), cell_node_pairs=int(planes.n_cells) * n)
     return out
 
 

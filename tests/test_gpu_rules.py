@@ -257,3 +257,18 @@ def test_genetic_algorithm_seeded_and_fitness_pinned(cuda):
         sel = [list(np.flatnonzero(bits[ga.offsets[n]:ga.offsets[n + 1]])) for n in range(8)]
         raw, fit = ref_port.population_fitness(ga.nodes, logics, [sel], dense, ga.generations, ga.generations)
         assert ga.final_raw[p] == raw[0] and ga.final_fitness[p] == fit[0][0]
+
+
+def test_population_fitness_wide_counts_path(cuda):
+    """Counts at or above 2^31 (multi-billion-cell totals after an all-reduce) take the int64 path."""
+    from scbonita2_b200 import device
+    torch = cuda
+    rng = np.random.default_rng(8)
+    counts_np = rng.integers(0, 1 << 40, (9, 16)).astype(np.int64)
+    counts = torch.from_numpy(counts_np).cuda()
+    lut = rng.integers(0, 256, (70, 9)).astype(np.uint8)
+    diff, diff_pg = device.population_fitness(counts, lut, per_node=True)
+    want = np.array([[np_diff(counts_np[g], int(lut[p, g])) for g in range(9)] for p in range(70)])
+    assert (diff_pg.cpu().numpy() == want).all() and (diff.cpu().numpy() == want.sum(axis=1)).all()
+    tab = device.rule_error_table(counts, np.arange(9), lut[3]).cpu().numpy()
+    assert (tab == want[3]).all()
