@@ -330,7 +330,7 @@ def run_ours(args):
         for _ in range(args.steps):
             flush_l2()
             e0, e1 = ev(), ev()
-            torch.cuda.synchronize()
+            barrier()
             e0.record()
             graph.replay()
             e1.record()

@@ -692,7 +692,9 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.out_raw = reinterpret_cast<unsigned long long*>(out_raw);
     args.out_missing = reinterpret_cast<unsigned long long*>(out_missing);
     args.out_keyerror = reinterpret_cast<unsigned long long*>(out_keyerror);
-    if (sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem) return launch_sweep<64>(args, as_stream(stream));
+    const char* force = getenv("SCB_SWEEP_SLOTS");  // experiments
+    const bool prefer32 = force && force[0] == '3';
+    if (!prefer32 && sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem) return launch_sweep<64>(args, as_stream(stream));
     if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem) return launch_sweep<32>(args, as_stream(stream));
     set_error("ko_ki_sweep: %d nodes exceed the shared-memory resident limit (%d)", n_nodes, SCB_MAX_SWEEP_NODES);
     return SCB_ERR_UNSUPPORTED;
