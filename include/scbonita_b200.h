@@ -143,6 +143,15 @@ int scb_trajectories(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t 
                      const int32_t* net_parent /*[N][3]*/, const uint8_t* net_lut /*[N]*/,
                      int steps, uint8_t* out /*[M][N][steps]*/, scb_stream_t stream);
 
+/* Same with one node forced to 0 (knock-out) or 1 (knock-in) from the first update on
+ * (CalculateImportanceScore.vectorized_run_simulation, importance_scores.py:47-111);
+ * forced_node = -1 forces nothing. */
+int scb_trajectories_forced(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
+                            const int64_t* cell_idx /*[M]*/, int64_t n_selected,
+                            const int32_t* net_parent /*[N][3]*/, const uint8_t* net_lut /*[N]*/,
+                            int steps, int forced_node, int forced_value,
+                            uint8_t* out /*[M][N][steps]*/, scb_stream_t stream);
+
 /* ---- host-buffer entry points (the end-to-end path; all pointers HOST) ---------------------
  * One workspace owns the device buffers of one (device, stream); not thread-safe. */
 typedef struct scb_workspace scb_workspace;

@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(256)
 trajectories_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wpad,
                     const int64_t* __restrict__ cell_idx, int64_t n_selected,
                     const int32_t* __restrict__ net_parent, const uint8_t* __restrict__ net_lut,
-                    int steps, uint8_t* __restrict__ out) {
+                    int steps, int forced_node, uint32_t forced_value, uint8_t* __restrict__ out) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = n_nodes;
     const int S = blockDim.x / kTrajSlots;
@@ -589,6 +589,7 @@ trajectories_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wp
     for (int t = 0; t < steps; ++t) {
         for (int n = n_lo; n < n_hi; ++n) {
             uint32_t f = eval_node<kTrajSlots>(tab[n], cur, slot);
+            if (n == forced_node) f = forced_value;  // knock-out / knock-in from the first update on
             nxt[n * kTrajSlots + slot] = f;
             for (int b = 0; b < 32; ++b) {
                 int64_t m = first + b;
@@ -704,6 +705,16 @@ extern "C" int scb_trajectories(const uint32_t* planes, int n_nodes, int64_t wpa
                                 const int64_t* cell_idx, int64_t n_selected,
                                 const int32_t* net_parent, const uint8_t* net_lut, int steps,
                                 uint8_t* out, scb_stream_t stream) {
+    return scb_trajectories_forced(planes, n_nodes, wpad, n_cells, cell_idx, n_selected, net_parent, net_lut,
+                                   steps, -1, 0, out, stream);
+}
+
+extern "C" int scb_trajectories_forced(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
+                                       const int64_t* cell_idx, int64_t n_selected,
+                                       const int32_t* net_parent, const uint8_t* net_lut, int steps,
+                                       int forced_node, int forced_value, uint8_t* out,
+                                       scb_stream_t stream) {
+    SCB_REQUIRE(forced_node >= -1 && forced_node < n_nodes, "trajectories: forced node out of range");
     SCB_REQUIRE(n_nodes > 0 && steps >= 1 && n_selected >= 0, "trajectories: bad size");
     SCB_REQUIRE(wpad > 0 && wpad * 32 >= n_cells, "trajectories: wpad does not cover n_cells");
     if (n_selected == 0) return SCB_OK;
@@ -716,7 +727,8 @@ extern "C" int scb_trajectories(const uint32_t* planes, int n_nodes, int64_t wpa
     SCB_CUDA(cudaFuncSetAttribute(trajectories_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t slots = (n_selected + 31) / 32;
     trajectories_kernel<<<(unsigned)((slots + kTrajSlots - 1) / kTrajSlots), 256, smem, as_stream(stream)>>>(
-        planes, n_nodes, wpad, cell_idx, n_selected, net_parent, net_lut, steps, out);
+        planes, n_nodes, wpad, cell_idx, n_selected, net_parent, net_lut, steps, forced_node,
+        forced_value ? 0xFFFFFFFFu : 0u, out);
     SCB_LAUNCH_CHECK("trajectories_kernel");
     return SCB_OK;
 }

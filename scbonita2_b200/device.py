@@ -295,8 +295,10 @@ def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=Non
     return out
 
 
-def trajectories(planes: BitPlanes, cell_idx, net_parent, net_lut, steps: int = 20):
-    """uint8 ``[M, N, steps]`` device tensor of states after 1..steps updates."""
+def trajectories(planes: BitPlanes, cell_idx, net_parent, net_lut, steps: int = 20,
+                 forced_node: int = -1, forced_value: int = 0):
+    """uint8 ``[M, N, steps]`` device tensor of states after 1..steps updates; optionally with one
+    node knocked out (forced 0) or in (forced 1) from the first update on."""
     torch = _torch()
     dev = planes.words.device
     n = planes.n_rows
@@ -307,10 +309,10 @@ def trajectories(planes: BitPlanes, cell_idx, net_parent, net_lut, steps: int = 
     d_lut = _dev(np.asarray(net_lut, dtype=np.uint8).reshape(-1), torch.uint8, dev)
     out = torch.empty((int(idx.numel()), n, steps), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().scb_trajectories(planes.words.data_ptr(), n, planes.wpad,
-                                               planes.n_cells, idx.data_ptr(), int(idx.numel()),
-                                               parents.data_ptr(), d_lut.data_ptr(), steps,
-                                               out.data_ptr(), _stream()), "scb_trajectories")
+        _lib.check(_lib.lib().scb_trajectories_forced(
+            planes.words.data_ptr(), n, planes.wpad, planes.n_cells, idx.data_ptr(), int(idx.numel()),
+            parents.data_ptr(), d_lut.data_ptr(), steps, int(forced_node), int(forced_value),
+            out.data_ptr(), _stream()), "scb_trajectories_forced")
     return out
 
 

@@ -129,6 +129,54 @@ class CalculateImportanceScore:
             node.importance_score = scaled[node.name]
         return scaled
 
+    # ---- attractor dumps (reference intermediates; off the hot path) ------------------------
+    def vectorized_run_simulation(self, knockout_node=None, knockin_node=None):
+        """{cell position: bool array (nodes, lambda+1)} — the attractors the reference pickles as
+        ``knockout_results_{node}.pkl`` / ``knockin_results_{node}.pkl`` / ``normal_signaling.pkl``
+        (``importance_scores.py:47-132``).  The simulation runs on the GPU
+        (``scb_trajectories_forced``); the first-repeat search over the returned 50-step histories
+        is plain NumPy on the host.  ``calculate_importance_scores`` never needs these dumps (the
+        sweep kernel scores in place); they exist for consumers of the intermediate files and as an
+        independent cross-check of the sweep."""
+        if any(node.calculation_function is None for node in self.nodes):
+            self.prepare_nodes()
+        parents, luts = compile_network(self.nodes)
+        names = [node.name for node in self.nodes]
+        forced, value = -1, 0
+        if knockout_node in names:      # the reference tests the knock-out name first (:66-70)
+            forced, value = names.index(knockout_node), 0
+        elif knockin_node in names:
+            forced, value = names.index(knockin_node), 1
+        cells = np.arange(self.planes.n_cells)
+        hist = device.trajectories(self.planes, cells, parents, luts, steps=self.STEPS,
+                                   forced_node=forced, forced_value=value).cpu().numpy()   # [cells, N, steps]
+        attractors = {}
+        for cell in range(hist.shape[0]):
+            states = hist[cell]
+            for i in range(1, states.shape[1]):
+                same = np.flatnonzero((states[:, :i] == states[:, i:i + 1]).all(axis=0))
+                if same.size:
+                    attractors[cell] = states[:, same[0]:i + 1].astype(bool)
+                    break
+        return attractors
+
+    def write_intermediates(self):
+        """Write ``normal_signaling.pkl`` and the per-node knock-out / knock-in pickles into
+        ``intermediate_dir`` exactly where the reference keeps them (:219-246)."""
+        self.save_to_disk(self.vectorized_run_simulation(), f'{self.intermediate_dir}/normal_signaling.pkl')
+        for node in self.nodes:
+            self.save_to_disk(self.vectorized_run_simulation(knockout_node=node.name),
+                              f'{self.intermediate_dir}/knockout_results_{node.name}.pkl')
+            self.save_to_disk(self.vectorized_run_simulation(knockin_node=node.name),
+                              f'{self.intermediate_dir}/knockin_results_{node.name}.pkl')
+
+    @staticmethod
+    def align_attractors(ko_attractor, ki_attractor):
+        """Trim two (nodes, steps) arrays to their common extent (``importance_scores.py:325-340``)."""
+        rows = min(ko_attractor.shape[0], ki_attractor.shape[0])
+        cols = min(ko_attractor.shape[1], ki_attractor.shape[1])
+        return ko_attractor[:rows, :cols], ki_attractor[:rows, :cols]
+
     @staticmethod
     def save_to_disk(data, filename):
         with open(filename, 'wb') as f:

@@ -165,3 +165,40 @@ def test_trajectories_many_cells_vs_oracle(cuda):
     got = simulate_trajectories(nodes, dense, cells)
     hist = ref_port.run_simulation(nodes, dense[:, cells].astype(bool), 20)   # (steps, nodes, cells)
     assert (got == np.transpose(hist, (2, 1, 0)).astype(np.uint8)).all()
+
+
+def test_attractor_dumps_cross_check_the_sweep(cuda, tmp_path):
+    """next-2: the attractor dicts the reference pickles (rebuilt from GPU trajectories + a host
+    first-repeat search) must reproduce the sweep kernel's integer totals through the reference's
+    own scoring recipe (align + XOR + sum)."""
+    import pickle
+
+    from scbonita2_b200 import file_paths
+    from scbonita2_b200.importance_scores import CalculateImportanceScore
+    file_paths.set_output_root(str(tmp_path / "out"))
+    g = golden("sweep_mixed.json")       # cycle lengths 4 and 12, transients
+    dense = matrix_of(g["matrix"])
+    nodes = nodes_of(g["specs"], with_logic=True)
+    for node, logic in zip(nodes, g["logics"]):
+        node.best_rule[2] = logic
+    calc = CalculateImportanceScore(nodes, dense, "net", "ds", cells=None)
+    raw, missing, keyerr = calc.run_sweep()
+    normal = calc.vectorized_run_simulation()
+    lens = [normal[c].shape[1] if c in normal else 0 for c in range(dense.shape[1])]
+    assert sorted(lens) == sorted(g["len_normal"])      # same cells, sample order differs
+    totals = []
+    for node in nodes:
+        ko = calc.vectorized_run_simulation(knockout_node=node.name)
+        ki = calc.vectorized_run_simulation(knockin_node=node.name)
+        total = 0
+        for cell in range(dense.shape[1]):
+            if cell in ko and cell in ki:
+                for pert in (ki[cell], ko[cell]):
+                    a, b = calc.align_attractors(pert, normal[cell])
+                    total += int(np.sum(a ^ b))
+        totals.append(total)
+    assert totals == raw.tolist() == g["raw"]
+    calc.write_intermediates()
+    with open(f"{calc.intermediate_dir}/knockout_results_{nodes[0].name}.pkl", "rb") as fh:
+        back = pickle.load(fh)
+    assert set(back) == set(calc.vectorized_run_simulation(knockout_node=nodes[0].name))
