@@ -81,6 +81,27 @@ int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_
                     int n_groups, const int32_t* target_row /*[G]*/,
                     const int32_t* parent_row /*[G][3]*/, void* scratch, int64_t scratch_bytes,
                     int64_t* out_counts /*[G][16]*/, scb_stream_t stream);
+/* Same with flags.  The kernel always leaves `scratch` zeroed behind it; a caller that zeroed the
+ * scratch once (or reuses it after a successful call, in stream order) passes
+ * SCB_COUNTS_SCRATCH_CLEAN and the call enqueues no memset. */
+#define SCB_COUNTS_SCRATCH_CLEAN 1
+int scb_rule_counts_ex(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
+                       int n_groups, const int32_t* target_row /*[G]*/,
+                       const int32_t* parent_row /*[G][3]*/, void* scratch, int64_t scratch_bytes,
+                       int64_t* out_counts /*[G][16]*/, int flags, scb_stream_t stream);
+
+/* Repeated passes over the same groups (GA generations, the cell shards of one pathway): the
+ * cell-independent part -- groups sorted by arity, shared-memory row offsets, which group also
+ * counts its target row -- is built once into a caller-owned `plan` buffer
+ * (scb_rule_counts_plan_bytes bytes, 16-byte aligned); scb_rule_counts_run then enqueues ONE
+ * kernel per 1024 groups and nothing else.  scb_rule_counts == plan_build + run. */
+int64_t scb_rule_counts_plan_bytes(int n_rows, int n_groups);
+int scb_rule_counts_plan_build(int n_rows, int n_groups, const int32_t* target_row /*[G]*/,
+                               const int32_t* parent_row /*[G][3]*/, void* plan, int64_t plan_bytes,
+                               scb_stream_t stream);
+int scb_rule_counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
+                        int n_groups, const void* plan, void* scratch, int64_t scratch_bytes,
+                        int64_t* out_counts /*[G][16]*/, int flags, scb_stream_t stream);
 
 /* difference for T (group, lut) tasks: the batched calculate_error.  count == n_cells. */
 int scb_rule_error_table(const int64_t* counts /*[G][16]*/, int n_groups, int64_t n_tasks,

@@ -17,6 +17,8 @@ _I64P = POINTER(c_int64)
 _U8P = POINTER(c_uint8)
 _U32P = POINTER(c_uint32)
 
+SCB_COUNTS_SCRATCH_CLEAN = 1
+
 # name -> (restype, argtypes).  Device pointers are passed as integers (c_void_p).
 SIGNATURES = {
     "scb_abi_version": (c_int, []),
@@ -29,6 +31,12 @@ SIGNATURES = {
     "scb_rule_counts_scratch_bytes": (c_int64, [c_int, c_int]),
     "scb_rule_counts": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p,
                                 c_void_p, c_int64, c_void_p, c_void_p]),
+    "scb_rule_counts_ex": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    "scb_rule_counts_plan_bytes": (c_int64, [c_int, c_int]),
+    "scb_rule_counts_plan_build": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "scb_rule_counts_run": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64,
+                                    c_void_p, c_int, c_void_p]),
     "scb_rule_error_table": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
     "scb_rule_error_table_direct": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p,

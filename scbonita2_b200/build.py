@@ -37,6 +37,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    if os.environ.get("SCB_TRACE"):   # phase timestamps of rule_counts_kernel (tools/trace_counts.py)
+        cmd += ["-DSCB_TRACE"]
+    if os.environ.get("SCB_CONSUMER_WARPS"):   # experiments
+        cmd += ["-DSCB_CONSUMER_WARPS=" + os.environ["SCB_CONSUMER_WARPS"]]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:

@@ -7,19 +7,10 @@
 // every GA individual.  They are obtained as popcounts of the 15 non-empty AND-subsets of the
 // four bitplane rows (4 single rows, 11 multi-variable terms) followed by a Moebius inversion.
 //
-// Kernel structure (B200):
-//  * persistent CTAs pull 32-word cell tiles from a global ticket; a tile (all rows x 128 B) is
-//    staged in shared memory by the TMA engine: one cp.async.bulk per row, completion on an
-//    mbarrier, two stages, so the copy of tile i+1 overlaps the arithmetic on tile i;
-//  * a QUAD of lanes owns one node per tile: lane l reads words 4*(j^q)+l, j = 0..7 (q = quad
-//    in warp), which keeps the 8 quads of a warp on disjoint banks;
-//  * the eight words of a term are compressed with a Harley-Seal carry-save tree (7 CSA = 14
-//    LOP3) into ones/twos/fours/eights, so a term costs 4 POPC instead of 8: POPC issues on the
-//    quarter-rate XU pipe, which was the measured limiter of the plain version
-//    (profiles/r1_counts_v1_ncu.txt);
-//  * quad partials are folded with two shuffles on 16-bit packed pairs, accumulated per CTA in
-//    shared memory, added to global int64 accumulators with atomics (integer adds: exact and
-//    order-free) and inverted by the last CTA to finish.  No second kernel.
+// Kernel structure (B200): see rule_counts_kernel below -- one persistent CTA per SM, a ring of
+// TMA-filled stages (cp.async.bulk.tensor.2d, full/empty mbarriers), 24 consumer warps drawing
+// work items from a shared counter, Harley-Seal style carry-save popcounts, shared-memory
+// atomics per CTA, global int64 atomics per launch, Moebius inversion in the last CTA.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -29,10 +20,15 @@ namespace scb {
 
 constexpr int kTermsPerGroup = 11;  // multi-variable AND terms
 constexpr int kTileWords = 32;      // words per row per tile (128 B)
-constexpr int kStages = 2;
-constexpr int kCountThreads = 256;
-constexpr int kMaxClasses = 15;
-constexpr int kTicketBytes = (kMaxClasses + 1) * 4;
+constexpr int kMaxStages = 8;
+constexpr int kInFlight = 3;        // bulk copies outstanding per SM
+#ifndef SCB_CONSUMER_WARPS
+#define SCB_CONSUMER_WARPS 24
+#endif
+constexpr int kConsumerWarps = SCB_CONSUMER_WARPS;
+constexpr int kCountThreads = (kConsumerWarps + 1) * 32;  // + the producer warp
+constexpr int kTicketBytes = 16;
+constexpr int kMaxGroupsPerLaunch = 1024;  // groups are processed in slices so the per-CTA accumulators fit in shared memory
 
 // term order (bit3=T, bit2=A, bit1=B, bit0=C): masks of the 11 multi-variable subsets
 #define SCB_TERM_MASKS {0x6 /*AB*/, 0x5 /*AC*/, 0x3 /*BC*/, 0x7 /*ABC*/, 0xC /*AT*/, 0xA /*BT*/, \
@@ -84,84 +80,181 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
         : "memory");
 }
 
+#ifdef SCB_TRACE
+__device__ int g_dbg;  // experiments: bit 0 = consumers skip the arithmetic, bit 1 = producer skips the copies
+__device__ long long g_trace[256][12];
+#define SCB_TRACE_AT(slot, cond) do { if (cond) g_trace[blockIdx.x & 255][slot] = clock64(); } while (0)
+#else
+#define SCB_TRACE_AT(slot, cond) do { } while (0)
+#endif
+
+// barrier among the consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+}
+
 // carry-save adder: (sum, carry) of three words, 2 LOP3
 __device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
     sum = lop3<0x96>(a, b, c);
     carry = lop3<0xE8>(a, b, c);
 }
 
-// popcount of eight words through a Harley-Seal tree: 7 CSA + 4 POPC
+// popcount of eight words: four carry-save adders take seven of them down to one word of weight
+// 1, one of weight 2 and one of weight 4; the eighth is counted as it is (8 LOP3 + 4 POPC; the
+// weighted sum is finished arithmetically).  POPC issues on the quarter-rate XU pipe, LOP3 on the
+// half-rate ALU pipe: with the eight ANDs that form a term this split keeps the two equally busy.
 __device__ __forceinline__ uint32_t popc8(const uint32_t (&x)[8]) {
-    uint32_t ones, twos_a, twos_b, twos_c, twos_d, twos, fours_a, fours_b, fours, eights;
-    csa(twos_a, ones, x[0], x[1], x[2]);
-    csa(twos_b, ones, ones, x[3], x[4]);
-    csa(twos_c, ones, ones, x[5], x[6]);
-    twos_d = ones & x[7];
-    ones ^= x[7];
-    csa(fours_a, twos, twos_a, twos_b, twos_c);
-    fours_b = twos & twos_d;
-    twos ^= twos_d;
-    eights = fours_a & fours_b;
-    fours = fours_a ^ fours_b;
-    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+    uint32_t o1, t1, o2, t2, o3, t3, tt, f1;
+    csa(t1, o1, x[0], x[1], x[2]);
+    csa(t2, o2, x[3], x[4], x[5]);
+    csa(t3, o3, o1, o2, x[6]);
+    csa(f1, tt, t1, t2, t3);
+    return __popc(o3) + __popc(x[7]) + 2 * __popc(tt) + 4 * __popc(f1);
 }
 
 // number of parent slots a group binds when they are packed to the left (A, AB, ABC); any other
 // pattern takes the general three-parent path
-__device__ __forceinline__ int group_arity(int ra, int rb, int rc) {
+__host__ __device__ __forceinline__ int group_arity(int ra, int rb, int rc) {
     if (rc >= 0) return 3;
     if (rb >= 0) return ra >= 0 ? 2 : 3;
     return ra >= 0 ? 1 : 0;
 }
 
-// The AND-subset popcounts of one group over one 32-word tile, taken by a quad (lane l reads the
-// eight words widx[]), folded across the quad and added to the CTA accumulators dst[0..10]
-// (term order of SCB_TERM_MASKS).  ARITY selects which terms can be non-zero.
+// ---- the plan: everything about a set of groups that does not depend on the cells --------------
+// Built once per (groups, n_rows) by a one-CTA kernel, read by every pass:
+//   header   int32[4]     {n_groups, n_rows, n_orphans, 0}
+//   desc     uint4[G]     groups sorted by arity (widest first): byte offsets of rows A, B, C, T inside a
+//                         stage; .x carries arity (bits 0-1) and "owns its target row" (bit 2)
+//   order    uint16[G]    original group index of sorted position
+//   orphans  uint16[R]    rows that are no group's target (their popcounts need items of their own)
+//   target   int32[G], parents int32[3G]   copies for the final inversion
+//   owner    uint32[R]    build-time temporary
+struct PlanLayout {
+    size_t desc, order, orphans, target, parents, owner, bytes;
+};
+__host__ __device__ inline size_t pad16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline PlanLayout plan_layout(int n_rows, int n_groups) {
+    PlanLayout L;
+    L.desc = 16;
+    L.order = L.desc + (size_t)n_groups * 16;
+    L.orphans = L.order + pad16((size_t)n_groups * 2);
+    L.target = L.orphans + pad16((size_t)n_rows * 2);
+    L.parents = L.target + pad16((size_t)n_groups * 4);
+    L.owner = L.parents + pad16((size_t)n_groups * 12);
+    L.bytes = L.owner + pad16((size_t)n_rows * 4);
+    return L;
+}
+constexpr uint32_t kDescOwn = 4u;
+
+__global__ void __launch_bounds__(256)
+rule_counts_plan_kernel(int n_rows, int n_groups, int zero_row, const int32_t* __restrict__ target_row,
+                        const int32_t* __restrict__ parent_row, unsigned char* __restrict__ plan) {
+    const PlanLayout L = plan_layout(n_rows, n_groups);
+    int* header = reinterpret_cast<int*>(plan);
+    uint4* desc = reinterpret_cast<uint4*>(plan + L.desc);
+    unsigned short* order = reinterpret_cast<unsigned short*>(plan + L.order);
+    unsigned short* orphans = reinterpret_cast<unsigned short*>(plan + L.orphans);
+    int* target = reinterpret_cast<int*>(plan + L.target);
+    int* parents = reinterpret_cast<int*>(plan + L.parents);
+    unsigned int* owner = reinterpret_cast<unsigned int*>(plan + L.owner);
+    __shared__ int s_count[4], s_fill[4], s_orphans;
+    const int tid = threadIdx.x;
+    if (tid < 4) s_count[tid] = s_fill[tid] = 0;
+    if (tid == 0) s_orphans = 0;
+    for (int r = tid; r < n_rows; r += blockDim.x) owner[r] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (int g = tid; g < n_groups; g += blockDim.x) {
+        target[g] = target_row[g];
+        for (int k = 0; k < 3; ++k) parents[3 * g + k] = parent_row[3 * g + k];
+        atomicAdd(&s_count[group_arity(parent_row[3 * g], parent_row[3 * g + 1], parent_row[3 * g + 2])], 1);
+    }
+    __syncthreads();
+    // counting sort by arity, widest first; the first sorted group that targets a row owns it
+    for (int g = tid; g < n_groups; g += blockDim.x) {
+        const int ra = parent_row[3 * g], rb = parent_row[3 * g + 1], rc = parent_row[3 * g + 2];
+        const int ar = group_arity(ra, rb, rc);
+        int pos = atomicAdd(&s_fill[ar], 1);
+        for (int k = 3; k > ar; --k) pos += s_count[k];
+        order[pos] = (unsigned short)g;
+        const uint32_t row_bytes = kTileWords * 4;
+        desc[pos] = make_uint4((uint32_t)(ra < 0 ? zero_row : ra) * row_bytes | (uint32_t)ar,
+                               (uint32_t)(rb < 0 ? zero_row : rb) * row_bytes,
+                               (uint32_t)(rc < 0 ? zero_row : rc) * row_bytes,
+                               (uint32_t)target_row[g] * row_bytes);
+        atomicMin(&owner[target_row[g]], (unsigned int)pos);
+    }
+    __syncthreads();
+    for (int pos = tid; pos < n_groups; pos += blockDim.x) {
+        const int rt = (int)(desc[pos].w / (kTileWords * 4));
+        if (owner[rt] == (unsigned int)pos) desc[pos].x |= kDescOwn;
+    }
+    for (int r = tid; r < n_rows; r += blockDim.x)
+        if (owner[r] == 0xFFFFFFFFu) orphans[atomicAdd(&s_orphans, 1)] = (unsigned short)r;
+    __syncthreads();
+    if (tid == 0) {
+        header[0] = n_groups;
+        header[1] = n_rows;
+        header[2] = s_orphans;
+        header[3] = 0;
+    }
+}
+
+__device__ __forceinline__ void load8(uint32_t (&x)[8], const uint32_t* row, int c0) {
+    // two 128-bit shared loads: 16-byte chunks c0 and c0^4 of the 128-byte row
+    const uint4 lo = *reinterpret_cast<const uint4*>(row + 4 * c0);
+    const uint4 hi = *reinterpret_cast<const uint4*>(row + 4 * (c0 ^ 4));
+    x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w;
+    x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+}
+
+__device__ __forceinline__ uint32_t quad_sum(uint32_t v) {
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+    v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+    return v;
+}
+
+// The AND-subset popcounts of one group over one 32-word tile, taken by a quad (lane l holds the
+// eight words of chunks c0, c0^4), folded across the quad and added to the CTA accumulators
+// dst[0..10] (term order of SCB_TERM_MASKS); the popcount of the target row itself goes to *dst_t
+// when the group owns that row.  ARITY selects which terms can be non-zero.  Per-lane counts are
+// <= 256, quad sums <= 1024: two ride in one register as 16-bit fields.
 template <int ARITY>
 __device__ __forceinline__ void group_terms(const uint32_t* __restrict__ pa, const uint32_t* __restrict__ pb,
                                             const uint32_t* __restrict__ pc, const uint32_t* __restrict__ pt,
-                                            const int (&widx)[8], int l, bool live, uint32_t* dst) {
+                                            int c0, int l, bool live, bool own, uint32_t* dst, uint32_t* dst_t) {
     uint32_t a[8], t[8], x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        a[j] = pa[widx[j]];
-        t[j] = pt[widx[j]];
-    }
+    load8(a, pa, c0);
+    load8(t, pt, c0);
 #define SCB_TERM(var, expr)                                      \
     _Pragma("unroll") for (int j = 0; j < 8; ++j) x[j] = (expr); \
     uint32_t var = popc8(x);
-    if (ARITY == 1) {
+    const uint32_t tt = popc8(t);
+    if (ARITY <= 1) {
         SCB_TERM(at, a[j] & t[j])
-        at += __shfl_xor_sync(0xFFFFFFFFu, at, 1);
-        at += __shfl_xor_sync(0xFFFFFFFFu, at, 2);
-        if (live && l == 0) dst[4] += at;
+        const uint32_t p = quad_sum(at | (tt << 16));
+        if (live && l == 0 && ARITY == 1) atomicAdd(dst + 4, p & 0xFFFFu);
+        if (live && l == 1 && own) atomicAdd(dst_t, p >> 16);
         return;
     }
     uint32_t b[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = pb[widx[j]];
+    load8(b, pb, c0);
     if (ARITY == 2) {
         SCB_TERM(ab, a[j] & b[j])
         SCB_TERM(at, a[j] & t[j])
         SCB_TERM(bt, b[j] & t[j])
         SCB_TERM(abt, lop3<0x80>(a[j], b[j], t[j]))
-        // counts <= 256 per lane: two per register in 16-bit fields
-        uint32_t p0 = ab | (at << 16), p1 = bt | (abt << 16);
-        p0 += __shfl_xor_sync(0xFFFFFFFFu, p0, 1);
-        p1 += __shfl_xor_sync(0xFFFFFFFFu, p1, 1);
-        p0 += __shfl_xor_sync(0xFFFFFFFFu, p0, 2);
-        p1 += __shfl_xor_sync(0xFFFFFFFFu, p1, 2);
+        const uint32_t p0 = quad_sum(ab | (at << 16)), p1 = quad_sum(bt | (abt << 16)), p2 = quad_sum(tt);
         if (live) {  // lanes 0..3 own AB, AT, BT, ABT
             const uint32_t v = ((l & 2) ? p1 : p0) >> ((l & 1) * 16) & 0xFFFFu;
             const int term = l == 0 ? 0 : (l == 1 ? 4 : (l == 2 ? 5 : 7));
-            dst[term] += v;
+            atomicAdd(dst + term, v);
+            if (l == 0 && own) atomicAdd(dst_t, p2);
         }
         return;
     }
     uint32_t c[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) c[j] = pc[widx[j]];
-    uint32_t cnt[kTermsPerGroup];
+    load8(c, pc, c0);
+    uint32_t cnt[kTermsPerGroup + 1];
 #define SCB_TERM_I(idx, expr)                                    \
     _Pragma("unroll") for (int j = 0; j < 8; ++j) x[j] = (expr); \
     cnt[idx] = popc8(x);
@@ -176,201 +269,306 @@ __device__ __forceinline__ void group_terms(const uint32_t* __restrict__ pa, con
     SCB_TERM_I(8, lop3<0x80>(a[j], c[j], t[j]))
     SCB_TERM_I(9, lop3<0x80>(b[j], c[j], t[j]))
     SCB_TERM_I(10, lop3<0x80>(a[j], b[j], c[j]) & t[j])
+    cnt[11] = tt;
 #undef SCB_TERM_I
 #undef SCB_TERM
     uint32_t pk[6];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) pk[k] = cnt[2 * k] | (cnt[2 * k + 1] << 16);
-    pk[5] = cnt[10];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        pk[k] += __shfl_xor_sync(0xFFFFFFFFu, pk[k], 1);
-        pk[k] += __shfl_xor_sync(0xFFFFFFFFu, pk[k], 2);
-    }
-    // lane l of the quad owns terms l, l+4, l+8 (term 11 does not exist)
+    for (int k = 0; k < 6; ++k) pk[k] = quad_sum(cnt[2 * k] | (cnt[2 * k + 1] << 16));
+    // lane l of the quad owns terms l, l+4, l+8; "term 11" is the target row's own popcount
     const bool hi_pair = (l >> 1) != 0;
     const int shift = (l & 1) * 16;
     uint32_t v0 = ((hi_pair ? pk[1] : pk[0]) >> shift) & 0xFFFFu;
     uint32_t v1 = ((hi_pair ? pk[3] : pk[2]) >> shift) & 0xFFFFu;
     uint32_t v2 = ((hi_pair ? pk[5] : pk[4]) >> shift) & 0xFFFFu;
     if (live) {
-        dst[l] += v0;
-        dst[l + 4] += v1;
-        if (l < 3) dst[l + 8] += v2;
+        atomicAdd(dst + l, v0);
+        atomicAdd(dst + l + 4, v1);
+        if (l < 3) atomicAdd(dst + l + 8, v2);
+        else if (own) atomicAdd(dst_t, v2);
     }
 }
 
-__global__ void __launch_bounds__(kCountThreads, 3)
-rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes,
-                   int n_rows, int64_t wpad, int64_t n_tiles,
-                   int n_groups, const int32_t* __restrict__ target_row,
-                   const int32_t* __restrict__ parent_row,
-                   unsigned long long* __restrict__ acc /*[n_rows + 11*G], zeroed*/,
-                   unsigned int* __restrict__ tickets /*[kMaxClasses+1], zeroed: tile ticket per class, CTA ticket*/,
-                   int n_classes, int64_t n_cells, int64_t* __restrict__ out_counts /*[G][16]*/) {
+// One persistent CTA per SM: 24 consumer warps + 1 producer warp around a ring of TMA stages.
+//   producer (one lane): waits for a stage to be released, points the stage at the CTA's next
+//     tile (static round robin over the grid) and starts the 2-D bulk copy; full[stage] counts
+//     the bytes;
+//   consumers: every warp walks the tiles in ring order; inside a tile the work is cut into
+//     ITEMS -- eight groups of one arity class (one group per quad; the group that owns its
+//     target row also counts that row), or eight rows nobody targets -- and warps draw items from
+//     the stage's shared counter, heaviest first, so the SM stays balanced without any CTA-wide
+//     barrier; a warp that finds the counter exhausted releases the stage (empty[stage] counts
+//     the 24 warps) and moves on.
+// Partial counts go to the CTA's shared accumulators with shared-memory atomics, then to the global
+// int64 accumulators (integer adds: order-free, exact); the last CTA to finish inverts the subset
+// sums into the 16 minterm x target counts and leaves the scratch zeroed for the next call.
+__global__ void __launch_bounds__(kCountThreads, 1)
+rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes, int n_stages,
+                   int n_teams, int n_rows, int64_t n_tiles, int n_groups, const unsigned char* __restrict__ plan,
+                   unsigned long long* __restrict__ acc /*[n_rows + 11*G], zero on entry, zero on exit*/,
+                   unsigned int* __restrict__ cta_ticket /*zero on entry, zero on exit*/,
+                   int64_t n_cells, int64_t* __restrict__ out_counts /*[G][16]*/) {
     extern __shared__ __align__(128) uint32_t smem[];
-    // layout: stage[kStages][(rows_alloc+1)][32] | cta_acc[n_rows + 11*G] | mbarriers | tile ids
+    // layout: stage[n_stages][(rows_alloc+1)][32] | desc[G] (uint4) | cta_acc[n_rows + 11*G] |
+    //         full[kMaxStages], empty[kMaxStages] | s_tile[kMaxStages], s_next[kMaxStages] |
+    //         order[G] (u16) | orphans[n_rows] (u16)
     // rows_alloc = n_boxes * box_rows >= n_rows (TMA zero-fills the excess); row rows_alloc is the
     // explicit all-zero row that unused parent slots read.
     const int rows_alloc = n_boxes * box_rows;
     const int stage_words = (rows_alloc + 1) * kTileWords;
     uint32_t* stages = smem;
-    uint32_t* cta_acc = stages + (size_t)kStages * stage_words;
+    uint4* desc = reinterpret_cast<uint4*>(stages + (size_t)n_stages * stage_words);
+    uint32_t* cta_acc = reinterpret_cast<uint32_t*>(desc + n_groups);
     const int n_acc = n_rows + kTermsPerGroup * n_groups;
     uint64_t* full = reinterpret_cast<uint64_t*>(cta_acc + ((n_acc + 1) & ~1));
-    int* s_tile = reinterpret_cast<int*>(full + kStages);
-    unsigned short* order = reinterpret_cast<unsigned short*>(s_tile + kStages);  // groups by arity
-    __shared__ int s_arity_count[4], s_arity_fill[4];
+    uint64_t* empty = full + kMaxStages;
+    volatile int* s_tile = reinterpret_cast<volatile int*>(empty + kMaxStages);
+    int* s_next = const_cast<int*>(s_tile) + kMaxStages;
+    unsigned short* order = reinterpret_cast<unsigned short*>(s_next + kMaxStages);
+    unsigned short* orphans = order + ((n_groups + 1) & ~1);
 
+    const PlanLayout L = plan_layout(n_rows, n_groups);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int quad_in_warp = lane >> 2;             // q: 0..7
-    const int l = lane & 3;                         // lane in quad
-    const int n_quads = (blockDim.x >> 5) * 8;
+    SCB_TRACE_AT(0, tid == 0);
 
-    // Work split: groups (and rows) can be dealt round-robin into n_classes classes; CTA b belongs
-    // to class b % n_classes and walks ALL tiles for its class (n_classes = 1 by default).
-    const int cls = blockIdx.x % n_classes;
-    const int cta_in_cls = blockIdx.x / n_classes;
-    const int ctas_in_cls = (gridDim.x - cls + n_classes - 1) / n_classes;
-    // one thread starts the copy of `tile` into `stage` (a tile past the end just completes the phase)
-    auto issue_tile = [&](int stage, int tile) {
-        s_tile[stage] = tile;
-        if (tile >= n_tiles) {
-            mbar_arrive(&full[stage]);
-            return;
+    // the plan's tables are fetched first thing (the loads fly while the barriers are set up)
+    const int n_orphans = reinterpret_cast<const int*>(plan)[2];
+    constexpr int kPlanPerThread = (kMaxGroupsPerLaunch + kConsumerWarps * 32 - 1) / (kConsumerWarps * 32);
+    uint4 my_desc[kPlanPerThread];
+    unsigned short my_order[kPlanPerThread];
+    if (warp < kConsumerWarps) {
+        const uint4* g_desc = reinterpret_cast<const uint4*>(plan + L.desc);
+        const unsigned short* g_order = reinterpret_cast<const unsigned short*>(plan + L.order);
+#pragma unroll
+        for (int k = 0; k < kPlanPerThread; ++k) {
+            const int i = tid + k * kConsumerWarps * 32;
+            if (i < n_groups) {
+                my_desc[k] = __ldg(g_desc + i);
+                my_order[k] = __ldg(g_order + i);
+            }
         }
-        uint32_t* dst = stages + (size_t)stage * stage_words;
-        mbar_arrive_expect_tx(&full[stage], (uint32_t)(rows_alloc * kTileWords * 4));
-        for (int b = 0; b < n_boxes; ++b)
-            tma_load_2d(dst + (size_t)b * box_rows * kTileWords, &tmap, tile * kTileWords, b * box_rows, &full[stage]);
-    };
-    // the first kStages tiles of a CTA are static: get them moving before any other set-up work
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    }
+    const int team_warps = kConsumerWarps / n_teams;
+    if (tid == kConsumerWarps * 32) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], team_warps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int s = 0; s < kStages; ++s) issue_tile(s, cta_in_cls + s * ctas_in_cls);
     }
-    for (int i = tid; i < n_acc; i += blockDim.x) cta_acc[i] = 0;
-    if (tid < 4) s_arity_count[tid] = s_arity_fill[tid] = 0;
     __syncthreads();
-    // counting sort of the groups by arity, widest first (order inside a class is irrelevant)
-    for (int g = tid; g < n_groups; g += blockDim.x)
-        atomicAdd(&s_arity_count[group_arity(parent_row[3 * g], parent_row[3 * g + 1], parent_row[3 * g + 2])], 1);
-    __syncthreads();
-    for (int g = tid; g < n_groups; g += blockDim.x) {
-        const int ar = group_arity(parent_row[3 * g], parent_row[3 * g + 1], parent_row[3 * g + 2]);
-        int base = 0;
-        for (int k = 3; k > ar; --k) base += s_arity_count[k];
-        order[base + atomicAdd(&s_arity_fill[ar], 1)] = (unsigned short)g;
-    }
-    for (int s = 0; s < kStages; ++s)               // the all-zero row of every stage
-        for (int i = tid; i < kTileWords; i += blockDim.x)
-            stages[(size_t)s * stage_words + (size_t)rows_alloc * kTileWords + i] = 0;
-    __syncthreads();
+    SCB_TRACE_AT(1, tid == 0);
 
-    // later tiles come from the global ticket, claimed one tile ahead so that its L2 round trip
-    // hides behind the arithmetic
-    const int first_dynamic = kStages * ctas_in_cls;
-    auto claim = [&]() {
-        int t = 0;
-        if (lane == 0) t = first_dynamic + (int)atomicAdd(&tickets[cls], 1u);
-        return t;  // valid in lane 0
-    };
-
-    for (int it = 0;; ++it) {
-        const int stage = it % kStages;
-        const uint32_t parity = (it / kStages) & 1;
-        mbar_wait(&full[stage], parity);
-        const int tile = s_tile[stage];
-        if (tile >= n_tiles) break;  // tiles are claimed in increasing order: later stages are empty too
-        int next_tile = 0;
-        if (warp == 0) next_tile = claim();  // consumed after this tile's arithmetic
-        uint32_t* buf = stages + (size_t)stage * stage_words;
-        int widx[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) widx[j] = 4 * (j ^ quad_in_warp) + l;
-
-        // ---- single-row popcounts: one quad per row ----
-        // (loops are warp-uniform: an out-of-range quad works on a clamped index and is masked out,
-        //  because the quad folds below are full-warp shuffles)
-        for (int i0 = warp * 8; cls + n_classes * i0 < n_rows; i0 += n_quads) {
-            const int mine = cls + n_classes * (i0 + quad_in_warp);
-            const bool live = mine < n_rows;
-            const int r = live ? mine : n_rows - 1;
-            const uint32_t* p = buf + (size_t)r * kTileWords;
-            uint32_t x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = p[widx[j]];
-            uint32_t s = popc8(x);
-            s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
-            s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
-            if (l == 0 && live) cta_acc[r] += s;
+    if (warp == kConsumerWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const uint32_t tile_bytes = (uint32_t)(rows_alloc * kTileWords * 4);
+            int stage = 0;
+            uint32_t phase = 1;  // parity of the "previous" empty phase: passes at once for the first lap
+            int markers = 0;
+            // at most kInFlight copies are outstanding: enough to cover the HBM latency at this SM's
+            // share of the bandwidth; more only queue behind each other and delay the first tile
+            const int in_flight = n_stages < kInFlight ? n_stages : kInFlight;  // never waits on a re-armed stage
+            int land_stage = 0, seq = 0;
+            uint32_t land_phase = 0;
+            for (int64_t tile = blockIdx.x;; tile += gridDim.x, ++seq) {
+                if (seq >= in_flight) {
+                    mbar_wait(&full[land_stage], land_phase);
+                    if (++land_stage == n_stages) {
+                        land_stage = 0;
+                        land_phase ^= 1;
+                    }
+                }
+                mbar_wait(&empty[stage], phase);
+                *reinterpret_cast<volatile int*>(s_next + stage) = 0;
+                if (tile >= n_tiles) {  // end marker, one per team: consumers leave when they reach theirs
+                    s_tile[stage] = -1;
+                    mbar_arrive(&full[stage]);
+                    if (++markers == n_teams) break;
+                } else {
+                    s_tile[stage] = (int)tile;
+                    uint32_t* dst = stages + (size_t)stage * stage_words;
+#ifdef SCB_TRACE
+                    if (g_dbg & 2) {
+                        mbar_arrive(&full[stage]);
+                    } else
+#endif
+                    {
+                    mbar_arrive_expect_tx(&full[stage], tile_bytes);
+                    for (int b = 0; b < n_boxes; ++b)
+                        tma_load_2d(dst + (size_t)b * box_rows * kTileWords, &tmap, (int)tile * kTileWords,
+                                    b * box_rows, &full[stage]);
+                    }
+                }
+                if (++stage == n_stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
         }
-        // ---- the multi-variable terms: one quad per group, specialised by arity ----
-        // groups are visited in arity order (3, 2, 1, 0 parents), so a warp's eight groups almost
-        // always share one code path; a mixed round runs the widest path (missing parents read the
-        // all-zero row, their terms come out 0).
-        for (int i0 = warp * 8; cls + n_classes * i0 < n_groups; i0 += n_quads) {
-            const int mine = cls + n_classes * (i0 + quad_in_warp);
-            const bool live = mine < n_groups;
-            const int g = live ? (int)order[mine] : 0;
-            int ra = __ldg(parent_row + 3 * g + 0), rb = __ldg(parent_row + 3 * g + 1),
-                rc = __ldg(parent_row + 3 * g + 2), rt = __ldg(target_row + g);
-            const int arity = __reduce_max_sync(0xFFFFFFFFu, live ? group_arity(ra, rb, rc) : 0);
-            const uint32_t* pa = buf + (size_t)(ra < 0 ? rows_alloc : ra) * kTileWords;
-            const uint32_t* pb = buf + (size_t)(rb < 0 ? rows_alloc : rb) * kTileWords;
-            const uint32_t* pc = buf + (size_t)(rc < 0 ? rows_alloc : rc) * kTileWords;
-            const uint32_t* pt = buf + (size_t)rt * kTileWords;
-            uint32_t* dst = cta_acc + n_rows + (size_t)g * kTermsPerGroup;
-            if (arity >= 3) group_terms<3>(pa, pb, pc, pt, widx, l, live, dst);
-            else if (arity == 2) group_terms<2>(pa, pb, pc, pt, widx, l, live, dst);
-            else if (arity == 1) group_terms<1>(pa, pb, pc, pt, widx, l, live, dst);
+        __syncwarp();
+    } else {
+        // ---------------- consumers ----------------
+        // set-up (overlaps the first copies): accumulators, all-zero rows, the plan's tables
+        for (int i = tid; i < n_acc; i += kConsumerWarps * 32) cta_acc[i] = 0;
+        for (int s = 0; s < n_stages; ++s)
+            if (tid < kTileWords) stages[(size_t)s * stage_words + (size_t)rows_alloc * kTileWords + tid] = 0;
+        {
+#pragma unroll
+            for (int k = 0; k < kPlanPerThread; ++k) {
+                const int i = tid + k * kConsumerWarps * 32;
+                if (i < n_groups) {
+                    desc[i] = my_desc[k];
+                    order[i] = my_order[k];
+                }
+            }
+            const unsigned short* g_orph = reinterpret_cast<const unsigned short*>(plan + L.orphans);
+            for (int i = tid; i < n_orphans; i += kConsumerWarps * 32) orphans[i] = __ldg(g_orph + i);
         }
-        __syncthreads();  // every reader is done with this stage
-        if (tid == 0) issue_tile(stage, next_tile);
+        consumer_sync();
+        SCB_TRACE_AT(2, tid == 0);
+
+        const int quad = lane >> 2;  // 0..7: which of the item's eight groups / rows
+        const int l = lane & 3;      // lane in quad
+        // lane l of quad q reads 16-byte chunks c0 and c0^4: the eight lanes of every quarter-warp
+        // (two quads) cover eight distinct chunks, so the 128-bit loads are conflict-free whatever
+        // rows the quads point at
+        const int c0 = l ^ ((quad & 1) << 2);
+        const int n_gitems = (n_groups + 7) >> 3;
+        const int n_items = n_gitems + ((n_orphans + 7) >> 3);
+
+        // the warps form n_teams teams; team t takes the tiles t, t + n_teams, ... of the ring, so a
+        // warp pays the per-tile bookkeeping for every n_teams-th tile only
+        int stage = warp / team_warps;
+        uint32_t phase = 0;
+        for (;;) {
+            mbar_wait(&full[stage], phase);
+            SCB_TRACE_AT(3, tid == 0 && stage == 0 && phase == 0);
+            if (s_tile[stage] < 0) break;
+            const char* buf = reinterpret_cast<const char*>(stages + (size_t)stage * stage_words);
+            const uint32_t next_addr = smem_u32(s_next + stage);
+            auto claim = [&]() {
+                int it = 0;
+                if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(it) : "r"(next_addr) : "memory");
+                return __shfl_sync(0xFFFFFFFFu, it, 0);
+            };
+            int item = claim();
+            while (item < n_items) {
+                const int next_item = claim();  // drawn one ahead: its latency hides behind the arithmetic
+#ifdef SCB_TRACE
+                if (g_dbg & 1) {
+                    item = next_item;
+                    continue;
+                }
+#endif
+                if (item < n_gitems) {
+                    const int slot = item * 8 + quad;
+                    const bool live = slot < n_groups;
+                    const int sl = live ? slot : n_groups - 1;
+                    const uint4 d = desc[sl];
+                    const int g = order[sl];
+                    const int arity = __reduce_max_sync(0xFFFFFFFFu, live ? (int)(d.x & 3u) : 0);
+                    const bool own = (d.x & kDescOwn) != 0;
+                    const uint32_t* pa = reinterpret_cast<const uint32_t*>(buf + (d.x & ~7u));
+                    const uint32_t* pb = reinterpret_cast<const uint32_t*>(buf + d.y);
+                    const uint32_t* pc = reinterpret_cast<const uint32_t*>(buf + d.z);
+                    const uint32_t* pt = reinterpret_cast<const uint32_t*>(buf + d.w);
+                    uint32_t* dst = cta_acc + n_rows + (size_t)g * kTermsPerGroup;
+                    uint32_t* dst_t = cta_acc + (d.w >> 7);
+                    if (arity >= 3) group_terms<3>(pa, pb, pc, pt, c0, l, live, own, dst, dst_t);
+                    else if (arity == 2) group_terms<2>(pa, pb, pc, pt, c0, l, live, own, dst, dst_t);
+                    else if (arity == 1) group_terms<1>(pa, pb, pc, pt, c0, l, live, own, dst, dst_t);
+                    else group_terms<0>(pa, pb, pc, pt, c0, l, live, own, dst, dst_t);
+                } else {
+                    const int idx = (item - n_gitems) * 8 + quad;
+                    const bool live = idx < n_orphans;
+                    const int r = orphans[live ? idx : n_orphans - 1];
+                    uint32_t x[8];
+                    load8(x, reinterpret_cast<const uint32_t*>(buf) + (size_t)r * kTileWords, c0);
+                    const uint32_t s = quad_sum(popc8(x));
+                    if (l == 0 && live) atomicAdd(cta_acc + r, s);
+                }
+                item = next_item;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);  // this warp is done with the stage
+            stage += n_teams;
+            if (stage >= n_stages) {
+                stage -= n_stages;
+                phase ^= 1;
+            }
+        }
     }
+    SCB_TRACE_AT(4, tid == 0);
     __syncthreads();
+    SCB_TRACE_AT(5, tid == 0);
 
     // fold this CTA's sums into the global int64 accumulators (integer adds: order-free, exact)
     for (int i = tid; i < n_acc; i += blockDim.x)
         if (cta_acc[i]) atomicAdd(acc + i, (unsigned long long)cta_acc[i]);
-    __threadfence();
     __syncthreads();
+    SCB_TRACE_AT(6, tid == 0);
+    // one thread publishes the CTA: the barrier above orders every thread's adds before its
+    // release, the acquire side orders the last CTA's reads after every other CTA's ticket
     __shared__ unsigned int s_ticket;
-    if (tid == 0) s_ticket = atomicAdd(&tickets[kMaxClasses], 1u);
+    if (tid == 0) {
+        unsigned int t;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(cta_ticket) : "memory");
+        s_ticket = t;
+    }
     __syncthreads();
+    SCB_TRACE_AT(7, tid == 0);
     if (s_ticket != gridDim.x - 1) return;
-    // last CTA: every other CTA's adds are visible; invert the subset sums per group
-    __threadfence();
-    constexpr int kTermMask[kTermsPerGroup] = SCB_TERM_MASKS;
-    for (int g = tid; g < n_groups; g += blockDim.x) {
-        int ra = parent_row[3 * g], rb = parent_row[3 * g + 1], rc = parent_row[3 * g + 2];
-        int rt = target_row[g];
-        long long sub[16];  // sub[S] = #cells where every variable in S is 1 (T=8, A=4, B=2, C=1)
+    // last CTA: Moebius inversion of the subset sums, sixteen lanes per group.  Lane q holds
+    // sub[q] = #cells where every variable of q is 1 (T=8, A=4, B=2, C=1): one L2 load each, four
+    // butterfly steps through shuffles, one coalesced store.  Rows and the original group index
+    // come from the shared-memory tables.
+    {
+        const int q = tid & 15;
+        // term index of the multi-variable masks (SCB_TERM_MASKS), one nibble per mask
+        constexpr unsigned long long kTermOfMask = 0xA784956F301F2FFFull;
+        const int term = (int)((kTermOfMask >> (4 * q)) & 15ull);
+        constexpr int kBatch = 4;                       // loads of kBatch groups fly together
+        constexpr int kPerRound = kCountThreads / 16;   // groups per round of the CTA
+        for (int base = 0; base < n_groups; base += kBatch * kPerRound) {  // CTA-uniform trip count
+            const int pos0 = base + (tid >> 4);
+            long long v[kBatch];
+            int g[kBatch];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) sub[i] = 0;
-        sub[0] = n_cells;
-        if (ra >= 0) sub[0x4] = (long long)__ldcg(acc + ra);
-        if (rb >= 0) sub[0x2] = (long long)__ldcg(acc + rb);
-        if (rc >= 0) sub[0x1] = (long long)__ldcg(acc + rc);
-        sub[0x8] = (long long)__ldcg(acc + rt);
-        const unsigned long long* terms = acc + n_rows + (size_t)g * kTermsPerGroup;
+            for (int k = 0; k < kBatch; ++k) {
+                const int pos = pos0 + k * kPerRound;
+                const int p = pos < n_groups ? pos : n_groups - 1;
+                const uint4 d = desc[p];
+                g[k] = pos < n_groups ? (int)order[p] : -1;
+                if (q == 0) v[k] = n_cells;
+                else if (term != 15) v[k] = (long long)__ldcg(acc + n_rows + (size_t)order[p] * kTermsPerGroup + term);
+                else {
+                    const uint32_t off = q == 8 ? d.w : (q == 4 ? d.x : (q == 2 ? d.y : d.z));
+                    const int row = (int)(off >> 7);
+                    v[k] = row == rows_alloc ? 0ll : (long long)__ldcg(acc + row);
+                }
+            }
 #pragma unroll
-        for (int k = 0; k < kTermsPerGroup; ++k) sub[kTermMask[k]] = (long long)__ldcg(terms + k);
-        // Moebius inversion over the 4-variable lattice: exact[S] = #cells whose set of ones is S
+            for (int k = 0; k < kBatch; ++k) {
+                long long x = v[k];
 #pragma unroll
-        for (int bit = 1; bit < 16; bit <<= 1)
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-                if (!(q & bit)) sub[q] -= sub[q | bit];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            out_counts[(size_t)g * 16 + 2 * k + 0] = sub[k];      // minterm k, target 0
-            out_counts[(size_t)g * 16 + 2 * k + 1] = sub[8 | k];  // minterm k, target 1
+                for (int bit = 1; bit < 16; bit <<= 1) {
+                    const long long other = __shfl_xor_sync(0xFFFFFFFFu, x, bit);
+                    if (!(q & bit)) x -= other;  // exact[S] = #cells whose set of ones is exactly S
+                }
+                // q = target << 3 | minterm  ->  counts[g][2 * minterm + target]
+                if (g[k] >= 0) out_counts[(size_t)g[k] * 16 + (((q & 7) << 1) | (q >> 3))] = x;
+            }
         }
     }
+    // leave the scratch as it was found (all zero) so the next call needs no memset
+    __syncthreads();
+    SCB_TRACE_AT(8, tid == 0);
+    for (int i = tid; i < n_acc; i += blockDim.x) acc[i] = 0ull;
+    if (tid == 0) *cta_ticket = 0u;
+    SCB_TRACE_AT(9, tid == 0);
 }
 
 static void box_shape(int n_rows, int* box_rows, int* n_boxes) {
@@ -378,12 +576,16 @@ static void box_shape(int n_rows, int* box_rows, int* n_boxes) {
     *box_rows = (n_rows + *n_boxes - 1) / *n_boxes;
 }
 
-static size_t counts_smem_bytes(int n_rows, int n_groups) {
+// shared memory besides the stages, and the bytes of one stage
+static size_t counts_fixed_smem(int n_rows, int n_groups) {
+    size_t n_acc = (size_t)n_rows + (size_t)kTermsPerGroup * n_groups;
+    return (size_t)n_groups * 16 + ((n_acc + 1) & ~(size_t)1) * 4 + kMaxStages * (8 + 8 + 4 + 4) +
+           ((size_t)n_groups * 2 + 4) + ((size_t)n_rows * 2 + 16);
+}
+static size_t counts_stage_bytes(int n_rows) {
     int box_rows, n_boxes;
     box_shape(n_rows, &box_rows, &n_boxes);
-    size_t n_acc = (size_t)n_rows + (size_t)kTermsPerGroup * n_groups;
-    return (size_t)kStages * ((size_t)box_rows * n_boxes + 1) * kTileWords * 4 + ((n_acc + 1) & ~(size_t)1) * 4 +
-           kStages * 8 + kStages * 4 + ((size_t)n_groups * 2 + 16);
+    return ((size_t)box_rows * n_boxes + 1) * kTileWords * 4;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -422,30 +624,79 @@ static int make_tensor_map(const uint32_t* planes, int n_rows, int64_t wpad, int
 
 using namespace scb;
 
-// groups are processed in slices so the per-CTA accumulators always fit in shared memory
-static const int kMaxGroupsPerLaunch = 1024;
+#ifdef SCB_TRACE
+extern "C" int scb_debug_trace_read(long long* out /*HOST [256][12]*/) {
+    SCB_CUDA(cudaDeviceSynchronize());
+    SCB_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 256 * 12));
+    return SCB_OK;
+}
+#endif
 
-extern "C" int64_t scb_rule_counts_scratch_bytes(int n_rows, int n_groups) {
-    // int64 accumulators (rows + 11 per group of one launch slice) + the two tickets
-    if (n_rows < 0 || n_groups < 0) return 0;
+
+static int64_t acc_bytes(int n_rows, int n_groups) {
     int gn = n_groups < kMaxGroupsPerLaunch ? n_groups : kMaxGroupsPerLaunch;
-    return ((int64_t)n_rows + (int64_t)kTermsPerGroup * gn) * 8 + kTicketBytes;
+    return (int64_t)pad16(((size_t)n_rows + (size_t)kTermsPerGroup * gn) * 8 + kTicketBytes);
 }
 
-extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
-                               int n_groups, const int32_t* target_row, const int32_t* parent_row,
-                               void* scratch, int64_t scratch_bytes, int64_t* out_counts,
-                               scb_stream_t stream) {
+extern "C" int64_t scb_rule_counts_plan_bytes(int n_rows, int n_groups) {
+    if (n_rows <= 0 || n_groups < 0) return 0;
+    int64_t total = 0;
+    for (int g0 = 0; g0 < n_groups; g0 += kMaxGroupsPerLaunch) {
+        int gn = n_groups - g0 < kMaxGroupsPerLaunch ? n_groups - g0 : kMaxGroupsPerLaunch;
+        total += (int64_t)plan_layout(n_rows, gn).bytes;
+    }
+    return total;
+}
+
+extern "C" int64_t scb_rule_counts_scratch_bytes(int n_rows, int n_groups) {
+    // int64 accumulators (rows + 11 per group of one launch slice) + the CTA ticket, then room for
+    // the plan that scb_rule_counts builds for itself
+    if (n_rows < 0 || n_groups < 0) return 0;
+    return acc_bytes(n_rows, n_groups) + scb_rule_counts_plan_bytes(n_rows, n_groups);
+}
+
+extern "C" int scb_rule_counts_plan_build(int n_rows, int n_groups, const int32_t* target_row,
+                                          const int32_t* parent_row, void* plan, int64_t plan_bytes,
+                                          scb_stream_t stream) {
+    SCB_REQUIRE(n_rows > 0 && n_rows < 65536, "rule_counts: n_rows=%d out of range", n_rows);
+    SCB_REQUIRE(n_groups >= 0, "rule_counts: negative n_groups");
+    if (n_groups == 0) return SCB_OK;
+    SCB_REQUIRE(target_row && parent_row && plan, "rule_counts_plan_build: null pointer");
+    SCB_REQUIRE(reinterpret_cast<uintptr_t>(plan) % 16 == 0, "rule_counts_plan_build: plan must be 16-byte aligned");
+    SCB_REQUIRE(plan_bytes >= scb_rule_counts_plan_bytes(n_rows, n_groups), "rule_counts_plan_build: plan buffer too small (%lld < %lld bytes)", (long long)plan_bytes, (long long)scb_rule_counts_plan_bytes(n_rows, n_groups));
+    int box_rows, n_boxes;
+    box_shape(n_rows, &box_rows, &n_boxes);
+    unsigned char* at = static_cast<unsigned char*>(plan);
+    for (int g0 = 0; g0 < n_groups; g0 += kMaxGroupsPerLaunch) {
+        int gn = n_groups - g0 < kMaxGroupsPerLaunch ? n_groups - g0 : kMaxGroupsPerLaunch;
+        rule_counts_plan_kernel<<<1, 256, 0, as_stream(stream)>>>(n_rows, gn, box_rows * n_boxes, target_row + g0,
+                                                                 parent_row + 3 * (size_t)g0, at);
+        SCB_LAUNCH_CHECK("rule_counts_plan_kernel");
+        at += plan_layout(n_rows, gn).bytes;
+    }
+    return SCB_OK;
+}
+
+extern "C" int scb_rule_counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
+                                   int n_groups, const void* plan, void* scratch, int64_t scratch_bytes,
+                                   int64_t* out_counts, int flags, scb_stream_t stream) {
     SCB_REQUIRE(n_rows > 0 && n_rows < 65536, "rule_counts: n_rows=%d out of range", n_rows);
     SCB_REQUIRE(wpad > 0 && wpad % 4 == 0 && wpad * 32 >= n_cells && n_cells >= 0, "rule_counts: wpad must be a positive multiple of 4 covering n_cells");
     SCB_REQUIRE(n_cells < ((int64_t)1 << 31), "rule_counts: at most 2^31-1 cells per call (shard the cells)");
     SCB_REQUIRE(n_groups >= 0, "rule_counts: negative n_groups");
+    SCB_REQUIRE((flags & ~SCB_COUNTS_SCRATCH_CLEAN) == 0, "rule_counts: unknown flags 0x%x", flags);
     if (n_groups == 0) return SCB_OK;
-    SCB_REQUIRE(planes && target_row && parent_row && scratch && out_counts, "rule_counts: null pointer");
+    SCB_REQUIRE(planes && plan && scratch && out_counts, "rule_counts: null pointer");
     SCB_REQUIRE(reinterpret_cast<uintptr_t>(planes) % 16 == 0, "rule_counts: planes must be 16-byte aligned");
     SCB_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 8 == 0, "rule_counts: scratch must be 8-byte aligned");
+    SCB_REQUIRE(reinterpret_cast<uintptr_t>(plan) % 16 == 0, "rule_counts: plan must be 16-byte aligned");
     const int64_t n_tiles = (wpad + kTileWords - 1) / kTileWords;
-    SCB_REQUIRE(n_tiles < ((int64_t)1 << 30), "rule_counts: too many tiles");
+    SCB_REQUIRE(n_tiles < ((int64_t)1 << 26), "rule_counts: too many tiles");
+    const int64_t need = acc_bytes(n_rows, n_groups);
+    if (need > scratch_bytes) {
+        set_error("rule_counts: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
+        return SCB_ERR_SCRATCH;
+    }
     int box_rows, n_boxes;
     box_shape(n_rows, &box_rows, &n_boxes);
     CUtensorMap tmap;
@@ -453,56 +704,81 @@ extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad,
         int rc = make_tensor_map(planes, n_rows, wpad, box_rows, &tmap);
         if (rc != SCB_OK) return rc;
     }
+    const size_t stage_bytes = counts_stage_bytes(n_rows);
+    // the kernel leaves the scratch zeroed; a caller that vouches for it skips the memset
+    if (!(flags & SCB_COUNTS_SCRATCH_CLEAN)) SCB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)need, as_stream(stream)));
+    const unsigned char* plan_at = static_cast<const unsigned char*>(plan);
     for (int g0 = 0; g0 < n_groups; g0 += kMaxGroupsPerLaunch) {
         int gn = n_groups - g0 < kMaxGroupsPerLaunch ? n_groups - g0 : kMaxGroupsPerLaunch;
-        size_t smem = counts_smem_bytes(n_rows, gn);
-        if (smem > 227 * 1024) {
+        const size_t fixed = counts_fixed_smem(n_rows, gn);
+        const size_t budget = 227 * 1024 - 256;  // static shared variables (+ alignment) live in the remainder
+        int n_stages = fixed < budget ? (int)((budget - fixed) / stage_bytes) : 0;
+        if (n_stages > kMaxStages) n_stages = kMaxStages;
+        if (const char* cap = getenv("SCB_COUNTS_STAGES")) {  // experiments
+            int c = atoi(cap);
+            if (c >= 2 && c < n_stages) n_stages = c;
+        }
+        if (n_stages < 2) {
             set_error("rule_counts: %d rows x %d groups do not fit in shared memory", n_rows, gn);
             return SCB_ERR_UNSUPPORTED;
         }
-        int64_t n_acc = (int64_t)n_rows + (int64_t)kTermsPerGroup * gn;
-        int64_t need = n_acc * 8 + kTicketBytes;
-        if (need > scratch_bytes) {
-            set_error("rule_counts: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)need);
-            return SCB_ERR_SCRATCH;
+        int n_teams = n_stages >= 6 ? 3 : (n_stages >= 4 ? 2 : 1);
+        if (const char* cap = getenv("SCB_COUNTS_TEAMS")) {  // experiments
+            int c = atoi(cap);
+            if (c >= 1 && c <= n_stages && kConsumerWarps % c == 0) n_teams = c;
         }
-        // attribute + occupancy are queried once per shared-memory size (keeps the enqueue path
-        // free of non-stream API calls, e.g. under CUDA-graph capture)
-        static thread_local size_t cached_smem = 0;
-        static thread_local int cached_per_sm = 0;
-        if (smem != cached_smem) {
+        const size_t smem = fixed + (size_t)n_stages * stage_bytes;
+        // the attribute is raised once per thread to the largest size seen (keeps the enqueue
+        // path free of non-stream API calls, e.g. under CUDA-graph capture)
+        static thread_local size_t attr_smem = 0;
+        if (smem > attr_smem) {
             SCB_CUDA(cudaFuncSetAttribute(rule_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int q = 1;
-            SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, rule_counts_kernel, kCountThreads, smem));
-            cached_per_sm = q < 1 ? 1 : q;
-            cached_smem = smem;
+            attr_smem = smem;
         }
-        int per_sm = cached_per_sm;
-        if (const char* cap = getenv("SCB_COUNTS_CTAS_PER_SM")) {
-            int c = atoi(cap);
-            if (c >= 1 && c < per_sm) per_sm = c;
-        }
-        // one class = at most one round of the CTA's quads (8 per warp)
-        const int quads = (kCountThreads / 32) * 8;
-        int n_classes = 1;
-        (void)quads;
-        if (const char* cap = getenv("SCB_COUNTS_CLASSES")) {
-            int c = atoi(cap);
-            if (c >= 1) n_classes = c;
-        }
-        if (n_classes > kMaxClasses) n_classes = kMaxClasses;
-        if (n_classes < 1) n_classes = 1;
-        int64_t grid = (int64_t)sm_count() * per_sm;
-        if (grid > n_tiles * n_classes) grid = n_tiles * n_classes;
-        grid -= grid % n_classes;
-        if (grid < n_classes) grid = n_classes;
-        SCB_CUDA(cudaMemsetAsync(scratch, 0, (size_t)need, as_stream(stream)));
+        int64_t grid = sm_count();
+        if (grid > n_tiles) grid = n_tiles;
+        const int64_t n_acc = (int64_t)n_rows + (int64_t)kTermsPerGroup * gn;
         auto* acc = static_cast<unsigned long long*>(scratch);
-        auto* tickets = reinterpret_cast<unsigned int*>(acc + n_acc);
+        auto* ticket = reinterpret_cast<unsigned int*>(acc + n_acc);
+#ifdef SCB_TRACE
+        {
+            int dbg = getenv("SCB_COUNTS_DBG") ? atoi(getenv("SCB_COUNTS_DBG")) : 0;
+            SCB_CUDA(cudaMemcpyToSymbolAsync(g_dbg, &dbg, sizeof(int), 0, cudaMemcpyHostToDevice, as_stream(stream)));
+        }
+#endif
         rule_counts_kernel<<<(unsigned)grid, kCountThreads, smem, as_stream(stream)>>>(
-            tmap, box_rows, n_boxes, n_rows, wpad, n_tiles, gn, target_row + g0, parent_row + 3 * (size_t)g0, acc,
-            tickets, n_classes, n_cells, out_counts + (size_t)g0 * 16);
+            tmap, box_rows, n_boxes, n_stages, n_teams, n_rows, n_tiles, gn, plan_at, acc, ticket, n_cells,
+            out_counts + (size_t)g0 * 16);
         SCB_LAUNCH_CHECK("rule_counts_kernel");
+        plan_at += plan_layout(n_rows, gn).bytes;
     }
     return SCB_OK;
+}
+
+extern "C" int scb_rule_counts_ex(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
+                                  int n_groups, const int32_t* target_row, const int32_t* parent_row,
+                                  void* scratch, int64_t scratch_bytes, int64_t* out_counts, int flags,
+                                  scb_stream_t stream) {
+    SCB_REQUIRE(n_rows > 0 && n_rows < 65536, "rule_counts: n_rows=%d out of range", n_rows);
+    SCB_REQUIRE(n_groups >= 0, "rule_counts: negative n_groups");
+    if (n_groups == 0) return SCB_OK;
+    SCB_REQUIRE(planes && target_row && parent_row && scratch && out_counts, "rule_counts: null pointer");
+    SCB_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 16 == 0, "rule_counts: scratch must be 16-byte aligned");
+    const int64_t accb = acc_bytes(n_rows, n_groups), planb = scb_rule_counts_plan_bytes(n_rows, n_groups);
+    if (accb + planb > scratch_bytes) {
+        set_error("rule_counts: scratch too small (%lld < %lld bytes)", (long long)scratch_bytes, (long long)(accb + planb));
+        return SCB_ERR_SCRATCH;
+    }
+    void* plan = static_cast<unsigned char*>(scratch) + accb;
+    int rc = scb_rule_counts_plan_build(n_rows, n_groups, target_row, parent_row, plan, planb, stream);
+    if (rc != SCB_OK) return rc;
+    return scb_rule_counts_run(planes, n_rows, wpad, n_cells, n_groups, plan, scratch, accb, out_counts, flags, stream);
+}
+
+extern "C" int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
+                               int n_groups, const int32_t* target_row, const int32_t* parent_row,
+                               void* scratch, int64_t scratch_bytes, int64_t* out_counts,
+                               scb_stream_t stream) {
+    return scb_rule_counts_ex(planes, n_rows, wpad, n_cells, n_groups, target_row, parent_row, scratch,
+                              scratch_bytes, out_counts, 0, stream);
 }

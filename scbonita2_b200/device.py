@@ -151,9 +151,17 @@ class RuleCountsPlan:
         self.n_groups = int(target.size)
         self.target = torch.from_numpy(target).to(dev)
         self.parents = torch.from_numpy(parents).to(dev)
+        L = _lib.lib()
         with torch.cuda.device(dev):
-            self.scratch_bytes = int(_lib.lib().scb_rule_counts_scratch_bytes(self.n_rows, self.n_groups))
-        self.scratch = torch.empty(max(self.scratch_bytes, 16), dtype=torch.uint8, device=dev)
+            self.scratch_bytes = int(L.scb_rule_counts_scratch_bytes(self.n_rows, self.n_groups))
+            self.plan_bytes = int(L.scb_rule_counts_plan_bytes(self.n_rows, self.n_groups))
+            # zeroed ONCE: the kernel leaves its scratch zeroed, so run() enqueues no memset
+            self.scratch = torch.zeros(max(self.scratch_bytes, 16), dtype=torch.uint8, device=dev)
+            self.plan = torch.empty(max(self.plan_bytes, 16), dtype=torch.uint8, device=dev)
+            # the cell-independent tables (arity order, row offsets, row owners) are built once
+            _lib.check(L.scb_rule_counts_plan_build(self.n_rows, self.n_groups, self.target.data_ptr(),
+                                                    self.parents.data_ptr(), self.plan.data_ptr(),
+                                                    self.plan_bytes, _stream()), "scb_rule_counts_plan_build")
         self.counts = torch.empty((self.n_groups, 16), dtype=torch.int64, device=dev)
 
     def run(self, planes: BitPlanes):
@@ -162,10 +170,10 @@ class RuleCountsPlan:
         if planes.n_rows != self.n_rows:
             raise ValueError("plan was built for a different number of rows")
         with torch.cuda.device(self.counts.device):
-            _lib.check(_lib.lib().scb_rule_counts(
+            _lib.check(_lib.lib().scb_rule_counts_run(
                 planes.words.data_ptr(), planes.n_rows, planes.wpad, planes.n_cells, self.n_groups,
-                self.target.data_ptr(), self.parents.data_ptr(), self.scratch.data_ptr(),
-                self.scratch_bytes, self.counts.data_ptr(), _stream()), "scb_rule_counts")
+                self.plan.data_ptr(), self.scratch.data_ptr(), self.scratch_bytes,
+                self.counts.data_ptr(), _lib.SCB_COUNTS_SCRATCH_CLEAN, _stream()), "scb_rule_counts_run")
         return self.counts
 
 

@@ -47,6 +47,22 @@ def test_counts_degenerate_groups(cuda):
         assert (counts[g] == np_counts(dense, t, p)).all(), g
 
 
+def test_plan_reruns_leave_the_scratch_clean(cuda):
+    """The kernel zeroes its own scratch: repeated runs of one plan (no memset in between), also on
+    different data, keep giving exact counts."""
+    from scbonita2_b200 import device
+    specs, planes_a = synth.synthetic_dataset(40, 70001, 21, flip=0.1)
+    _, planes_b = synth.synthetic_dataset(40, 70001, 22, flip=0.3)
+    targets, parents = _groups(specs)
+    plan = device.RuleCountsPlan(40, targets, parents)
+    for packed in (planes_a, planes_b, planes_a, planes_a):
+        dense = synth.planes_to_dense(packed, 70001)
+        counts = plan.run(device.BitPlanes.from_packed(packed, 70001)).cpu().numpy()
+        for g in range(0, 40, 3):
+            assert (counts[g] == np_counts(dense, targets[g], parents[g])).all(), g
+    assert int(plan.scratch.view(-1).to(dtype=__import__("torch").int32).abs().sum().item()) == 0
+
+
 def test_many_groups_are_sliced(cuda):
     from scbonita2_b200 import device
     rng = np.random.default_rng(4)

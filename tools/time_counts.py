@@ -1,4 +1,5 @@
-"""Time scb_rule_counts alone (CUDA-graph replay, L2 flushed) for quick A/B experiments."""
+"""Time scb_rule_counts alone (CUDA-graph replay, L2 flushed between replays, no host sync inside
+the timed region) for quick A/B experiments."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +8,7 @@ from tools import synth
 from scbonita2_b200 import device
 
 def main():
-    n, cells = 200, 1_000_000
+    n = int(os.environ.get("N_NODES", 200)); cells = int(os.environ.get("N_CELLS", 1_000_000))
     specs = synth.random_network(n, 0)
     planes_np = synth.random_planes(n, cells, 1000)
     planes = device.BitPlanes.from_packed(planes_np, cells)
@@ -24,12 +25,18 @@ def main():
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         plan.run(planes)
-    ts = []
-    for _ in range(20):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    print(f"ctas_per_sm={os.environ.get('SCB_COUNTS_CTAS_PER_SM','max')}: counts graph replay us: median {np.median(ts):.1f} min {min(ts):.1f}  checksum {int(plan.counts.sum().item())}")
+    for cold in (True, False):
+        pairs = []
+        torch.cuda.synchronize()
+        for _ in range(30):
+            if cold:
+                flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record()
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) * 1e3 for a, b in pairs]
+        print(f"stages={os.environ.get('SCB_COUNTS_STAGES','max')} {'cold' if cold else 'warm'}: counts graph replay us: "
+              f"median {np.median(ts):.1f} mean {np.mean(ts):.1f} min {min(ts):.1f}  checksum {int(plan.counts.sum().item())}")
 
 main()
