@@ -505,6 +505,12 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     __syncthreads();
     SCB_TRACE_AT(5, tid == 0);
 
+    // Programmatic dependent launch, both directions: the kernel that follows in the stream (e.g. the
+    // fitness kernel) may be scheduled from here on, and everything above may have run while the
+    // kernel BEFORE this one (a reader of out_counts from the previous pass) was still draining --
+    // nothing above writes global memory.  Both are no-ops for plain launches.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // fold this CTA's sums into the global int64 accumulators (integer adds: order-free, exact)
     for (int i = tid; i < n_acc; i += blockDim.x)
         if (cta_acc[i]) atomicAdd(acc + i, (unsigned long long)cta_acc[i]);
@@ -746,10 +752,19 @@ extern "C" int scb_rule_counts_run(const uint32_t* planes, int n_rows, int64_t w
             SCB_CUDA(cudaMemcpyToSymbolAsync(g_dbg, &dbg, sizeof(int), 0, cudaMemcpyHostToDevice, as_stream(stream)));
         }
 #endif
-        rule_counts_kernel<<<(unsigned)grid, kCountThreads, smem, as_stream(stream)>>>(
-            tmap, box_rows, n_boxes, n_stages, n_teams, n_rows, n_tiles, gn, plan_at, acc, ticket, n_cells,
-            out_counts + (size_t)g0 * 16);
-        SCB_LAUNCH_CHECK("rule_counts_kernel");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kCountThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        // only the first slice of a call may overlap the previous kernel: later slices share the scratch
+        cfg.numAttrs = (g0 == 0 && (flags & SCB_COUNTS_SCRATCH_CLEAN) && !getenv("SCB_NO_PDL")) ? 1 : 0;
+        SCB_CUDA(cudaLaunchKernelEx(&cfg, rule_counts_kernel, tmap, box_rows, n_boxes, n_stages, n_teams, n_rows,
+                                    n_tiles, gn, plan_at, acc, ticket, n_cells, out_counts + (size_t)g0 * 16));
         plan_at += plan_layout(n_rows, gn).bytes;
     }
     return SCB_OK;

@@ -25,78 +25,104 @@ __global__ void error_table_kernel(const int64_t* __restrict__ counts, int64_t n
     out_diff[t] = diff_from_counts(counts + (size_t)task_group[t] * 16, task_lut[t]);
 }
 
-// One warp per individual, lanes stride over the groups.  With
+// One warp per individual.  With
 //   diff(L) = sum_k c[k][1] + sum_{k: L_k = 1} (c[k][0] - c[k][1])
 // the CTA stages base[g] and, per table nibble, the 16 partial sums of the deltas:
 //   diff(L) = base[g] + lo[L & 15][g] + hi[L >> 4][g]            (2 shared loads per pair)
-// laid out [nibble][g] so lanes with consecutive g mostly hit distinct banks.  The nibble sums are
-// kept in int32 when every count fits (always, below 2^31 cells); otherwise the CTA falls back to
-// the eight int64 deltas.
-__global__ void __launch_bounds__(512)
+// laid out [nibble][g].  The nibble sums are kept in int32 when every count fits (always, below
+// 2^31 cells); otherwise the CTA falls back to the eight int64 deltas.
+// Launched as a programmatic dependent of the kernel before it in the stream (rule_counts_kernel
+// in the GA step): its launch latency hides behind that kernel's tail; griddepcontrol.wait comes
+// before the first global read.
+__global__ void __launch_bounds__(1024)
 population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int64_t n_ind,
                           const uint8_t* __restrict__ lut, const uint8_t* __restrict__ active,
                           int64_t* __restrict__ out_diff, int64_t* __restrict__ out_diff_pg) {
-    extern __shared__ __align__(16) long long s_tab[];  // base[G] | delta[8][G] (int64)  or  lo/hi[32][G] (int32)
+    extern __shared__ __align__(16) long long s_tab[];  // base[G] | delta[8][G] (int64) | lo/hi[32][G] (int32)
     long long* base = s_tab;
     long long* delta = s_tab + n_groups;
-    int* nib = reinterpret_cast<int*>(s_tab + n_groups);  // aliases delta: only one form is built
+    int* nib = reinterpret_cast<int*>(s_tab + 9 * (size_t)n_groups);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // the producers' writes are visible from here on
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // the first individual's truth tables are requested before the tables are built from the counts
+    constexpr int kMaxRounds = 8;  // register-prefetched rows: up to 256 groups
+    const bool fast = n_groups <= 32 * kMaxRounds && !active && !out_diff_pg;
+    uint32_t tab[kMaxRounds];
+    if (fast && warp0 < n_ind) {
+#pragma unroll
+        for (int j = 0; j < kMaxRounds; ++j) {
+            const int g = lane + 32 * j;
+            tab[j] = g < n_groups ? (uint32_t)__ldg(lut + (size_t)warp0 * n_groups + g) : 0u;
+        }
+    }
+    // one thread per group: 16 counts in (8 x 16-byte loads), base and the eight deltas out
     int wide = 0;
     for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
-        const int64_t* c = counts + (size_t)g * 16;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) wide |= (int)((unsigned long long)c[k] >> 31 != 0);
-    }
-    wide = __syncthreads_or(wide);
-    for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
-        const int64_t* c = counts + (size_t)g * 16;
-        long long b = 0, d[8];
+        const longlong2* c = reinterpret_cast<const longlong2*>(counts + (size_t)g * 16);
+        long long b = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            b += c[2 * k + 1];
-            d[k] = c[2 * k] - c[2 * k + 1];
+            const longlong2 v = __ldcg(c + k);  // (minterm k, target 0), (minterm k, target 1)
+            wide |= (int)(((unsigned long long)v.x | (unsigned long long)v.y) >> 31 != 0);
+            b += v.y;
+            delta[k * n_groups + g] = v.x - v.y;
         }
         base[g] = b;
-        if (wide) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) delta[k * n_groups + g] = d[k];
-        } else {
-#pragma unroll
-            for (int v = 0; v < 16; ++v) {
-                long long lo = 0, hi = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if ((v >> k) & 1) {
-                        lo += d[k];
-                        hi += d[k + 4];
-                    }
-                nib[v * n_groups + g] = (int)lo;
-                nib[(16 + v) * n_groups + g] = (int)hi;
-            }
-        }
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = warp; p < n_ind; p += n_warps) {
-        const uint8_t* row = lut + (size_t)p * n_groups;
-        const uint8_t* act = active ? active + (size_t)p * n_groups : nullptr;
-        long long total = 0;
-        for (int g = lane; g < n_groups; g += 32) {
-            long long d = 0;
-            if (!act || act[g]) {
-                const uint32_t table = row[g];
-                d = base[g];
-                if (wide) {
+    wide = __syncthreads_or(wide);
+    if (!wide) {
+        // every thread builds a few entries of the nibble tables from the deltas in shared memory
+        for (int e = threadIdx.x; e < n_groups * 32; e += blockDim.x) {
+            const int g = e % n_groups, what = e / n_groups;  // what: 0..15 low nibble, 16..31 high nibble
+            const int k0 = (what >> 4) * 4, v = what & 15;
+            long long sum = 0;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if ((table >> k) & 1u) d += delta[k * n_groups + g];
-                } else {
-                    d += nib[(table & 15u) * n_groups + g] + nib[(16u + (table >> 4)) * n_groups + g];
-                }
+            for (int k = 0; k < 4; ++k)
+                if ((v >> k) & 1) sum += delta[(k0 + k) * n_groups + g];
+            nib[what * n_groups + g] = (int)sum;
+        }
+        __syncthreads();
+    }
+    for (int64_t p = warp0; p < n_ind; p += n_warps) {
+        long long total = 0;
+        if (fast && !wide) {
+            uint32_t next[kMaxRounds];
+            const bool more = p + n_warps < n_ind;
+#pragma unroll
+            for (int j = 0; j < kMaxRounds; ++j) {
+                const int g = lane + 32 * j;
+                next[j] = (more && g < n_groups) ? (uint32_t)__ldg(lut + (size_t)(p + n_warps) * n_groups + g) : 0u;
             }
-            if (out_diff_pg) out_diff_pg[(size_t)p * n_groups + g] = d;
-            total += d;
+#pragma unroll
+            for (int j = 0; j < kMaxRounds; ++j) {
+                const int g = lane + 32 * j;
+                if (g < n_groups)
+                    total += base[g] + nib[(tab[j] & 15u) * n_groups + g] + nib[(16u + (tab[j] >> 4)) * n_groups + g];
+            }
+#pragma unroll
+            for (int j = 0; j < kMaxRounds; ++j) tab[j] = next[j];
+        } else {
+            const uint8_t* row = lut + (size_t)p * n_groups;
+            const uint8_t* act = active ? active + (size_t)p * n_groups : nullptr;
+            for (int g = lane; g < n_groups; g += 32) {
+                long long d = 0;
+                if (!act || act[g]) {
+                    const uint32_t table = row[g];
+                    d = base[g];
+                    if (wide) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if ((table >> k) & 1u) d += delta[k * n_groups + g];
+                    } else {
+                        d += nib[(table & 15u) * n_groups + g] + nib[(16u + (table >> 4)) * n_groups + g];
+                    }
+                }
+                if (out_diff_pg) out_diff_pg[(size_t)p * n_groups + g] = d;
+                total += d;
+            }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, off);
@@ -188,18 +214,30 @@ extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64
     SCB_REQUIRE(n_groups > 0 && n_individuals >= 0, "population_fitness: bad size");
     if (n_individuals == 0) return SCB_OK;
     SCB_REQUIRE(counts && lut && out_diff, "population_fitness: null pointer");
-    size_t smem = (size_t)n_groups * 17 * sizeof(long long);  // base + max(8 int64 deltas, 32 int32 nibble sums)
+    size_t smem = (size_t)n_groups * 25 * sizeof(long long);  // base + 8 int64 deltas + 32 int32 nibble sums
     if (smem > 200 * 1024) {
-        set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 136));
+        set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 200));
         return SCB_ERR_UNSUPPORTED;
     }
     if (smem > 48 * 1024)
         SCB_CUDA(cudaFuncSetAttribute(population_fitness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (n_individuals + 15) / 16;  // 16 warps per CTA, one individual per warp
-    int64_t cap = (int64_t)sm_count() * 2;
+    int64_t blocks = (n_individuals + 31) / 32;  // 32 warps per CTA, one individual per warp and round
+    int64_t cap = (int64_t)sm_count();
     if (blocks > cap) blocks = cap;
-    population_fitness_kernel<<<(unsigned)blocks, 512, smem, as_stream(stream)>>>(
-        counts, n_groups, n_individuals, lut, active, out_diff, out_diff_pg);
+    // programmatic dependent launch: the kernel may start while its producer (scb_rule_counts in the
+    // same stream) drains; it waits for it with griddepcontrol.wait before it reads the counts
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("SCB_NO_PDL") ? 0 : 1;
+    SCB_CUDA(cudaLaunchKernelEx(&cfg, population_fitness_kernel, counts, n_groups, n_individuals, lut, active,
+                                out_diff, out_diff_pg));
     SCB_LAUNCH_CHECK("population_fitness_kernel");
     return SCB_OK;
 }
