@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N>1: sum the counts with ncclAllReduce instead of peer memory")
     return ap.parse_args()
 
 
@@ -278,14 +279,23 @@ def run_ours(args):
 
     plan = device.RuleCountsPlan(args.nodes, targets, parents, dev)
     d_diff = torch.empty(args.population, dtype=torch.int64, device=dev)
+    # sharded cells: the per-shard counts are summed over peer memory (NVLink), fused into the
+    # fitness kernel -- no library collective in the step (--nccl keeps the ncclAllReduce variant)
+    exchange = None
+    if world > 1 and not args.nccl:
+        from scbonita2_b200.distributed import PeerExchange
+        exchange = PeerExchange.create(args.nodes)
 
     def fitness_step(k=0, timers=None):
         # two kernel launches (+ one NCCL all-reduce when sharded); nothing else is enqueued
         if timers is not None:
             timers[0].record()
-        counts = plan.run(rot[k % n_rot])
+        counts = plan.run(rot[k % n_rot], exchange=exchange)   # sharded: the last CTA pushes to the peers
         if timers is not None:
             timers[1].record()
+        if exchange is not None:
+            exchange.population_fitness(d_lut, out=d_diff)
+            return d_diff
         if world > 1:
             dist.all_reduce(counts)
         device.population_fitness(counts, d_lut, out=d_diff)
@@ -296,6 +306,15 @@ def run_ours(args):
     for k in range(max(args.warmup, 3)):
         fitness_step(k)
     barrier()
+    if exchange is not None:
+        # the peer-memory sum against ncclAllReduce of the same counts, once
+        exchange.check()
+        summed = plan.run(rot[0]).clone()
+        dist.all_reduce(summed)
+        want, _ = device.population_fitness(summed, d_lut)
+        fitness_step(0)
+        assert torch.equal(want, d_diff), "peer-memory exchange disagrees with ncclAllReduce"
+        barrier()
 
     def capture(body):
         side = torch.cuda.Stream()
@@ -310,7 +329,7 @@ def run_ours(args):
 
     # the step is launch-bound (two kernels of a few tens of us): the K steps are ONE CUDA graph
     graph = counts_graph = None
-    if world == 1 and not args.no_graph:
+    if (world == 1 or exchange is not None) and not args.no_graph:
         try:
             graph = capture(lambda: [fitness_step(k) for k in range(args.steps)])
             # the dominant kernel alone, K launches, for the roofline line
@@ -454,6 +473,9 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": workload_config(args, {
+                "exchange": ("none (1 GPU)" if world == 1 else
+                             "peer memory: counts pushed over NVLink, summed inside the fitness kernel"
+                             if exchange is not None else "ncclAllReduce(int64) between the kernels"),
                 "timing": f"K steps back to back between one CUDA event pair; inputs larger than L2: step k reads "
                           f"copy k % {n_rot} of the bitplanes ({n_rot} x {plane_bytes / 1e6:.1f} MB > 2 x 126 MB L2)",
                 "wall_s_timed_region": wall, "fitness_checksum": checksum,

@@ -129,6 +129,44 @@ int scb_population_fitness(const int64_t* counts /*[G][16]*/, int n_groups, int6
                            int64_t* out_diff /*[P]*/, int64_t* out_diff_pg /*[P][G]|NULL*/,
                            scb_stream_t stream);
 
+/* ---- (2c) multi-GPU: the joint counts of the cell shards summed over PEER MEMORY --------------
+ * Cells shard across the GPUs of one box; the only exchange on the GA-fitness path is the sum of
+ * the per-shard joint counts.  Instead of a library all-reduce between the two kernels, every rank
+ * owns a small "region" mapped into all its peers (CUDA IPC, NVLink): scb_peer_push_counts (or the
+ * last CTA of scb_rule_counts_run_push) stores the rank's counts into its slot of every region as
+ * 64-bit words {epoch tag : count} -- an aligned 8-byte store is atomic, so every word validates
+ * itself: no fence, no flag; scb_population_fitness_peers sums the slots of all ranks while it
+ * builds its tables, spinning on a word until its tag is the current epoch.  Integer sums:
+ * bit-identical to the single-GPU result at any GPU count.  Counts must be < 2^31 (they are:
+ * at most 2^31-1 cells per shard).
+ *   region : scb_peer_region_bytes(n_ranks, n_values) bytes from scb_peer_region_alloc (zeroed);
+ *            `ipc_handle` (64 bytes) goes to the peers, which map it with scb_peer_region_open
+ *   peer_regions : DEVICE array of n_ranks region pointers as seen from this rank (own region at
+ *            index `rank`)
+ * Both calls only enqueue work on `stream`; the same sequence must run on every rank. */
+#define SCB_MAX_PEERS 8
+#define SCB_IPC_HANDLE_BYTES 64
+int64_t scb_peer_region_bytes(int n_ranks, int64_t n_values);
+int scb_peer_region_alloc(int64_t bytes, void** region, unsigned char* ipc_handle /*HOST [64]*/);
+int scb_peer_region_open(const unsigned char* ipc_handle /*HOST [64]*/, void** region);
+int scb_peer_region_close(void* region);
+int scb_peer_region_free(void* region);
+int scb_peer_push_counts(const int64_t* counts /*[n_values]*/, int64_t n_values, void* local_region,
+                         void* const* peer_regions /*DEVICE [n_ranks]*/, int rank, int n_ranks,
+                         scb_stream_t stream);
+/* scb_rule_counts_run with the push folded into the kernel's last CTA: no kernel of its own */
+int scb_rule_counts_run_push(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
+                             int n_groups, const void* plan, void* scratch, int64_t scratch_bytes,
+                             int64_t* out_counts /*[G][16]*/, int flags,
+                             void* const* peer_regions /*DEVICE [n_ranks]*/, int rank, int n_ranks,
+                             scb_stream_t stream);
+int scb_population_fitness_peers(const void* local_region, int rank, int n_ranks, int n_groups,
+                                 int64_t n_individuals, const uint8_t* lut /*[P][G]*/,
+                                 const uint8_t* active /*[P][G]|NULL*/, int64_t* out_diff /*[P]*/,
+                                 int64_t* out_diff_pg /*[P][G]|NULL*/, scb_stream_t stream);
+/* 1 if a kernel gave up waiting for a peer (2 s); synchronises the device */
+int scb_peer_error(const void* local_region, int* out_error /*HOST*/);
+
 /* Multi-rule individuals of the historic GA: an individual is a 0/1 string over the concatenated
  * candidate lists of all nodes; out_diff[p] = sum of task_diff[j] over its set bits, out_nsel[p] =
  * number of set bits (the GA's complexity penalty).  task_diff is scb_rule_error_table's output. */

@@ -43,6 +43,17 @@ SIGNATURES = {
                                             c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_population_fitness": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p]),
+    "scb_peer_region_bytes": (c_int64, [c_int, c_int64]),
+    "scb_peer_region_alloc": (c_int, [c_int64, POINTER(c_void_p), c_char_p]),
+    "scb_peer_region_open": (c_int, [c_char_p, POINTER(c_void_p)]),
+    "scb_peer_region_close": (c_int, [c_void_p]),
+    "scb_peer_region_free": (c_int, [c_void_p]),
+    "scb_peer_push_counts": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "scb_rule_counts_run_push": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64,
+                                         c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "scb_population_fitness_peers": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p]),
+    "scb_peer_error": (c_int, [c_void_p, POINTER(c_int)]),
     "scb_bitstring_fitness": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_ko_ki_sweep_scratch_bytes": (c_int64, [c_int, c_int64, c_int]),
     "scb_ko_ki_sweep": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int,

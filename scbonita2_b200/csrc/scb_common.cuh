@@ -69,6 +69,44 @@ __device__ __forceinline__ uint32_t eval_lut(const LutMasks& t, uint32_t a, uint
     return lop3<0xCA>(a, h1, h0);
 }
 
+// ---- peer exchange region (scb_peer.cu, rule_counts_kernel, population_fitness_kernel) --------
+// One region per rank, mapped into every peer (CUDA IPC over NVLink).  Rank r stores its joint
+// counts into slot [parity][r] of EVERY rank's region as 64-bit words {tag = epoch + 1 : count}
+// (a count is < 2^31: at most 2^31-1 cells per shard).  An aligned 8-byte store is atomic, so the
+// tag validates the word it travels with: no fence, no flag, one NVLink traversal (the "LL"
+// protocol of collective libraries).  The reader takes the epoch from its OWN slot (written
+// earlier in its stream) and spins on a word until its tag matches.  parity = epoch & 1
+// double-buffers the slots; a rank can run at most one step ahead of its peers.
+constexpr int kPeerSlotsOffset = 256;
+struct PeerHeader {
+    unsigned long long push_ticket;  // CTAs of every push draw tickets: epoch = ticket / n_ranks
+    unsigned int error;              // raised by a kernel that gave up waiting for a peer
+    unsigned int pad;
+};
+static_assert(sizeof(PeerHeader) <= kPeerSlotsOffset, "peer header must fit before the slots");
+
+__device__ __forceinline__ unsigned long long peer_word(unsigned int tag, long long count) {
+    return ((unsigned long long)tag << 32) | (unsigned long long)(unsigned int)count;
+}
+__device__ __forceinline__ void st_peer(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_peer2(const unsigned long long* p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_peer(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ uint32_t tail_mask(int64_t word, int64_t n_cells) {
     // mask of valid cell bits in `word` (0 if the word is entirely past the end)
     int64_t first = word * 32;

@@ -307,7 +307,9 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
                    int n_teams, int n_rows, int64_t n_tiles, int n_groups, const unsigned char* __restrict__ plan,
                    unsigned long long* __restrict__ acc /*[n_rows + 11*G], zero on entry, zero on exit*/,
                    unsigned int* __restrict__ cta_ticket /*zero on entry, zero on exit*/,
-                   int64_t n_cells, int64_t* __restrict__ out_counts /*[G][16]*/) {
+                   int64_t n_cells, int64_t* __restrict__ out_counts /*[G][16]*/,
+                   void* const* __restrict__ peer_regions /*[n_ranks] or NULL: also push the counts to the peers*/,
+                   int rank, int n_ranks) {
     extern __shared__ __align__(128) uint32_t smem[];
     // layout: stage[n_stages][(rows_alloc+1)][32] | desc[G] (uint4) | cta_acc[n_rows + 11*G] |
     //         full[kMaxStages], empty[kMaxStages] | s_tile[kMaxStages], s_next[kMaxStages] |
@@ -527,6 +529,15 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     __syncthreads();
     SCB_TRACE_AT(7, tid == 0);
     if (s_ticket != gridDim.x - 1) return;
+    // sharded cells: this rank's counts also go to its slot of every peer's exchange region as
+    // tagged words (PeerHeader, scb_common.cuh) -- the push costs no kernel, no fence, no flag
+    __shared__ unsigned int s_epoch;
+    if (peer_regions && tid == 0) {
+        PeerHeader* hdr = static_cast<PeerHeader*>(peer_regions[rank]);
+        s_epoch = (unsigned int)(atomicAdd(&hdr->push_ticket, (unsigned long long)n_ranks) / (unsigned long long)n_ranks);
+    }
+    if (peer_regions) __syncthreads();
+    const int64_t peer_slot = peer_regions ? ((int64_t)(s_epoch & 1u) * n_ranks + rank) * ((int64_t)n_groups * 16) : 0;
     // last CTA: Moebius inversion of the subset sums, sixteen lanes per group.  Lane q holds
     // sub[q] = #cells where every variable of q is 1 (T=8, A=4, B=2, C=1): one L2 load each, four
     // butterfly steps through shuffles, one coalesced store.  Rows and the original group index
@@ -565,12 +576,20 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
                     if (!(q & bit)) x -= other;  // exact[S] = #cells whose set of ones is exactly S
                 }
                 // q = target << 3 | minterm  ->  counts[g][2 * minterm + target]
-                if (g[k] >= 0) out_counts[(size_t)g[k] * 16 + (((q & 7) << 1) | (q >> 3))] = x;
+                if (g[k] >= 0) {
+                    const size_t at = (size_t)g[k] * 16 + (((q & 7) << 1) | (q >> 3));
+                    out_counts[at] = x;
+                    for (int d = 0; d < (peer_regions ? n_ranks : 0); ++d)
+                        st_peer(reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(peer_regions[d]) +
+                                                                      kPeerSlotsOffset) + peer_slot + at,
+                                peer_word(s_epoch + 1u, x));
+                }
             }
         }
     }
     // leave the scratch as it was found (all zero) so the next call needs no memset
     __syncthreads();
+
     SCB_TRACE_AT(8, tid == 0);
     for (int i = tid; i < n_acc; i += blockDim.x) acc[i] = 0ull;
     if (tid == 0) *cta_ticket = 0u;
@@ -683,9 +702,9 @@ extern "C" int scb_rule_counts_plan_build(int n_rows, int n_groups, const int32_
     return SCB_OK;
 }
 
-extern "C" int scb_rule_counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
-                                   int n_groups, const void* plan, void* scratch, int64_t scratch_bytes,
-                                   int64_t* out_counts, int flags, scb_stream_t stream) {
+static int counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells, int n_groups,
+                      const void* plan, void* scratch, int64_t scratch_bytes, int64_t* out_counts, int flags,
+                      void* const* peer_regions, int rank, int n_ranks, scb_stream_t stream) {
     SCB_REQUIRE(n_rows > 0 && n_rows < 65536, "rule_counts: n_rows=%d out of range", n_rows);
     SCB_REQUIRE(wpad > 0 && wpad % 4 == 0 && wpad * 32 >= n_cells && n_cells >= 0, "rule_counts: wpad must be a positive multiple of 4 covering n_cells");
     SCB_REQUIRE(n_cells < ((int64_t)1 << 31), "rule_counts: at most 2^31-1 cells per call (shard the cells)");
@@ -764,10 +783,29 @@ extern "C" int scb_rule_counts_run(const uint32_t* planes, int n_rows, int64_t w
         // only the first slice of a call may overlap the previous kernel: later slices share the scratch
         cfg.numAttrs = (g0 == 0 && (flags & SCB_COUNTS_SCRATCH_CLEAN) && !getenv("SCB_NO_PDL")) ? 1 : 0;
         SCB_CUDA(cudaLaunchKernelEx(&cfg, rule_counts_kernel, tmap, box_rows, n_boxes, n_stages, n_teams, n_rows,
-                                    n_tiles, gn, plan_at, acc, ticket, n_cells, out_counts + (size_t)g0 * 16));
+                                    n_tiles, gn, plan_at, acc, ticket, n_cells, out_counts + (size_t)g0 * 16,
+                                    peer_regions, rank, n_ranks));
         plan_at += plan_layout(n_rows, gn).bytes;
     }
     return SCB_OK;
+}
+
+extern "C" int scb_rule_counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
+                                   int n_groups, const void* plan, void* scratch, int64_t scratch_bytes,
+                                   int64_t* out_counts, int flags, scb_stream_t stream) {
+    return counts_run(planes, n_rows, wpad, n_cells, n_groups, plan, scratch, scratch_bytes, out_counts, flags,
+                      nullptr, 0, 1, stream);
+}
+
+extern "C" int scb_rule_counts_run_push(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
+                                        int n_groups, const void* plan, void* scratch, int64_t scratch_bytes,
+                                        int64_t* out_counts, int flags, void* const* peer_regions, int rank,
+                                        int n_ranks, scb_stream_t stream) {
+    SCB_REQUIRE(n_ranks >= 1 && n_ranks <= SCB_MAX_PEERS && rank >= 0 && rank < n_ranks, "rule_counts_run_push: rank %d of %d", rank, n_ranks);
+    SCB_REQUIRE(peer_regions, "rule_counts_run_push: null peer table");
+    SCB_REQUIRE(n_groups <= kMaxGroupsPerLaunch, "rule_counts_run_push: at most %d groups (one launch)", kMaxGroupsPerLaunch);
+    return counts_run(planes, n_rows, wpad, n_cells, n_groups, plan, scratch, scratch_bytes, out_counts, flags,
+                      peer_regions, rank, n_ranks, stream);
 }
 
 extern "C" int scb_rule_counts_ex(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,

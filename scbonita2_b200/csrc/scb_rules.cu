@@ -37,7 +37,8 @@ __global__ void error_table_kernel(const int64_t* __restrict__ counts, int64_t n
 __global__ void __launch_bounds__(1024)
 population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int64_t n_ind,
                           const uint8_t* __restrict__ lut, const uint8_t* __restrict__ active,
-                          int64_t* __restrict__ out_diff, int64_t* __restrict__ out_diff_pg) {
+                          int64_t* __restrict__ out_diff, int64_t* __restrict__ out_diff_pg,
+                          const unsigned char* region /*peer exchange region or NULL*/, int rank, int n_ranks) {
     extern __shared__ __align__(16) long long s_tab[];  // base[G] | delta[8][G] (int64) | lo/hi[32][G] (int32)
     long long* base = s_tab;
     long long* delta = s_tab + n_groups;
@@ -47,6 +48,24 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the producers' writes are visible from here on
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Sharded cells: the counts are the sum of every rank's slot in the local exchange region, tagged
+    // words {epoch + 1 : count}.  The rank's own slot (written earlier in this stream) names the epoch.
+    const unsigned long long* slots = nullptr;
+    unsigned int want = 0;
+    if (region) {
+        __shared__ unsigned int s_want;
+        if (threadIdx.x == 0) {
+            const unsigned long long* own = reinterpret_cast<const unsigned long long*>(region + kPeerSlotsOffset) +
+                                            (int64_t)rank * n_groups * 16;
+            const unsigned int e0 = (unsigned int)(ld_peer(own) >> 32);
+            const unsigned int e1 = (unsigned int)(ld_peer(own + (int64_t)n_ranks * n_groups * 16) >> 32);
+            s_want = e0 > e1 ? e0 : e1;
+        }
+        __syncthreads();
+        want = s_want;
+        slots = reinterpret_cast<const unsigned long long*>(region + kPeerSlotsOffset) +
+                (int64_t)((want - 1u) & 1u) * n_ranks * n_groups * 16;
+    }
     // the first individual's truth tables are requested before the tables are built from the counts
     constexpr int kMaxRounds = 8;  // register-prefetched rows: up to 256 groups
     const bool fast = n_groups <= 32 * kMaxRounds && !active && !out_diff_pg;
@@ -58,18 +77,44 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
             tab[j] = g < n_groups ? (uint32_t)__ldg(lut + (size_t)warp0 * n_groups + g) : 0u;
         }
     }
-    // one thread per group: 16 counts in (8 x 16-byte loads), base and the eight deltas out
+    // one thread per (group, minterm): the two counts of the minterm in (one 16-byte load per rank),
+    // the delta out; the target-1 counts are parked in the nibble area until base[] is summed
     int wide = 0;
+    long long* ones = reinterpret_cast<long long*>(nib);
+    for (int e = threadIdx.x; e < n_groups * 8; e += blockDim.x) {
+        const int g = e >> 3, k = e & 7;
+        longlong2 v;  // (minterm k, target 0), (minterm k, target 1)
+        if (!slots) {
+            v = __ldcg(reinterpret_cast<const longlong2*>(counts + (size_t)g * 16) + k);
+        } else {
+            v = make_longlong2(0, 0);
+            for (int r = 0; r < n_ranks; ++r) {
+                const unsigned long long* w = slots + ((int64_t)r * n_groups + g) * 16 + 2 * k;
+                ulonglong2 t = ld_peer2(w);
+                if ((unsigned int)(t.x >> 32) != want || (unsigned int)(t.y >> 32) != want) {
+                    // the peer's word has not landed yet: spin, but never hang
+                    const unsigned long long t0 = global_timer_ns();
+                    do {
+                        t = ld_peer2(w);
+                        if (global_timer_ns() - t0 > 2000000000ull) {
+                            reinterpret_cast<PeerHeader*>(const_cast<unsigned char*>(region))->error = 1u;
+                            break;
+                        }
+                    } while ((unsigned int)(t.x >> 32) != want || (unsigned int)(t.y >> 32) != want);
+                }
+                v.x += (long long)(unsigned int)t.x;
+                v.y += (long long)(unsigned int)t.y;
+            }
+        }
+        wide |= (int)(((unsigned long long)v.x | (unsigned long long)v.y) >> 31 != 0);
+        delta[k * n_groups + g] = v.x - v.y;
+        ones[k * n_groups + g] = v.y;
+    }
+    __syncthreads();
     for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
-        const longlong2* c = reinterpret_cast<const longlong2*>(counts + (size_t)g * 16);
         long long b = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const longlong2 v = __ldcg(c + k);  // (minterm k, target 0), (minterm k, target 1)
-            wide |= (int)(((unsigned long long)v.x | (unsigned long long)v.y) >> 31 != 0);
-            b += v.y;
-            delta[k * n_groups + g] = v.x - v.y;
-        }
+        for (int k = 0; k < 8; ++k) b += ones[k * n_groups + g];
         base[g] = b;
     }
     wide = __syncthreads_or(wide);
@@ -208,19 +253,20 @@ extern "C" int scb_rule_error_table(const int64_t* counts, int n_groups, int64_t
     return SCB_OK;
 }
 
-extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64_t n_individuals,
-                                      const uint8_t* lut, const uint8_t* active, int64_t* out_diff,
-                                      int64_t* out_diff_pg, scb_stream_t stream) {
-    SCB_REQUIRE(n_groups > 0 && n_individuals >= 0, "population_fitness: bad size");
-    if (n_individuals == 0) return SCB_OK;
-    SCB_REQUIRE(counts && lut && out_diff, "population_fitness: null pointer");
+static int launch_population_fitness(const int64_t* counts, int n_groups, int64_t n_individuals,
+                                     const uint8_t* lut, const uint8_t* active, int64_t* out_diff,
+                                     int64_t* out_diff_pg, const unsigned char* region, int rank, int n_ranks,
+                                     scb_stream_t stream) {
     size_t smem = (size_t)n_groups * 25 * sizeof(long long);  // base + 8 int64 deltas + 32 int32 nibble sums
     if (smem > 200 * 1024) {
         set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 200));
         return SCB_ERR_UNSUPPORTED;
     }
-    if (smem > 48 * 1024)
+    static thread_local size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
         SCB_CUDA(cudaFuncSetAttribute(population_fitness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
     int64_t blocks = (n_individuals + 31) / 32;  // 32 warps per CTA, one individual per warp and round
     int64_t cap = (int64_t)sm_count();
     if (blocks > cap) blocks = cap;
@@ -237,9 +283,29 @@ extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64
     cfg.attrs = attr;
     cfg.numAttrs = getenv("SCB_NO_PDL") ? 0 : 1;
     SCB_CUDA(cudaLaunchKernelEx(&cfg, population_fitness_kernel, counts, n_groups, n_individuals, lut, active,
-                                out_diff, out_diff_pg));
-    SCB_LAUNCH_CHECK("population_fitness_kernel");
+                                out_diff, out_diff_pg, region, rank, n_ranks));
     return SCB_OK;
+}
+
+extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64_t n_individuals,
+                                      const uint8_t* lut, const uint8_t* active, int64_t* out_diff,
+                                      int64_t* out_diff_pg, scb_stream_t stream) {
+    SCB_REQUIRE(n_groups > 0 && n_individuals >= 0, "population_fitness: bad size");
+    if (n_individuals == 0) return SCB_OK;
+    SCB_REQUIRE(counts && lut && out_diff, "population_fitness: null pointer");
+    return launch_population_fitness(counts, n_groups, n_individuals, lut, active, out_diff, out_diff_pg, nullptr,
+                                     0, 1, stream);
+}
+
+extern "C" int scb_population_fitness_peers(const void* local_region, int rank, int n_ranks, int n_groups,
+                                            int64_t n_individuals, const uint8_t* lut, const uint8_t* active,
+                                            int64_t* out_diff, int64_t* out_diff_pg, scb_stream_t stream) {
+    SCB_REQUIRE(n_groups > 0 && n_individuals >= 0, "population_fitness_peers: bad size");
+    SCB_REQUIRE(n_ranks >= 1 && n_ranks <= SCB_MAX_PEERS && rank >= 0 && rank < n_ranks, "population_fitness_peers: rank %d of %d", rank, n_ranks);
+    if (n_individuals == 0) return SCB_OK;
+    SCB_REQUIRE(local_region && lut && out_diff, "population_fitness_peers: null pointer");
+    return launch_population_fitness(nullptr, n_groups, n_individuals, lut, active, out_diff, out_diff_pg,
+                                     static_cast<const unsigned char*>(local_region), rank, n_ranks, stream);
 }
 
 extern "C" int scb_bitstring_fitness(const int64_t* task_diff, int64_t n_tasks, int64_t n_individuals,

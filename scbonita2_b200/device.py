@@ -164,11 +164,23 @@ class RuleCountsPlan:
                                                     self.plan_bytes, _stream()), "scb_rule_counts_plan_build")
         self.counts = torch.empty((self.n_groups, 16), dtype=torch.int64, device=dev)
 
-    def run(self, planes: BitPlanes):
-        """Enqueue the pass on the current stream; returns the (reused) int64 [G, 16] tensor."""
+    def run(self, planes: BitPlanes, exchange=None):
+        """Enqueue the pass on the current stream; returns the (reused) int64 [G, 16] tensor.
+        With ``exchange`` (``distributed.PeerExchange``) the kernel's last CTA also pushes the counts
+        to every peer's exchange region (``scb_rule_counts_run_push``)."""
         torch = _torch()
         if planes.n_rows != self.n_rows:
             raise ValueError("plan was built for a different number of rows")
+        if exchange is not None:
+            if exchange.n_groups != self.n_groups:
+                raise ValueError("exchange was built for a different number of groups")
+            with torch.cuda.device(self.counts.device):
+                _lib.check(_lib.lib().scb_rule_counts_run_push(
+                    planes.words.data_ptr(), planes.n_rows, planes.wpad, planes.n_cells, self.n_groups,
+                    self.plan.data_ptr(), self.scratch.data_ptr(), self.scratch_bytes,
+                    self.counts.data_ptr(), _lib.SCB_COUNTS_SCRATCH_CLEAN, exchange.peer_table.data_ptr(),
+                    exchange.rank, exchange.world_size, _stream()), "scb_rule_counts_run_push")
+            return self.counts
         with torch.cuda.device(self.counts.device):
             _lib.check(_lib.lib().scb_rule_counts_run(
                 planes.words.data_ptr(), planes.n_rows, planes.wpad, planes.n_cells, self.n_groups,

@@ -288,3 +288,63 @@ def test_population_fitness_wide_counts_path(cuda):
     assert (diff_pg.cpu().numpy() == want).all() and (diff.cpu().numpy() == want.sum(axis=1)).all()
     tab = device.rule_error_table(counts, np.arange(9), lut[3]).cpu().numpy()
     assert (tab == want[3]).all()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_peer_exchange_sums_the_shards(cuda, world):
+    """scb_peer_push_counts + scb_population_fitness_peers on ONE device, `world` logical ranks wired
+    to each other: the fitness of the summed shards, bit for bit, over several epochs (both
+    parities of the double-buffered slots)."""
+    import torch
+    from scbonita2_b200 import device
+    from scbonita2_b200.distributed import PeerExchange
+    rng = np.random.default_rng(31 + world)
+    n_groups, n_ind = 24, 70
+    group = PeerExchange.local_group(n_groups, world)
+    lut = torch.from_numpy(rng.integers(0, 256, (n_ind, n_groups), dtype=np.uint8)).cuda()
+    try:
+        for epoch in range(5):
+            shards = [torch.from_numpy(rng.integers(0, 5000, (n_groups, 16))).cuda() for _ in range(world)]
+            want, want_pg = device.population_fitness(sum(shards), lut, per_node=True)
+            for ex, c in zip(group, shards):
+                ex.push(c)
+            for ex in group:
+                got, got_pg = ex.population_fitness(lut, per_node=(epoch % 2 == 0))
+                assert torch.equal(got, want), (world, epoch, ex.rank)
+                if got_pg is not None:
+                    assert torch.equal(got_pg, want_pg)
+        for ex in group:
+            ex.check()
+    finally:
+        for ex in group:
+            ex.close()
+
+
+def test_counts_kernel_pushes_to_peers(cuda):
+    """scb_rule_counts_run_push: three cell shards on one device, each pass pushing its counts from
+    the kernel's last CTA; every rank's fitness equals the unsharded one."""
+    import torch
+    from scbonita2_b200 import device
+    from scbonita2_b200.distributed import PeerExchange, word_range
+    n_nodes, n_cells, world = 30, 50_021, 3
+    specs, planes_np = synth.synthetic_dataset(n_nodes, n_cells, 41, flip=0.1)
+    targets, parents = _groups(specs)
+    full = device.BitPlanes.from_packed(planes_np, n_cells)
+    rng = np.random.default_rng(5)
+    lut = torch.from_numpy(rng.integers(0, 256, (50, n_nodes), dtype=np.uint8)).cuda()
+    want, _ = device.population_fitness(device.rule_counts(full, targets, parents), lut)
+    group = PeerExchange.local_group(n_nodes, world)
+    plans = [device.RuleCountsPlan(n_nodes, targets, parents) for _ in range(world)]
+    shards = [full.word_slice(*word_range(n_cells, r, world)) for r in range(world)]
+    try:
+        for _ in range(3):
+            for r in range(world):
+                plans[r].run(shards[r], exchange=group[r])
+            for r in range(world):
+                got, _ = group[r].population_fitness(lut)
+                assert torch.equal(got, want), r
+        for ex in group:
+            ex.check()
+    finally:
+        for ex in group:
+            ex.close()
