@@ -119,15 +119,17 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     }
     wide = __syncthreads_or(wide);
     if (!wide) {
-        // every thread builds a few entries of the nibble tables from the deltas in shared memory
-        for (int e = threadIdx.x; e < n_groups * 32; e += blockDim.x) {
-            const int g = e % n_groups, what = e / n_groups;  // what: 0..15 low nibble, 16..31 high nibble
+        // warp w builds row w of the nibble tables (0..15 low nibble, 16..31 high nibble) from the
+        // deltas in shared memory, lanes striding over the groups
+        for (int what = threadIdx.x >> 5; what < 32; what += blockDim.x >> 5) {
             const int k0 = (what >> 4) * 4, v = what & 15;
-            long long sum = 0;
+            for (int g = lane; g < n_groups; g += 32) {
+                long long sum = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((v >> k) & 1) sum += delta[(k0 + k) * n_groups + g];
-            nib[what * n_groups + g] = (int)sum;
+                for (int k = 0; k < 4; ++k)
+                    if ((v >> k) & 1) sum += delta[(k0 + k) * n_groups + g];
+                nib[what * n_groups + g] = (int)sum;
+            }
         }
         __syncthreads();
     }

@@ -101,6 +101,7 @@ struct SweepArgs {
     int64_t cap;
     unsigned int* node_count;       // [N] entries used in each list
     unsigned int* counters;         // [1] flags (bit 0: normal run has lambda >= 3 or an unsettled cell)
+    int fast_steps;                 // KO/KI: steps of the ring fast path before open cells are deferred
     unsigned long long* out_raw;
     unsigned long long* out_missing;
     unsigned long long* out_keyerror;
@@ -263,7 +264,8 @@ sweep_kernel(const SweepArgs args) {
             load_data(kRing - 1);
             __syncthreads();
             uint32_t frozen = ~cellmask;
-            for (int t = 0; t < steps; ++t) {
+            const int t_fast = MODE == MODE_KOKI ? min(steps, args.fast_steps) : steps;
+            for (int t = 0; t < t_fast; ++t) {
                 const int ks = (t + 3) & 3, kd = t & 3, k2 = (t + 2) & 3, k3 = (t + 1) & 3;
                 uint32_t neq1 = 0, neq2 = 0, neq3 = 0, neq4 = 0;
                 if (deep) {
@@ -690,6 +692,8 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.cells = reinterpret_cast<int32_t*>(args.np_found + wpad);
     args.node_count = reinterpret_cast<unsigned int*>(args.cells + (size_t)n_nodes * args.cap);
     args.counters = args.node_count + n_nodes;  // followed by 16 spare bytes
+    args.fast_steps = steps;
+    if (const char* e = getenv("SCB_SWEEP_FAST_STEPS")) args.fast_steps = atoi(e) > 0 ? atoi(e) : steps;  // experiments
     args.out_raw = reinterpret_cast<unsigned long long*>(out_raw);
     args.out_missing = reinterpret_cast<unsigned long long*>(out_missing);
     args.out_keyerror = reinterpret_cast<unsigned long long*>(out_keyerror);
