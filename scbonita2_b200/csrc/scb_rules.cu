@@ -88,22 +88,28 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
             v = __ldcg(reinterpret_cast<const longlong2*>(counts + (size_t)g * 16) + k);
         } else {
             v = make_longlong2(0, 0);
-            for (int r = 0; r < n_ranks; ++r) {
-                const unsigned long long* w = slots + ((int64_t)r * n_groups + g) * 16 + 2 * k;
-                ulonglong2 t = ld_peer2(w);
-                if ((unsigned int)(t.x >> 32) != want || (unsigned int)(t.y >> 32) != want) {
+            // the loads of all ranks fly together; only a word whose tag is stale is polled
+            ulonglong2 t[SCB_MAX_PEERS];
+#pragma unroll
+            for (int r = 0; r < SCB_MAX_PEERS; ++r)
+                if (r < n_ranks) t[r] = ld_peer2(slots + ((int64_t)r * n_groups + g) * 16 + 2 * k);
+#pragma unroll
+            for (int r = 0; r < SCB_MAX_PEERS; ++r) {
+                if (r >= n_ranks) continue;
+                if ((unsigned int)(t[r].x >> 32) != want || (unsigned int)(t[r].y >> 32) != want) {
                     // the peer's word has not landed yet: spin, but never hang
+                    const unsigned long long* w = slots + ((int64_t)r * n_groups + g) * 16 + 2 * k;
                     const unsigned long long t0 = global_timer_ns();
                     do {
-                        t = ld_peer2(w);
+                        t[r] = ld_peer2(w);
                         if (global_timer_ns() - t0 > 2000000000ull) {
                             reinterpret_cast<PeerHeader*>(const_cast<unsigned char*>(region))->error = 1u;
                             break;
                         }
-                    } while ((unsigned int)(t.x >> 32) != want || (unsigned int)(t.y >> 32) != want);
+                    } while ((unsigned int)(t[r].x >> 32) != want || (unsigned int)(t[r].y >> 32) != want);
                 }
-                v.x += (long long)(unsigned int)t.x;
-                v.y += (long long)(unsigned int)t.y;
+                v.x += (long long)(unsigned int)t[r].x;
+                v.y += (long long)(unsigned int)t[r].y;
             }
         }
         wide |= (int)(((unsigned long long)v.x | (unsigned long long)v.y) >> 31 != 0);
