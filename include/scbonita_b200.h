@@ -54,6 +54,13 @@ int scb_device_sm_count(void);
  * dense01: uint8 [n_rows][row_stride] (row_stride >= n_cells, bytes); any non-zero byte is 1. */
 int scb_pack_bitplanes(const uint8_t* dense01, int n_rows, int64_t n_cells, int64_t row_stride,
                        uint32_t* planes, int64_t wpad, scb_stream_t stream);
+/* Threshold + repack in one pass over a dense FLOAT matrix [n_rows][row_stride] (elements): bit =
+ * value > threshold, as sklearn.preprocessing.binarize does on the csr matrix
+ * (rule_inference.py:61-73; NaN compares false).  Skips the uint8 / csr intermediates. */
+int scb_binarize_pack_f32(const float* dense, int n_rows, int64_t n_cells, int64_t row_stride,
+                          float threshold, uint32_t* planes, int64_t wpad, scb_stream_t stream);
+int scb_binarize_pack_f64(const double* dense, int n_rows, int64_t n_cells, int64_t row_stride,
+                          double threshold, uint32_t* planes, int64_t wpad, scb_stream_t stream);
 /* inverse, for round-trip tests and for rebuilding dense intermediates */
 int scb_unpack_bitplanes(const uint32_t* planes, int n_rows, int64_t n_cells, int64_t wpad,
                          uint8_t* dense01, int64_t row_stride, scb_stream_t stream);

@@ -25,6 +25,8 @@ SIGNATURES = {
     "scb_last_error": (c_char_p, []),
     "scb_device_sm_count": (c_int, []),
     "scb_pack_bitplanes": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "scb_binarize_pack_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, ctypes.c_float, c_void_p, c_int64, c_void_p]),
+    "scb_binarize_pack_f64": (c_int, [c_void_p, c_int, c_int64, c_int64, ctypes.c_double, c_void_p, c_int64, c_void_p]),
     "scb_unpack_bitplanes": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "scb_chunk_majority": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_int,
                                    c_void_p, c_int64, c_void_p]),

@@ -132,6 +132,37 @@ static int grid_for(int64_t threads_needed, int block) {
     return (int)blocks;
 }
 
+// ---------------------------------------------------------------------------------------
+// threshold + pack in one pass over a dense FLOAT matrix (the reference builds a csr matrix and
+// calls sklearn binarize, rule_inference.py:61-73: stored values > threshold become 1).
+// warp <-> (row, block of 32 words); lane i of iteration j reads cell base + 32*j + i, so every
+// load instruction of the warp is one contiguous 128/256-byte segment.  NaN > t is false.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) binarize_pack_kernel(const T* __restrict__ dense, int n_rows,
+                                                            int64_t n_cells, int64_t row_stride, T threshold,
+                                                            uint32_t* __restrict__ planes, int64_t wpad) {
+    const int lane = threadIdx.x & 31;
+    int64_t blocks_per_row = (wpad + 31) / 32;
+    int64_t total = (int64_t)n_rows * blocks_per_row;
+    int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t item = warp; item < total; item += n_warps) {
+        int64_t row = item / blocks_per_row;
+        int64_t wb = (item - row * blocks_per_row) * 32;
+        const T* src = dense + row * row_stride;
+        uint32_t mine = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            int64_t cell = (wb + j) * 32 + lane;
+            bool one = cell < n_cells && __ldg(src + cell) > threshold;
+            uint32_t word = __ballot_sync(0xFFFFFFFFu, one);
+            if (lane == j) mine = word;
+        }
+        if (wb + lane < wpad) planes[row * wpad + wb + lane] = mine;
+    }
+}
+
 }  // namespace scb
 
 using namespace scb;
@@ -185,4 +216,31 @@ extern "C" int scb_chunk_majority(const uint32_t* planes, int n_rows, int64_t wp
         planes, n_rows, wpad, perm, n_chunks, chunk_size, min_ones, out_planes, wpad_out);
     SCB_LAUNCH_CHECK("chunk_majority");
     return SCB_OK;
+}
+
+template <typename T>
+static int binarize_pack(const T* dense, int n_rows, int64_t n_cells, int64_t row_stride, T threshold,
+                         uint32_t* planes, int64_t wpad, scb_stream_t stream) {
+    SCB_REQUIRE(n_rows > 0 && n_cells >= 0 && row_stride >= n_cells, "binarize_pack: bad matrix shape");
+    SCB_REQUIRE(wpad > 0 && wpad % 4 == 0 && wpad * 32 >= n_cells, "binarize_pack: wpad must be a positive multiple of 4 covering n_cells");
+    SCB_REQUIRE(dense && planes, "binarize_pack: null pointer");
+    int64_t items = (int64_t)n_rows * ((wpad + 31) / 32);
+    int64_t blocks = (items + 7) / 8;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    binarize_pack_kernel<T><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(dense, n_rows, n_cells, row_stride,
+                                                                            threshold, planes, wpad);
+    SCB_LAUNCH_CHECK("binarize_pack_kernel");
+    return SCB_OK;
+}
+
+extern "C" int scb_binarize_pack_f32(const float* dense, int n_rows, int64_t n_cells, int64_t row_stride,
+                                     float threshold, uint32_t* planes, int64_t wpad, scb_stream_t stream) {
+    return binarize_pack<float>(dense, n_rows, n_cells, row_stride, threshold, planes, wpad, stream);
+}
+
+extern "C" int scb_binarize_pack_f64(const double* dense, int n_rows, int64_t n_cells, int64_t row_stride,
+                                     double threshold, uint32_t* planes, int64_t wpad, scb_stream_t stream) {
+    return binarize_pack<double>(dense, n_rows, n_cells, row_stride, threshold, planes, wpad, stream);
 }

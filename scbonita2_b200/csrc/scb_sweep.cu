@@ -32,7 +32,10 @@
 namespace scb {
 
 constexpr int kLamPlanes = 6;  // lambda < steps <= 64
-constexpr int kSweepThreads = 512;
+#ifndef SCB_SWEEP_THREADS
+#define SCB_SWEEP_THREADS 512
+#endif
+constexpr int kSweepThreads = SCB_SWEEP_THREADS;
 
 struct __align__(16) NodeEntry {
     int pa, pb, pc;

@@ -70,6 +70,31 @@ class BitPlanes:
         return cls(words, n_rows, n_cells)
 
     @classmethod
+    def from_float(cls, matrix, threshold: float, device=None) -> "BitPlanes":
+        """From a dense (rows x cells) float32/float64 expression matrix (NumPy array or CUDA
+        tensor): bit = value > threshold, the reference's csr + ``sklearn.binarize`` recipe
+        (``rule_inference.py:61-73``) in one pass, without the uint8 / csr intermediates."""
+        torch = _torch()
+        if not isinstance(matrix, torch.Tensor):
+            matrix = np.ascontiguousarray(matrix)
+            if matrix.dtype not in (np.float32, np.float64):
+                matrix = matrix.astype(np.float64)
+            matrix = torch.from_numpy(matrix)
+        if matrix.ndim != 2 or matrix.dtype not in (torch.float32, torch.float64):
+            raise ValueError("expected a 2-D float32/float64 (genes x cells) matrix")
+        if threshold < 0:
+            raise ValueError("Cannot binarize a sparse matrix with threshold < 0")   # as the reference
+        d = matrix.to(device or "cuda").contiguous()
+        n_rows, n_cells = int(d.shape[0]), int(d.shape[1])
+        wpad = padded_words(n_cells)
+        words = torch.empty((n_rows, wpad), dtype=torch.int32, device=d.device)
+        fn = _lib.lib().scb_binarize_pack_f32 if d.dtype == torch.float32 else _lib.lib().scb_binarize_pack_f64
+        with torch.cuda.device(d.device):
+            _lib.check(fn(d.data_ptr(), n_rows, n_cells, n_cells, float(threshold), words.data_ptr(), wpad,
+                          _stream()), "scb_binarize_pack")
+        return cls(words, n_rows, n_cells)
+
+    @classmethod
     def from_packed(cls, packed: np.ndarray, n_cells: int, device=None) -> "BitPlanes":
         """From host uint32 words ``[n_rows][>= ceil(n_cells/32)]`` (tail bits must be zero)."""
         torch = _torch()

@@ -28,7 +28,11 @@ class RuleInference:
     """Class for single-cell experiments"""
 
     def __init__(self, data_file, graph, dataset_name, network_name, sep, node_indices,
-                 binarize_threshold=0.001, sample_cells=True):
+                 binarize_threshold=0.001, sample_cells=True, gpu_parent_pruning=False):
+        # gpu_parent_pruning (not in the reference): take the Spearman top-3 of every node from ONE
+        # pass of scb_rule_counts over the bitplanes (spearman.py) instead of one scipy call per edge;
+        # same parents in the same order, and the reference's floats for the stored correlations
+        self.gpu_parent_pruning = bool(gpu_parent_pruning)
         self.node_indices = node_indices
         self.dataset_name = dataset_name
         self.network_name = network_name
@@ -143,9 +147,17 @@ class RuleInference:
 
     # ---- predecessors ------------------------------------------------------------------
     def calculate_node_information(self):
+        self._gpu_top3 = None
+        if self.gpu_parent_pruning:
+            from . import device, spearman
+            planes = device.BitPlanes.from_dense(self.binarized_matrix)
+            incoming = [[self.node_list.index(p) for p in self.graph.predecessors(name)]
+                        for name in self.node_list]
+            self._gpu_top3, _ = spearman.top3_parents(planes, incoming)
         for node_num, _ in enumerate(self.node_list):
             chosen = self.find_predecessors(self.rule_graph, self.node_list, self.graph, node_num)
             self.predecessors.append([self.node_list.index(name) for name, _ in chosen])
+        self._gpu_top3 = None
 
     def calculate_spearman_correlation(self, node, predecessors_temp):
         """Spearman correlation of the node's binarised row with each candidate parent's row; rows
@@ -163,11 +175,16 @@ class RuleInference:
         (``rule_inference.py:263-320``)."""
         target = node_list[node_index]
         incoming = list(graph.predecessors(target))
-        correlations = self.calculate_spearman_correlation(node_index, incoming)
-        chosen = sorted(zip(incoming, correlations), reverse=True, key=lambda pair: pair[1])[:3]
+        if getattr(self, "_gpu_top3", None) is not None:
+            chosen = [(node_list[row], value) for row, value in self._gpu_top3[node_index]]
+            top_values = sorted((value for _, value in chosen), reverse=True)
+        else:
+            correlations = self.calculate_spearman_correlation(node_index, incoming)
+            chosen = sorted(zip(incoming, correlations), reverse=True, key=lambda pair: pair[1])[:3]
+            top_values = sorted(correlations, reverse=True)[:3]
 
         self.num_successors.append(len(list(graph.successors(target))))
-        self.rvalues.append(sorted(correlations, reverse=True)[:3])
+        self.rvalues.append(top_values)
         self.predecessors_final.append([name for name, _ in chosen])
 
         for parent, weight in chosen:

@@ -79,3 +79,25 @@ def test_chunk_majority_random_vs_oracle(cuda):
         perm, n_chunks, size = chunk_layout(n_cells, num_chunks)
         out = BitPlanes.from_dense(dense).chunk_majority(perm, n_chunks, size, chunk_min_ones(size))
         assert (out.to_dense() == ref_port.chunk_data(dense, num_chunks).astype(np.uint8)).all()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,threshold", [((1, 1), 0.0), ((3, 31), 0.5), ((5, 1000), 0.01), ((59, 3621), 0.001),
+                                             ((7, 40_003), 0.3)])
+def test_binarize_pack_matches_sklearn_recipe(cuda, dtype, shape, threshold):
+    """scb_binarize_pack_f32/f64 == csr + binarize(threshold) of the reference (value > threshold)."""
+    from scbonita2_b200 import device
+    rng = np.random.default_rng(shape[1])
+    x = rng.normal(0.2, 1.0, shape).astype(dtype)
+    x[rng.random(shape) < 0.3] = 0
+    x.flat[::97] = threshold            # values AT the threshold stay 0
+    if x.size > 5:
+        x.flat[3] = np.nan
+    planes = device.BitPlanes.from_float(x, threshold)
+    want = (x > dtype(threshold)).astype(np.uint8)
+    assert (planes.to_dense() == want).all()
+    tail = planes.words.cpu().numpy().view(np.uint32)
+    n_words = (shape[1] + 31) // 32
+    if shape[1] % 32:
+        assert (tail[:, n_words - 1] >> (shape[1] % 32) == 0).all()
+    assert (tail[:, n_words:] == 0).all()

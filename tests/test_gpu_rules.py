@@ -208,8 +208,9 @@ def test_counts_are_additive_over_cell_shards(cuda):
     assert int(whole.sum()) == 40 * 100_000
 
 
+@pytest.mark.parametrize("gpu_pruning", [False, True])
 @pytest.mark.parametrize("name", golden_names("ruleinf_"))
-def test_rule_inference_constructor_golden(cuda, name, tmp_path):
+def test_rule_inference_constructor_golden(cuda, name, tmp_path, gpu_pruning):
     """The whole RuleInference constructor (CSV -> sample -> binarise -> Spearman top-3 -> GPU rule
     scoring) against the reference run with the same NumPy seed; then the pickle round trip."""
     import pickle
@@ -230,7 +231,7 @@ def test_rule_inference_constructor_golden(cuda, name, tmp_path):
     csv_path.write_text(g["csv"])
     np.random.seed(g["seed"])
     ri = RuleInference(str(csv_path), graph, "ds", "net", ",", g["node_indices"],
-                       binarize_threshold=0.001, sample_cells=True)
+                       binarize_threshold=0.001, sample_cells=True, gpu_parent_pruning=gpu_pruning)
     assert list(ri.gene_names) == g["gene_names"] and list(ri.cv_genes) == g["cv_genes"]
     assert (np.asarray(ri.binarized_matrix.todense()).astype(np.uint8) == matrix_of(g["binarized"])).all()
     assert [[int(x) for x in p] for p in ri.predecessors] == g["predecessors"]
@@ -348,3 +349,40 @@ def test_counts_kernel_pushes_to_peers(cuda):
     finally:
         for ex in group:
             ex.close()
+
+
+def test_spearman_top3_matches_scipy_selection(cuda):
+    """GPU contingency tables + exact integer ordering pick the same three parents, in the same
+    order, as the reference's scipy.stats.spearmanr loop (rule_inference.py:234-320) -- including
+    duplicated rows (exact ties) and constant rows (nan -> 0)."""
+    from scipy.stats import spearmanr
+    from scbonita2_b200 import device, spearman
+    rng = np.random.default_rng(12)
+    n_rows, n_cells = 24, 3001
+    dense = (rng.random((n_rows, n_cells)) < rng.uniform(0.1, 0.6, (n_rows, 1))).astype(np.uint8)
+    dense[5] = dense[2]                 # exact tie between two candidates
+    dense[7] = 1 - dense[2]
+    dense[9] = 0                        # constant row: nan in scipy, 0 in the reference
+    for r in range(10, 16):             # correlated candidates
+        dense[r] = dense[0] ^ (rng.random(n_cells) < 0.05 * (r - 9))
+    planes = device.BitPlanes.from_dense(dense)
+    incoming = [[int(p) for p in rng.permutation(n_rows)[:rng.integers(0, 9)] if p != node]
+                for node in range(n_rows)]
+    incoming[0] = [2, 5, 9, 10, 11, 12, 7]
+    incoming[3] = [5, 2]
+    got, fallbacks = spearman.top3_parents(planes, incoming)
+    assert fallbacks > 0
+    for node, cands in enumerate(incoming):
+        corr = []
+        for p in cands:
+            rho, _ = spearmanr(dense[node].astype(float).tolist(), dense[p].astype(float).tolist())
+            corr.append(0 if np.isnan(rho) else rho)
+        want = sorted(zip(cands, corr), reverse=True, key=lambda pair: pair[1])[:3]
+        assert [p for p, _ in got[node]] == [p for p, _ in want], node
+        assert [v for _, v in got[node]] == [v for _, v in want], node      # the reference's floats
+    # the closed form agrees with scipy to rounding
+    tabs = spearman.edge_tables(planes, [(0, 10), (0, 7), (1, 2)])
+    for (a, b), t in zip([(0, 10), (0, 7), (1, 2)], tabs):
+        rho, _ = spearmanr(dense[a].astype(float), dense[b].astype(float))
+        assert abs(spearman.phi_from_table(*t) - rho) < 1e-12
+        assert t.sum() == n_cells
