@@ -39,6 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-Xptxas", "-v"]
     if os.environ.get("SCB_TRACE"):   # phase timestamps of rule_counts_kernel (tools/trace_counts.py)
         cmd += ["-DSCB_TRACE"]
+    if os.environ.get("SCB_DIRECT_RED"):   # experiments
+        cmd += ["-DSCB_DIRECT_RED=" + os.environ["SCB_DIRECT_RED"]]
     if os.environ.get("SCB_SWEEP_THREADS"):   # experiments
         cmd += ["-DSCB_SWEEP_THREADS=" + os.environ["SCB_SWEEP_THREADS"]]
     if os.environ.get("SCB_CONSUMER_WARPS"):   # experiments

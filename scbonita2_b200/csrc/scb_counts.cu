@@ -28,6 +28,15 @@ constexpr int kInFlight = 3;        // bulk copies outstanding per SM
 constexpr int kConsumerWarps = SCB_CONSUMER_WARPS;
 constexpr int kCountThreads = (kConsumerWarps + 1) * 32;  // + the producer warp
 constexpr int kTicketBytes = 16;
+#ifndef SCB_DIRECT_RED
+#define SCB_DIRECT_RED 0
+#endif
+// 0 (default): partial counts are kept per CTA in shared memory and flushed once at the end -- ~190 k
+// global atomics in one burst, which the last CTA's finalize waits out in L2 (~3.5 k cycles);
+// 1 (experiment, measured: 41 us instead of 22.5 us on H1M, 572 us instead of 143 us at 16M cells):
+// every partial count goes straight to the global accumulators with a 32-bit RED.ADD -- the 2 400 hot
+// addresses sustain only ~18 atomics per clock chip-wide, so spreading the atomics loses.
+constexpr bool kDirectRed = SCB_DIRECT_RED != 0;
 constexpr int kMaxGroupsPerLaunch = 1024;  // groups are processed in slices so the per-CTA accumulators fit in shared memory
 
 // term order (bit3=T, bit2=A, bit1=B, bit0=C): masks of the 11 multi-variable subsets
@@ -289,6 +298,82 @@ __device__ __forceinline__ void group_terms(const uint32_t* __restrict__ pa, con
     }
 }
 
+// entry i of the global accumulators: uint32 when the CTAs add to them directly (a count is < 2^31),
+// uint64 when they flush their shared-memory sums
+__device__ __forceinline__ long long load_acc(const unsigned long long* acc, size_t i) {
+    if (kDirectRed) return (long long)__ldcg(reinterpret_cast<const unsigned int*>(acc) + i);
+    return (long long)__ldcg(acc + i);
+}
+
+// Moebius inversion of the subset sums, sixteen lanes per group.  Lane q holds sub[q] = #cells
+// where every variable of q is 1 (T=8, A=4, B=2, C=1): one L2 load each, four butterfly steps
+// through shuffles, one coalesced store (and one tagged store per peer when the cells are sharded).
+// Rows and the original group index come from the shared-memory tables.
+// Only the LAST CTA needs the result, at the very end, where a cold instruction cache costs ~3 k
+// cycles -- so every CTA runs the routine once with dry = true (loads and arithmetic, no stores)
+// while it waits for its first tile: the code is resident when it matters.  __noinline__ keeps
+// the two call sites on the same instructions.
+__device__ __noinline__ void moebius_pass(const uint4* __restrict__ desc, const unsigned short* __restrict__ order,
+                                          const unsigned long long* __restrict__ acc, int n_rows, int rows_alloc,
+                                          int n_groups, int n_do, int64_t n_cells, int64_t* __restrict__ out_counts,
+                                          void* const* __restrict__ peer_regions, int n_ranks, int64_t peer_slot,
+                                          unsigned int peer_tag, int tid, bool dry) {
+    const int q = tid & 15;
+    // term index of the multi-variable masks (SCB_TERM_MASKS), one nibble per mask
+    constexpr unsigned long long kTermOfMask = 0xA784956F301F2FFFull;
+    const int term = (int)((kTermOfMask >> (4 * q)) & 15ull);
+    constexpr int kBatch = 4;                       // loads of kBatch groups fly together
+    constexpr int kPerRound = kCountThreads / 16;   // groups per round of the CTA
+    long long sink = 0;
+    for (int base = 0; base < n_do; base += kBatch * kPerRound) {  // uniform trip count
+        const int pos0 = base + (tid >> 4);
+        long long v[kBatch];
+        int g[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int pos = pos0 + k * kPerRound;
+            const int p = pos < n_groups ? pos : n_groups - 1;
+            const uint4 d = desc[p];
+            g[k] = pos < n_groups ? (int)order[p] : -1;
+            if (q == 0) v[k] = n_cells;
+            else if (term != 15) v[k] = load_acc(acc, n_rows + (size_t)order[p] * kTermsPerGroup + term);
+            else {
+                const uint32_t off = q == 8 ? d.w : (q == 4 ? d.x : (q == 2 ? d.y : d.z));
+                const int row = (int)(off >> 7);
+                v[k] = row == rows_alloc ? 0ll : load_acc(acc, row);
+            }
+        }
+#ifdef SCB_TRACE
+        if (base == 0 && tid == 0) {
+            g_trace[blockIdx.x & 255][10] = clock64();
+            long long t = v[0] + v[1] + v[2] + v[3];
+            if (t == 0x7FFFFFFFFFFFFFFFll) sink = 1;   // wait for the loads
+            g_trace[blockIdx.x & 255][11] = clock64();
+        }
+#endif
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            long long x = v[k];
+#pragma unroll
+            for (int bit = 1; bit < 16; bit <<= 1) {
+                const long long other = __shfl_xor_sync(0xFFFFFFFFu, x, bit);
+                if (!(q & bit)) x -= other;  // exact[S] = #cells whose set of ones is exactly S
+            }
+            sink ^= x;
+            // q = target << 3 | minterm  ->  counts[g][2 * minterm + target]
+            if (g[k] >= 0 && !dry) {
+                const size_t at = (size_t)g[k] * 16 + (((q & 7) << 1) | (q >> 3));
+                out_counts[at] = x;
+                for (int d = 0; d < (peer_regions ? n_ranks : 0); ++d)
+                    st_peer(reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(peer_regions[d]) +
+                                                                  kPeerSlotsOffset) + peer_slot + at,
+                            peer_word(peer_tag, x));
+            }
+        }
+    }
+    if (dry && sink == 0x7FFFFFFFFFFFFFFFll) out_counts[0] = sink;  // keeps the dry arithmetic alive; never true
+}
+
 // One persistent CTA per SM: 24 consumer warps + 1 producer warp around a ring of TMA stages.
 //   producer (one lane): waits for a stage to be released, points the stage at the CTA's next
 //     tile (static round robin over the grid) and starts the 2-D bulk copy; full[stage] counts
@@ -354,6 +439,7 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     }
     const int team_warps = kConsumerWarps / n_teams;
     if (tid == kConsumerWarps * 32) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");  // hide the descriptor fetch
         for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], team_warps);
@@ -414,7 +500,8 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     } else {
         // ---------------- consumers ----------------
         // set-up (overlaps the first copies): accumulators, all-zero rows, the plan's tables
-        for (int i = tid; i < n_acc; i += kConsumerWarps * 32) cta_acc[i] = 0;
+        if (!kDirectRed)
+            for (int i = tid; i < n_acc; i += kConsumerWarps * 32) cta_acc[i] = 0;
         for (int s = 0; s < n_stages; ++s)
             if (tid < kTileWords) stages[(size_t)s * stage_words + (size_t)rows_alloc * kTileWords + tid] = 0;
         {
@@ -477,8 +564,9 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
                     const uint32_t* pb = reinterpret_cast<const uint32_t*>(buf + d.y);
                     const uint32_t* pc = reinterpret_cast<const uint32_t*>(buf + d.z);
                     const uint32_t* pt = reinterpret_cast<const uint32_t*>(buf + d.w);
-                    uint32_t* dst = cta_acc + n_rows + (size_t)g * kTermsPerGroup;
-                    uint32_t* dst_t = cta_acc + (d.w >> 7);
+                    uint32_t* tally = kDirectRed ? reinterpret_cast<uint32_t*>(acc) : cta_acc;
+                    uint32_t* dst = tally + n_rows + (size_t)g * kTermsPerGroup;
+                    uint32_t* dst_t = tally + (d.w >> 7);
                     if (arity >= 3) group_terms<3>(pa, pb, pc, pt, c0, l, live, own, dst, dst_t);
                     else if (arity == 2) group_terms<2>(pa, pb, pc, pt, c0, l, live, own, dst, dst_t);
                     else if (arity == 1) group_terms<1>(pa, pb, pc, pt, c0, l, live, own, dst, dst_t);
@@ -490,7 +578,7 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
                     uint32_t x[8];
                     load8(x, reinterpret_cast<const uint32_t*>(buf) + (size_t)r * kTileWords, c0);
                     const uint32_t s = quad_sum(popc8(x));
-                    if (l == 0 && live) atomicAdd(cta_acc + r, s);
+                    if (l == 0 && live) atomicAdd((kDirectRed ? reinterpret_cast<uint32_t*>(acc) : cta_acc) + r, s);
                 }
                 item = next_item;
             }
@@ -514,8 +602,9 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // fold this CTA's sums into the global int64 accumulators (integer adds: order-free, exact)
-    for (int i = tid; i < n_acc; i += blockDim.x)
-        if (cta_acc[i]) atomicAdd(acc + i, (unsigned long long)cta_acc[i]);
+    if (!kDirectRed)
+        for (int i = tid; i < n_acc; i += blockDim.x)
+            if (cta_acc[i]) atomicAdd(acc + i, (unsigned long long)cta_acc[i]);
     __syncthreads();
     SCB_TRACE_AT(6, tid == 0);
     // one thread publishes the CTA: the barrier above orders every thread's adds before its
@@ -538,55 +627,9 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     }
     if (peer_regions) __syncthreads();
     const int64_t peer_slot = peer_regions ? ((int64_t)(s_epoch & 1u) * n_ranks + rank) * ((int64_t)n_groups * 16) : 0;
-    // last CTA: Moebius inversion of the subset sums, sixteen lanes per group.  Lane q holds
-    // sub[q] = #cells where every variable of q is 1 (T=8, A=4, B=2, C=1): one L2 load each, four
-    // butterfly steps through shuffles, one coalesced store.  Rows and the original group index
-    // come from the shared-memory tables.
-    {
-        const int q = tid & 15;
-        // term index of the multi-variable masks (SCB_TERM_MASKS), one nibble per mask
-        constexpr unsigned long long kTermOfMask = 0xA784956F301F2FFFull;
-        const int term = (int)((kTermOfMask >> (4 * q)) & 15ull);
-        constexpr int kBatch = 4;                       // loads of kBatch groups fly together
-        constexpr int kPerRound = kCountThreads / 16;   // groups per round of the CTA
-        for (int base = 0; base < n_groups; base += kBatch * kPerRound) {  // CTA-uniform trip count
-            const int pos0 = base + (tid >> 4);
-            long long v[kBatch];
-            int g[kBatch];
-#pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                const int pos = pos0 + k * kPerRound;
-                const int p = pos < n_groups ? pos : n_groups - 1;
-                const uint4 d = desc[p];
-                g[k] = pos < n_groups ? (int)order[p] : -1;
-                if (q == 0) v[k] = n_cells;
-                else if (term != 15) v[k] = (long long)__ldcg(acc + n_rows + (size_t)order[p] * kTermsPerGroup + term);
-                else {
-                    const uint32_t off = q == 8 ? d.w : (q == 4 ? d.x : (q == 2 ? d.y : d.z));
-                    const int row = (int)(off >> 7);
-                    v[k] = row == rows_alloc ? 0ll : (long long)__ldcg(acc + row);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < kBatch; ++k) {
-                long long x = v[k];
-#pragma unroll
-                for (int bit = 1; bit < 16; bit <<= 1) {
-                    const long long other = __shfl_xor_sync(0xFFFFFFFFu, x, bit);
-                    if (!(q & bit)) x -= other;  // exact[S] = #cells whose set of ones is exactly S
-                }
-                // q = target << 3 | minterm  ->  counts[g][2 * minterm + target]
-                if (g[k] >= 0) {
-                    const size_t at = (size_t)g[k] * 16 + (((q & 7) << 1) | (q >> 3));
-                    out_counts[at] = x;
-                    for (int d = 0; d < (peer_regions ? n_ranks : 0); ++d)
-                        st_peer(reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(peer_regions[d]) +
-                                                                      kPeerSlotsOffset) + peer_slot + at,
-                                peer_word(s_epoch + 1u, x));
-                }
-            }
-        }
-    }
+    // last CTA: Moebius inversion of the subset sums (moebius_pass above)
+    moebius_pass(desc, order, acc, n_rows, rows_alloc, n_groups, n_groups, n_cells, out_counts, peer_regions, n_ranks,
+                 peer_slot, s_epoch + 1u, tid, false);
     // leave the scratch as it was found (all zero) so the next call needs no memset
     __syncthreads();
 

@@ -30,7 +30,7 @@ def main():
     last = np.argmax(t[:, 9] > 0) if (t[:, 9] > 0).any() else -1
     lasts = np.nonzero(buf[:n_cta, 8] > buf[:n_cta, 7])[0]
     for c in lasts[-1:]:
-        print(f"last CTA {c}: finalize {buf[c,8]-buf[c,7]} cycles, clean {buf[c,9]-buf[c,8]} cycles")
+        print(f"last CTA {c}: finalize {buf[c,8]-buf[c,7]} cycles (loads issued at +{buf[c,10]-buf[c,7]}, landed at +{buf[c,11]-buf[c,7]}), clean {buf[c,9]-buf[c,8]} cycles")
     print(f"total entry->ticket: median {np.median(t[:,7]-t[:,0]):.0f} max {(t[:,7]-t[:,0]).max():.0f} cycles")
 
 main()
