@@ -202,7 +202,7 @@ def run_reference(args):
         return
     procs = os.cpu_count() or 1
     specs, planes_np = synth.synthetic_dataset(args.nodes, 4096, args.seed, flip=0.05, relax_steps=5)
-    sample_cells, sample_ind = 1000, 1
+    sample_cells, sample_ind = 4096, 1
     times, rates = [], []
     for i in range(args.warmup + args.steps):
         rate, dt, n_tasks = cpu_fitness_sample(specs, planes_np, sample_cells, sample_ind, args.seed + i, procs)
@@ -282,9 +282,22 @@ def run_ours(args):
     # sharded cells: the per-shard counts are summed over peer memory (NVLink), fused into the
     # fitness kernel -- no library collective in the step (--nccl keeps the ncclAllReduce variant)
     exchange = None
+    exchange_note = ""
     if world > 1 and not args.nccl:
         from scbonita2_b200.distributed import PeerExchange
-        exchange = PeerExchange.create(args.nodes)
+        try:
+            exchange = PeerExchange.create(args.nodes)
+            ok = 1
+        except Exception as exc:     # e.g. CUDA IPC not permitted between the processes of this box
+            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc})", file=sys.stderr)
+            ok = 0
+        agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) == 0:   # every rank takes the same path
+            if exchange is not None:
+                exchange.close()
+            exchange = None
+            exchange_note = " (peer memory unavailable on this box)"
 
     def fitness_step(k=0, timers=None):
         # two kernel launches (+ one NCCL all-reduce when sharded); nothing else is enqueued
@@ -462,11 +475,23 @@ def run_ours(args):
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes}
 
+    # integer-pipe view: the per-individual evaluation the reference performs is 4
+    # integer instructions per (node, individual, 32 cells); the joint-count statistic replaces it by
+    # one pass that does not depend on the population, hence a "fraction" far above 1
+    int_peak, int_src = 18081.0, "profiles/r1_int_peaks.jsonl (tools/int_peaks.cu, LOP3 lane-ops on this B200)"
+    algo_int = units_per_step / world * 4.0 / 32.0
+    roofline_int = {"bound": "int_pipe", "achieved": algo_int / (ms_per_step * 1e-3) / 1e9, "peak": int_peak,
+                    "unit": "Gop/s", "frac": algo_int / (ms_per_step * 1e-3) / 1e9 / int_peak,
+                    "peak_source": int_src,
+                    "note": "algorithmic ops of evaluating every individual's rule on every cell (4 per 32 "
+                            "cells); the 16 joint counts per node are a sufficient statistic, so the pass over "
+                            "the cells is done once for the whole population"}
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        rate, dt, n_tasks = cpu_fitness_sample(specs, planes_np, 2000, 1, args.seed, 1)
+        rate, dt, n_tasks = cpu_fitness_sample(specs, planes_np, 12000, 1, args.seed, 1)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"1 individual x {args.nodes} nodes x 2000 cells = {n_tasks} calculate_error "
+                        "sample": f"1 individual x {args.nodes} nodes x 12000 cells = {n_tasks} calculate_error "
                                   f"calls (Python eval per cell), {dt:.1f} s, single process like the reference"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -475,13 +500,13 @@ def run_ours(args):
             "config": workload_config(args, {
                 "exchange": ("none (1 GPU)" if world == 1 else
                              "peer memory: counts pushed over NVLink, summed inside the fitness kernel"
-                             if exchange is not None else "ncclAllReduce(int64) between the kernels"),
+                             if exchange is not None else "ncclAllReduce(int64) between the kernels" + exchange_note),
                 "timing": f"K steps back to back between one CUDA event pair; inputs larger than L2: step k reads "
                           f"copy k % {n_rot} of the bitplanes ({n_rot} x {plane_bytes / 1e6:.1f} MB > 2 x 126 MB L2)",
                 "wall_s_timed_region": wall, "fitness_checksum": checksum,
                 "launch": "one cuda graph of K steps" if graph is not None else "eager",
                 "ms_per_step_eager": eager_ms, "ms_per_step_isolated_l2_flushed": isolated_ms}),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "sweep": sweep,
+            "roofline": roofline, "roofline_int": roofline_int, "cpu_baseline": cpu_baseline, "e2e": e2e, "sweep": sweep,
             "clocks": clk, "gpu_launches": 2 * args.steps}
     print(json.dumps(line), flush=True)
     if world > 1:
