@@ -100,9 +100,14 @@ struct SweepArgs {
     uint32_t* np_states;            // [steps][N][wpad]  normal-run states from each cell's own mu
     uint32_t* np_lam;               // [6][wpad]         lambda of the normal run, bit-sliced
     uint32_t* np_found;             // [wpad]
-    int32_t* cells;                 // [N][cap] deferred cells per knocked node (KO and KI travel together)
-    int64_t cap;
-    unsigned int* node_count;       // [N] entries used in each list
+    // per-node lists of deferred cells (KO and KI of a cell travel together): a pass reads the
+    // `in` lists (gather modes) and appends the cells it leaves open to the `out` lists
+    const int32_t* in_cells;        // [N][in_cap]
+    int64_t in_cap;
+    const unsigned int* in_count;   // [N] entries used
+    int32_t* out_cells;             // [N][out_cap]
+    int64_t out_cap;
+    unsigned int* out_count;        // [N]
     unsigned int* counters;         // [1] flags (bit 0: normal run has lambda >= 3 or an unsettled cell)
     int fast_steps;                 // KO/KI: steps of the ring fast path before open cells are deferred
     unsigned long long* out_raw;
@@ -110,7 +115,13 @@ struct SweepArgs {
     unsigned long long* out_keyerror;
 };
 
-enum { MODE_NORMAL = 0, MODE_KOKI = 1, MODE_CLEANUP = 2 };
+// MODE_NORMAL  the unperturbed run (ring fast path, slow path in place)
+// MODE_KOKI    KO/KI of every node on the plane words: ring fast path for the first `fast_steps`
+//              steps, cells still open are appended to the out lists
+// MODE_RECHECK deferred cells, compacted 32 to a virtual word: the full-length ring fast path; what is
+//              still open (long cycles, no repeat) goes to the out lists
+// MODE_CLEANUP deferred cells, compacted: the general slow path (Brent + replays)
+enum { MODE_NORMAL = 0, MODE_KOKI = 1, MODE_CLEANUP = 2, MODE_RECHECK = 3 };
 
 constexpr int kRing = 4;  // state copies per slot: ring of the fast path, P/Q pairs of the slow path
 
@@ -137,6 +148,8 @@ sweep_kernel(const SweepArgs args) {
     int* pre = reinterpret_cast<int*>(nrm + (1 + kLamPlanes) * HALF);  // [N + 1]
     __shared__ int s_node;
 
+    constexpr bool IS_GATHER = MODE == MODE_CLEANUP || MODE == MODE_RECHECK;
+    constexpr bool DEFERS = MODE == MODE_KOKI || MODE == MODE_RECHECK;
     const int tid = threadIdx.x;
     const int slot = tid % SLOTS;
     const int part = tid / SLOTS;
@@ -154,13 +167,13 @@ sweep_kernel(const SweepArgs args) {
         masks[n] = expand_lut(e.lut);
     }
     int total_batches = 0;
-    if (MODE == MODE_CLEANUP) {
+    if (IS_GATHER) {
         if (tid == 0) {
             int acc = 0;
             for (int k = 0; k < N; ++k) {
                 pre[k] = acc;
-                int64_t cnt = args.node_count[k];
-                if (cnt > args.cap) cnt = args.cap;
+                int64_t cnt = args.in_count[k];
+                if (cnt > args.in_cap) cnt = args.in_cap;
                 acc += (int)((cnt + BATCH_CELLS - 1) / BATCH_CELLS);
             }
             pre[N] = acc;
@@ -168,11 +181,11 @@ sweep_kernel(const SweepArgs args) {
         __syncthreads();
         total_batches = pre[N];
     }
-    const bool deep_ring = MODE == MODE_KOKI ? (args.counters[1] & 1u) != 0 : true;
+    const bool deep_ring = DEFERS ? (args.counters[1] & 1u) != 0 : true;
 
     int batch = blockIdx.x;
     do {
-        if (MODE == MODE_CLEANUP && batch >= total_batches) break;
+        if (IS_GATHER && batch >= total_batches) break;
         // ------------------------------------------------------------ what this slot simulates
         int64_t word;
         int forced_node = -1;
@@ -199,13 +212,13 @@ sweep_kernel(const SweepArgs args) {
             __syncthreads();
             forced_node = s_node;
             forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
-            int64_t cnt = args.node_count[forced_node];
-            if (cnt > args.cap) cnt = args.cap;
+            int64_t cnt = args.in_count[forced_node];
+            if (cnt > args.in_cap) cnt = args.in_cap;
             const int64_t first = ((int64_t)(batch - pre[forced_node]) * HALF + (slot % HALF)) * 32;
             if (slot < HALF)
                 for (int ln = part; ln < 32; ln += S)
                     cellidx[slot * 32 + ln] =
-                        first + ln < cnt ? args.cells[(size_t)forced_node * args.cap + first + ln] : -1;
+                        first + ln < cnt ? args.in_cells[(size_t)forced_node * args.in_cap + first + ln] : -1;
             __syncthreads();
             word = 0;
             cellmask = 0;
@@ -229,7 +242,7 @@ sweep_kernel(const SweepArgs args) {
         auto at = [&](int k, int n) -> uint32_t& { return state[(n * 4 + k) * SLOTS + slot]; };
         auto load_data = [&](int k) {
             for (int n = n_lo; n < n_hi; ++n) {
-                if (MODE == MODE_CLEANUP)
+                if (IS_GATHER)
                     at(k, n) = gather_bits(args.planes + (size_t)n * wpad, cellmask);
                 else
                     at(k, n) = word_ok ? __ldg(args.planes + (size_t)n * wpad + word) : 0u;
@@ -324,8 +337,8 @@ sweep_kernel(const SweepArgs args) {
             unresolved = ~frozen;
         }
 
-        // ---------------------------------------------- KO/KI: hand unsettled cells to the cleanup
-        if (MODE == MODE_KOKI) {
+        // ------------------------------------- KO/KI, recheck: hand unsettled cells to the next pass
+        if (DEFERS) {
             if (part == 0) xchg[slot] = unresolved;
             __syncthreads();
             const uint32_t both = unresolved | xchg[(slot + HALF) % SLOTS];  // KO and KI travel together
@@ -333,13 +346,16 @@ sweep_kernel(const SweepArgs args) {
                 uint32_t deferred = 0;
                 if (both) {  // reserve room in the node's list; a full list keeps the cells here
                     const unsigned int k = __popc(both);
-                    const unsigned int at0 = atomicAdd(&args.node_count[forced_node], k);
-                    if ((int64_t)at0 + k <= args.cap) {
-                        int32_t* dst = args.cells + (size_t)forced_node * args.cap + at0;
-                        for (uint32_t m = both; m; m &= m - 1) *dst++ = (int32_t)(word * 32 + __ffs(m) - 1);
+                    const unsigned int at0 = atomicAdd(&args.out_count[forced_node], k);
+                    if ((int64_t)at0 + k <= args.out_cap) {
+                        int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + at0;
+                        for (uint32_t m = both; m; m &= m - 1) {
+                            const int ln = __ffs(m) - 1;
+                            *dst++ = IS_GATHER ? cellidx[slot * 32 + ln] : (int32_t)(word * 32 + ln);
+                        }
                         deferred = both;
                     } else {
-                        atomicSub(&args.node_count[forced_node], k);
+                        atomicSub(&args.out_count[forced_node], k);
                     }
                 }
                 xchg[SLOTS + slot] = deferred;
@@ -494,7 +510,7 @@ sweep_kernel(const SweepArgs args) {
             const uint32_t partner = xchg[(slot + HALF) % SLOTS];
             uint32_t found_n;
             uint32_t lamn[kLamPlanes];
-            if (MODE == MODE_CLEANUP) {
+            if (IS_GATHER) {
                 // thread (slot < HALF, part q) assembles plane q of the normal run for its virtual word
                 if (slot < HALF && part < 1 + kLamPlanes)
                     nrm[part * HALF + slot] = gather_bits(
@@ -528,7 +544,7 @@ sweep_kernel(const SweepArgs args) {
                     uint32_t sc = 0;
                     for (int n = n_lo; n < n_hi; ++n) {
                         const uint32_t* row = args.np_states + ((size_t)t * N + n) * wpad;
-                        uint32_t ref = MODE == MODE_CLEANUP ? gather_bits(row, act) : __ldg(row + word);
+                        uint32_t ref = IS_GATHER ? gather_bits(row, act) : __ldg(row + word);
                         sc += __popc((at(xs, n) ^ ref) & act);
                     }
                     score += sc;
@@ -550,8 +566,8 @@ sweep_kernel(const SweepArgs args) {
             if ((tid & 31) == 0 && score) atomicAdd(args.out_raw + forced_node, score);
         }
         batch += gridDim.x;
-        if (MODE == MODE_CLEANUP) __syncthreads();
-    } while (MODE == MODE_CLEANUP);
+        if (IS_GATHER) __syncthreads();
+    } while (IS_GATHER);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -612,29 +628,50 @@ static size_t sweep_smem_bytes(int n_nodes, int slots) {
            (size_t)(slots / 2) * 32 * 4 + (size_t)(1 + kLamPlanes) * (slots / 2) * 4 + (size_t)(n_nodes + 1) * 4;
 }
 
-// room per node for deferred cells; a full list only means its cells are settled in place
-static int64_t sweep_list_capacity(int64_t n_cells) {
-    int64_t div = 8;
-    if (const char* e = getenv("SCB_SWEEP_CAP_DIV")) div = atoi(e) > 0 ? atoi(e) : 8;  // experiments
+// room per node for deferred cells (list A: a quarter of the cells, list B: an eighth); a full list
+// only means its cells are settled in place
+static int64_t sweep_list_capacity(int64_t n_cells, int div) {
     int64_t cap = n_cells / div;
     if (cap < 65536) cap = 65536;
     return cap < n_cells ? cap : n_cells;
 }
+constexpr int kListDivA = 4, kListDivB = 8;
 
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB
 
+// Lists of deferred cells: list A takes what the KO/KI pass leaves open after `fast_steps` ring steps
+// (slow convergers and hard cells alike), list B what the recheck pass leaves open after the full
+// number of steps (cycles longer than the ring, no repeat).  A full list only means that its cells
+// are settled in place.
+struct SweepLists {
+    int32_t* cells_a;
+    int64_t cap_a;
+    unsigned int* count_a;
+    int32_t* cells_b;
+    int64_t cap_b;
+    unsigned int* count_b;
+};
+
 template <int SLOTS>
-static int launch_sweep(const SweepArgs& args, cudaStream_t stream) {
+static int launch_sweep(SweepArgs args, const SweepLists& lists, cudaStream_t stream) {
     size_t smem = sweep_smem_bytes(args.n_nodes, SLOTS);
     int64_t n_words = (args.n_cells + 31) / 32;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_KOKI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_RECHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_CLEANUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    SCB_CUDA(cudaMemsetAsync(args.node_count, 0, (size_t)args.n_nodes * 4 + 16, stream));
+    // count_a | count_b | counters are contiguous
+    SCB_CUDA(cudaMemsetAsync(lists.count_a, 0, (size_t)args.n_nodes * 8 + 16, stream));
+    args.in_cells = nullptr;
+    args.in_cap = 0;
+    args.in_count = nullptr;
+    args.out_cells = nullptr;
+    args.out_cap = 0;
+    args.out_count = nullptr;
     dim3 grid_n((unsigned)((n_words + SLOTS - 1) / SLOTS));
     sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<normal>");
@@ -643,11 +680,33 @@ static int launch_sweep(const SweepArgs& args, cudaStream_t stream) {
         if (ring[0] == '2') SCB_CUDA(cudaMemsetAsync(args.counters + 1, 0, 1, stream));
     }
     constexpr int HALF = SLOTS / 2;
+    const bool two_level = args.fast_steps < args.steps;
+    // KO/KI on the plane words; open cells go to list A (or straight to B without a recheck pass)
+    args.out_cells = two_level ? lists.cells_a : lists.cells_b;
+    args.out_cap = two_level ? lists.cap_a : lists.cap_b;
+    args.out_count = two_level ? lists.count_a : lists.count_b;
     dim3 grid_k((unsigned)((n_words + HALF - 1) / HALF), (unsigned)args.n_nodes);
     sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<koki>");
-    // stragglers, compacted: a persistent grid walks the deferred (word, node) pairs
     int per_sm = smem <= kMaxDynSmem / 2 ? 2 : 1;
+    if (two_level) {
+        // slow convergers, compacted: a persistent grid runs the full-length ring on list A
+        args.in_cells = lists.cells_a;
+        args.in_cap = lists.cap_a;
+        args.in_count = lists.count_a;
+        args.out_cells = lists.cells_b;
+        args.out_cap = lists.cap_b;
+        args.out_count = lists.count_b;
+        sweep_kernel<SLOTS, MODE_RECHECK><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
+        SCB_LAUNCH_CHECK("sweep_kernel<recheck>");
+    }
+    // stragglers, compacted: the general slow path on list B
+    args.in_cells = lists.cells_b;
+    args.in_cap = lists.cap_b;
+    args.in_count = lists.count_b;
+    args.out_cells = nullptr;
+    args.out_cap = 0;
+    args.out_count = nullptr;
     sweep_kernel<SLOTS, MODE_CLEANUP><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<cleanup>");
     return SCB_OK;
@@ -659,9 +718,11 @@ using namespace scb;
 
 extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int steps) {
     if (n_nodes <= 0 || wpad <= 0 || steps <= 0) return 0;
-    // normal-run states + lambda planes + found plane + per-node lists of deferred cells + counters
+    // normal-run states + lambda planes + found plane + the two per-node lists of deferred cells +
+    // their fill counts + counters
     return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4 +
-           (int64_t)n_nodes * sweep_list_capacity(wpad * 32) * 4 + (int64_t)n_nodes * 4 + 16;
+           (int64_t)n_nodes * (sweep_list_capacity(wpad * 32, kListDivA) + sweep_list_capacity(wpad * 32, kListDivB)) * 4 +
+           (int64_t)n_nodes * 8 + 16;
 }
 
 extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
@@ -691,19 +752,29 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.np_states = static_cast<uint32_t*>(scratch);
     args.np_lam = args.np_states + (size_t)steps * n_nodes * wpad;
     args.np_found = args.np_lam + (size_t)kLamPlanes * wpad;
-    args.cap = sweep_list_capacity(wpad * 32);
-    args.cells = reinterpret_cast<int32_t*>(args.np_found + wpad);
-    args.node_count = reinterpret_cast<unsigned int*>(args.cells + (size_t)n_nodes * args.cap);
-    args.counters = args.node_count + n_nodes;  // followed by 16 spare bytes
+    SweepLists lists;
+    lists.cap_a = sweep_list_capacity(wpad * 32, kListDivA);
+    lists.cap_b = sweep_list_capacity(wpad * 32, kListDivB);
+    lists.cells_a = reinterpret_cast<int32_t*>(args.np_found + wpad);
+    lists.cells_b = lists.cells_a + (size_t)n_nodes * lists.cap_a;
+    lists.count_a = reinterpret_cast<unsigned int*>(lists.cells_b + (size_t)n_nodes * lists.cap_b);
+    lists.count_b = lists.count_a + n_nodes;
+    args.counters = lists.count_b + n_nodes;  // followed by 16 spare bytes
+    // Default: the KO/KI pass runs the ring for all `steps` and only cells the ring cannot settle are
+    // deferred (list B).  SCB_SWEEP_FAST_STEPS=k cuts the pass after k steps and sends the open cells
+    // through the compacted recheck pass first -- measured on imp-1M: 254 ms (default), 297 ms (k=32),
+    // 331 ms (k=24): gathering a compacted cell's bits costs ~10 ns per (cell, node) against 1.1 ns
+    // for leaving it where it is, so the early cut does not pay on this data.
     args.fast_steps = steps;
-    if (const char* e = getenv("SCB_SWEEP_FAST_STEPS")) args.fast_steps = atoi(e) > 0 ? atoi(e) : steps;  // experiments
+    if (const char* e = getenv("SCB_SWEEP_FAST_STEPS")) args.fast_steps = atoi(e) > 0 ? atoi(e) : steps;
+    if (args.fast_steps > steps) args.fast_steps = steps;
     args.out_raw = reinterpret_cast<unsigned long long*>(out_raw);
     args.out_missing = reinterpret_cast<unsigned long long*>(out_missing);
     args.out_keyerror = reinterpret_cast<unsigned long long*>(out_keyerror);
     const char* force = getenv("SCB_SWEEP_SLOTS");  // experiments
     const bool prefer32 = force && force[0] == '3';
-    if (!prefer32 && sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem) return launch_sweep<64>(args, as_stream(stream));
-    if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem) return launch_sweep<32>(args, as_stream(stream));
+    if (!prefer32 && sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem) return launch_sweep<64>(args, lists, as_stream(stream));
+    if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem) return launch_sweep<32>(args, lists, as_stream(stream));
     set_error("ko_ki_sweep: %d nodes exceed the shared-memory resident limit (%d)", n_nodes, SCB_MAX_SWEEP_NODES);
     return SCB_ERR_UNSUPPORTED;
 }

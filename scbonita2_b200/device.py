@@ -334,9 +334,11 @@ def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=Non
                                      out[1].data_ptr(), out[2].data_ptr(), _stream()),
                    "scb_ko_ki_sweep")
         if stats:  # diagnostic only (synchronises): deferred (word, node) pairs and ring-depth flag
-            tail = scratch[nbytes - 16 - 4 * n:nbytes].view(torch.int32).cpu().numpy()
-            LAST_SWEEP_STATS.update(deferred_cells=int(tail[:n].sum()), deferred_max_per_node=int(tail[:n].max()),
-                                    deep_ring=bool(tail[n + 1] & 1), cell_node_pairs=int(planes.n_cells) * n)
+            tail = scratch[nbytes - 16 - 8 * n:nbytes].view(torch.int32).cpu().numpy()
+            LAST_SWEEP_STATS.update(rechecked_cells=int(tail[:n].sum()), rechecked_max_per_node=int(tail[:n].max()),
+                                    deferred_cells=int(tail[n:2 * n].sum()),
+                                    deferred_max_per_node=int(tail[n:2 * n].max()),
+                                    deep_ring=bool(tail[2 * n + 1] & 1), cell_node_pairs=int(planes.n_cells) * n)
     return out
 
 
