@@ -27,6 +27,8 @@
 // (importance_scores.py:278).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "scb_common.cuh"
 
 namespace scb {
@@ -100,6 +102,12 @@ struct SweepArgs {
     uint32_t* np_states;            // [steps][N][wpad]  normal-run states from each cell's own mu
     uint32_t* np_lam;               // [6][wpad]         lambda of the normal run, bit-sliced
     uint32_t* np_found;             // [wpad]
+    // cell-major copies (bit n%32 of word n/32 of cell c's record = node n), read by the passes that
+    // simulate compacted lists of cells: a cell's whole state is ONE 16/32-byte record
+    uint32_t* planes_t;             // [wpad*32][nwp]         the data
+    uint32_t* np_states_t;          // [steps][wpad*32][nwp]  normal-run states from each cell's own mu
+    int nwp;                        // words per record: ceil(N/32) rounded up to a multiple of 4
+    uint32_t* np_info_t;            // [wpad*32]  bits 0..5 lambda, bit 6 found (np_lam | np_found, cell-major)
     // per-node lists of deferred cells (KO and KI of a cell travel together): a pass reads the
     // `in` lists (gather modes) and appends the cells it leaves open to the `out` lists
     const int32_t* in_cells;        // [N][in_cap]
@@ -115,6 +123,55 @@ struct SweepArgs {
     unsigned long long* out_keyerror;
 };
 
+// Bit-matrix transpose: node-major bitplanes src[slice][n_rows][wpad] (bit c%32 of word c/32 of row
+// n) -> cell-major records dst[slice][wpad*32][nwp] (bit n%32 of word n/32 of cell c).  One CTA
+// moves a tile of 32 rows x 32 words: coalesced row reads into shared memory, then one warp per
+// word column -- lane b holds row b's word, bit l of every lane is collected with a ballot and
+// kept by lane l, which ends up with the 32 row bits of cell l.  Slices past *last_slice (when
+// given) are skipped: the normal run only fills the slices its longest cycle needs.
+__global__ void __launch_bounds__(256)
+cell_major_kernel(const uint32_t* __restrict__ src, int n_rows, int64_t wpad, uint32_t* __restrict__ dst,
+                  int nwp, const unsigned int* __restrict__ last_slice) {
+    if (last_slice && blockIdx.z > *last_slice) return;
+    __shared__ uint32_t tile[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w0 = (int64_t)blockIdx.x * 32;
+    const int j = blockIdx.y;
+    src += (size_t)blockIdx.z * n_rows * wpad;
+    dst += (size_t)blockIdx.z * wpad * 32 * nwp;
+    for (int r = warp; r < 32; r += 8) {
+        const int row = 32 * j + r;
+        tile[r][lane] = (row < n_rows && w0 + lane < wpad) ? __ldg(src + (size_t)row * wpad + w0 + lane) : 0u;
+    }
+    __syncthreads();
+    for (int wc = warp; wc < 32; wc += 8) {
+        if (w0 + wc >= wpad) break;
+        const uint32_t v = tile[lane][wc];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+            const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (v >> l) & 1u);
+            if (lane == l) mine = bits;
+        }
+        dst[((size_t)(w0 + wc) * 32 + lane) * nwp + j] = mine;
+    }
+}
+
+#ifdef SCB_TRACE
+// phase clock sums per MODE (tools/trace_sweep.py): [mode][phase] cycles of thread 0, [mode][15] CTAs/batches
+__device__ unsigned long long g_sweep_phase[4][16];
+#define SCB_SWEEP_PHASE(i)                                                         \
+    do {                                                                           \
+        if (tid == 0) {                                                            \
+            const long long now_ = clock64();                                      \
+            atomicAdd(&g_sweep_phase[MODE][i], (unsigned long long)(now_ - trace_t_)); \
+            trace_t_ = now_;                                                       \
+        }                                                                          \
+    } while (0)
+#else
+#define SCB_SWEEP_PHASE(i) do { } while (0)
+#endif
+
 // MODE_NORMAL  the unperturbed run (ring fast path, slow path in place)
 // MODE_KOKI    KO/KI of every node on the plane words: ring fast path for the first `fast_steps`
 //              steps, cells still open are appended to the out lists
@@ -123,12 +180,168 @@ struct SweepArgs {
 // MODE_CLEANUP deferred cells, compacted: the general slow path (Brent + replays)
 enum { MODE_NORMAL = 0, MODE_KOKI = 1, MODE_CLEANUP = 2, MODE_RECHECK = 3 };
 
+#ifndef SCB_REG_RING
+#define SCB_REG_RING 1
+#endif
+constexpr bool kRegRing = SCB_REG_RING != 0;  // experiments: 0 keeps the ring of the fast path in shared memory
+constexpr int kMaskPad = 15;  // all-zero truth tables after the last node
 constexpr int kRing = 4;  // state copies per slot: ring of the fast path, P/Q pairs of the slow path
+
+// Ring-of-2 fast path with the ring in REGISTERS (KO/KI and recheck passes, 64-slot CTAs of 16 warps,
+// N <= 16 * CH, N <= 256).  Thread (lane, warp p) owns nodes [p*CH, p*CH + CH) of the KO slot `lane`
+// AND the KI slot `lane + 32` of the same word: the truth-table masks are fetched once for both, the
+// parent rows of the thread's nodes sit in registers (three bytes of one word per node), the two
+// previous states of its own nodes never leave its registers, and shared memory only holds the
+// current and the next state (copies 3 and 0, swapped every step) for the other warps to read --
+// 10 shared-memory wavefronts per (node, 64 slots, step) instead of 18, and one CTA barrier per step
+// (three sets of vote words: set t%3 is written in step t, read after its barrier, cleared in step
+// t+1 -- by then every reader is past the barrier of step t+1).  The barrier of step t also carries
+// "every lane was frozen after step t-1", so a CTA leaves one (idempotent) step late.
+// Same semantics as the shared-memory ring: a lane whose new state equals state_{t-1} (t >= 1) or
+// state_{t-2} (t >= 2) has its first repeat there and is frozen at it.
+// Results per slot go to votes[0..63] (frozen), [64..127] (lambda bit 0), [128..191] (bit 1);
+// returns the state copy that holds the final states.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((uint32_t)pred) : "memory");
+}
+__device__ __forceinline__ uint32_t shared_addr(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+template <int CH>
+__device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, const NodeOffsets* __restrict__ offs,
+                                               const LutMasks* __restrict__ masks, uint32_t* __restrict__ votes,
+                                               int N, int forced_node, uint32_t cellmask, int t_fast, int tid) {
+    constexpr int SL = 64, STRIDE = 4 * SL, SET = 2 * SL;
+    const int lane = tid & 31;
+    const int n0 = (tid >> 5) * CH;
+    const int n_mine = N - n0;              // node i of this thread exists iff i < n_mine
+    const int forced_i = forced_node - n0;  // ... and is the forced one iff i == forced_i
+    uint32_t xa0[CH], xb0[CH], xa1[CH], xb1[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        xa0[i] = xa1[i] = xb0[i] = xb1[i] = 0u;
+        if (i < n_mine) {
+            xa0[i] = state[((n0 + i) * 4 + 3) * SL + lane];
+            xa1[i] = state[((n0 + i) * 4 + 3) * SL + lane + 32];
+        }
+    }
+    for (int i = tid; i < 3 * SET; i += blockDim.x) votes[i] = 0;
+    __syncthreads();
+    uint32_t frozen0 = ~cellmask, frozen1 = ~cellmask;
+    uint32_t lam0_0 = 0, lam1_0 = 0, lam0_1 = 0, lam1_1 = 0;
+    bool all_prev = false;
+    int vset = 0;  // t % 3
+
+    // one step: reads copy RD, writes copy WR; cur* hold state_{t-1} of the own nodes, prv* state_{t-2}
+    // and receive state_t.  Returns true when the CTA is done.
+    auto step = [&](auto rd_tag, uint32_t (&cur0)[CH], uint32_t (&prv0)[CH], uint32_t (&cur1)[CH],
+                    uint32_t (&prv1)[CH], int t) -> bool {
+        constexpr int RD = decltype(rd_tag)::value ? 3 : 0, WR = decltype(rd_tag)::value ? 0 : 3;
+        uint32_t q10 = 0, q20 = 0, q11 = 0, q21 = 0;
+        const uint32_t* srd = state + RD * SL + lane;
+        uint32_t* swr = state + (n0 * 4 + WR) * SL + lane;
+        if (n_mine > 0) {  // warps past the last node only join the barrier
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                // a node past the end (only in the last warp with nodes: the offset and mask tables are
+                // padded with zero entries) has an all-zero truth table and all-zero registers: it votes
+                // "equal" and only its stores are suppressed
+                const NodeOffsets o = offs[n0 + i];
+                const uint4 lo = *reinterpret_cast<const uint4*>(&masks[n0 + i].m[0]);
+                const uint4 hi = *reinterpret_cast<const uint4*>(&masks[n0 + i].m[4]);
+                const uint32_t a0 = srd[o.pa], b0 = srd[o.pb], c0 = srd[o.pc];
+                const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32], c1 = srd[o.pc + 32];
+                uint32_t f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
+                                         lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
+                uint32_t f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
+                                         lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
+                if (i == forced_i) {  // never true past the end
+                    f0 = 0u;
+                    f1 = 0xFFFFFFFFu;
+                }
+                q10 |= f0 ^ cur0[i];
+                q20 |= f0 ^ prv0[i];
+                q11 |= f1 ^ cur1[i];
+                q21 |= f1 ^ prv1[i];
+                const uint32_t w0 = (f0 & ~frozen0) | (cur0[i] & frozen0);
+                const uint32_t w1 = (f1 & ~frozen1) | (cur1[i] & frozen1);
+                if (i < n_mine) {
+                    swr[i * STRIDE] = w0;
+                    swr[i * STRIDE + 32] = w1;
+                }
+                prv0[i] = w0;
+                prv1[i] = w1;
+            }
+        }
+        uint32_t* v = votes + vset * SET;
+        if (q10) atomicOr(v + lane, q10);
+        if (q11) atomicOr(v + 32 + lane, q11);
+        if (q20) atomicOr(v + SL + lane, q20);
+        if (q21) atomicOr(v + SL + 32 + lane, q21);
+        if (__syncthreads_and(all_prev)) return true;  // nothing moved in this step: copy RD holds the result
+        // state_{t-d} exists for t >= d only (the raw data state is never compared)
+        uint32_t open = ~frozen0;
+        uint32_t e1 = t >= 1 ? ~v[lane] & open : 0u;
+        open &= ~e1;
+        uint32_t e2 = t >= 2 ? ~v[SL + lane] & open : 0u;
+        lam0_0 |= e1;
+        lam1_0 |= e2;
+        frozen0 |= e1 | e2;
+        open = ~frozen1;
+        e1 = t >= 1 ? ~v[32 + lane] & open : 0u;
+        open &= ~e1;
+        e2 = t >= 2 ? ~v[SL + 32 + lane] & open : 0u;
+        lam0_1 |= e1;
+        lam1_1 |= e2;
+        frozen1 |= e1 | e2;
+        const int vclear = vset == 0 ? 2 : vset - 1;  // (t + 2) % 3
+        if (tid < SET) votes[vclear * SET + tid] = 0;
+        vset = vset == 2 ? 0 : vset + 1;
+        all_prev = (frozen0 & frozen1) == 0xFFFFFFFFu;
+        return false;
+    };
+    using Odd = std::integral_constant<bool, true>;    // reads copy 3
+    using Even = std::integral_constant<bool, false>;  // reads copy 0
+    int result_copy = 3;
+    for (int t = 0; t < t_fast; t += 2) {
+        result_copy = 3;
+        if (step(Odd{}, xa0, xb0, xa1, xb1, t)) break;  // xa = state_{t-1}, xb <- state_t, written to copy 0
+        result_copy = 0;
+        if (t + 1 >= t_fast) break;
+        if (step(Even{}, xb0, xa0, xb1, xa1, t + 1)) break;  // xb = state_t, xa <- state_{t+1}, written to copy 3
+        result_copy = 3;
+    }
+    __syncthreads();  // every vote word has been read
+    if (tid < 32) {
+        votes[lane] = frozen0;
+        votes[32 + lane] = frozen1;
+        votes[64 + lane] = lam0_0;
+        votes[96 + lane] = lam0_1;
+        votes[128 + lane] = lam1_0;
+        votes[160 + lane] = lam1_1;
+    }
+    __syncthreads();
+    return result_copy;
+}
 
 // State layout in shared memory: word (node n, copy k, slot s) lives at ((n*4 + k)*SLOTS + s), so
 // the four copies of a node sit at compile-time offsets from each other.
 template <int SLOTS, int MODE>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, SLOTS >= 64 ? 1 : 2)
 sweep_kernel(const SweepArgs args) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = args.n_nodes;
@@ -137,8 +350,8 @@ sweep_kernel(const SweepArgs args) {
     const int S = blockDim.x / SLOTS;
     uint32_t* state = smem;                                                            // [N][4][SLOTS]
     NodeOffsets* offs = reinterpret_cast<NodeOffsets*>(smem + (size_t)4 * N * SLOTS);  // [N]
-    LutMasks* masks = reinterpret_cast<LutMasks*>(offs + N);                           // [N]
-    uint32_t* votes = reinterpret_cast<uint32_t*>(masks + N);  // [2][kRing][SLOTS] OR-accumulators
+    LutMasks* masks = reinterpret_cast<LutMasks*>(offs + N + kMaskPad);                // [N + pad]
+    uint32_t* votes = reinterpret_cast<uint32_t*>(masks + N + kMaskPad);  // [2][kRing][SLOTS] OR-accumulators
     uint32_t* xchg = votes + 2 * kRing * SLOTS;                // [2][SLOTS]
     // cleanup only: the 32 cell indices behind each virtual word, their normal-run planes, and
     // the per-node batch prefix
@@ -151,6 +364,9 @@ sweep_kernel(const SweepArgs args) {
     constexpr bool IS_GATHER = MODE == MODE_CLEANUP || MODE == MODE_RECHECK;
     constexpr bool DEFERS = MODE == MODE_KOKI || MODE == MODE_RECHECK;
     const int tid = threadIdx.x;
+#ifdef SCB_TRACE
+    long long trace_t_ = clock64();
+#endif
     const int slot = tid % SLOTS;
     const int part = tid / SLOTS;
     const int chunk = (N + S - 1) / S;
@@ -159,6 +375,12 @@ sweep_kernel(const SweepArgs args) {
     constexpr int NODE_STRIDE = 4 * SLOTS;
     constexpr int BATCH_CELLS = HALF * 32;  // cells of one node a cleanup batch simulates
 
+    if (tid < kMaskPad) {  // all-zero entries past the end (ring2_registers)
+        masks[N + tid] = expand_lut(0u);
+        NodeOffsets z;
+        z.pa = z.pb = z.pc = z.pad = 0;
+        offs[N + tid] = z;
+    }
     for (int n = tid; n < N; n += blockDim.x) {
         NodeEntry e = make_entry(args.net_parent, args.net_lut, n);
         NodeOffsets o;
@@ -181,7 +403,11 @@ sweep_kernel(const SweepArgs args) {
         __syncthreads();
         total_batches = pre[N];
     }
-    const bool deep_ring = DEFERS ? (args.counters[1] & 1u) != 0 : true;
+    // KO/KI on the plane words: the short ring when the unperturbed run showed no cycle longer than 2.
+    // The compacted recheck pass always runs the deep ring: a perturbation often creates cycles of
+    // length 3 or 4 (half of the cells the short ring leaves open on the H1M data), and the ring settles
+    // them at a fifth of the cost of the general scheme.
+    const bool deep_ring = MODE == MODE_KOKI ? (args.counters[1] & 1u) != 0 : true;
 
     int batch = blockIdx.x;
     do {
@@ -214,39 +440,73 @@ sweep_kernel(const SweepArgs args) {
             forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
             int64_t cnt = args.in_count[forced_node];
             if (cnt > args.in_cap) cnt = args.in_cap;
-            const int64_t first = ((int64_t)(batch - pre[forced_node]) * HALF + (slot % HALF)) * 32;
-            if (slot < HALF)
-                for (int ln = part; ln < 32; ln += S)
-                    cellidx[slot * 32 + ln] =
-                        first + ln < cnt ? args.in_cells[(size_t)forced_node * args.in_cap + first + ln] : -1;
+            // the batch's cells are consecutive list entries: coalesced copy, virtual word v = entries
+            // [32v, 32v + 32)
+            const int64_t batch_first = (int64_t)(batch - pre[forced_node]) * BATCH_CELLS;
+            for (int i = tid; i < BATCH_CELLS; i += blockDim.x)
+                cellidx[i] = batch_first + i < cnt ? args.in_cells[(size_t)forced_node * args.in_cap + batch_first + i] : -1;
             __syncthreads();
             word = 0;
-            cellmask = 0;
-            for (int ln = 0; ln < 32; ++ln) cellmask |= (uint32_t)(cellidx[(slot % HALF) * 32 + ln] >= 0) << ln;
+            const int64_t left = cnt - (batch_first + (int64_t)(slot % HALF) * 32);
+            cellmask = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << (int)left) - 1u : 0u);
         }
         const bool word_ok = word < wpad;
-        // bit `ln` of the result = bit of cell cellidx[ln] in the bitplane row `row` (cleanup only)
-        auto gather_bits = [&](const uint32_t* __restrict__ row, uint32_t lanes) {
-            uint32_t w = 0;
-            const int* idx = cellidx + (slot % HALF) * 32;
-            while (lanes) {
-                const int ln = __ffs(lanes) - 1;
-                lanes &= lanes - 1;
-                const int c = idx[ln];
-                w |= ((__ldg(row + (c >> 5)) >> (c & 31)) & 1u) << ln;
-            }
-            return w;
-        };
         for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
 
         auto at = [&](int k, int n) -> uint32_t& { return state[(n * 4 + k) * SLOTS + slot]; };
-        auto load_data = [&](int k) {
-            for (int n = n_lo; n < n_hi; ++n) {
-                if (IS_GATHER)
-                    at(k, n) = gather_bits(args.planes + (size_t)n * wpad, cellmask);
-                else
-                    at(k, n) = word_ok ? __ldg(args.planes + (size_t)n * wpad + word) : 0u;
+        // gather modes: copy k of every node, both halves, from the cell-major records of the batch's
+        // cells; `kstage` names a state copy that is dead at the call (staging area).  One warp per
+        // virtual word: lane = cell, 128-bit loads fetch its record, every record word goes through 32
+        // ballots (lane b keeps the word of node 32j + b) and is parked in copy kstage at a rotated slot
+        // position -- lanes hold different nodes, whose rows all start on the same bank, and the
+        // rotation by the node index spreads them over the banks.  After a barrier every thread
+        // moves the words of its own (slot, nodes) into copy k, again conflict-free.
+        auto load_cells = [&](const uint32_t* __restrict__ src_t, int k, int kstage) {
+            const int lane = tid & 31;
+            const int nwp = args.nwp;
+            const int n_warps = blockDim.x >> 5;
+            for (int v0 = tid >> 5; v0 < HALF; v0 += 2 * n_warps) {
+                // two virtual words per round: their record loads fly together
+                const int v1 = v0 + n_warps;
+                const int c0 = cellidx[v0 * 32 + lane];
+                const int c1 = v1 < HALF ? cellidx[v1 * 32 + lane] : -1;
+                for (int j4 = 0; j4 < nwp; j4 += 4) {
+                    uint4 x0 = make_uint4(0u, 0u, 0u, 0u), x1 = x0;
+                    if (c0 >= 0) x0 = __ldg(reinterpret_cast<const uint4*>(src_t + (size_t)c0 * nwp + j4));
+                    if (c1 >= 0) x1 = __ldg(reinterpret_cast<const uint4*>(src_t + (size_t)c1 * nwp + j4));
+                    const uint32_t xw[2][4] = {{x0.x, x0.y, x0.z, x0.w}, {x1.x, x1.y, x1.z, x1.w}};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int v = h ? v1 : v0;
+                        if (v >= HALF) break;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int nb = (j4 + q) * 32;
+                            if (nb < N) {
+                                uint32_t mine = 0;
+#pragma unroll
+                                for (int b = 0; b < 32; ++b) {
+                                    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (xw[h][q] >> b) & 1u);
+                                    if (lane == b) mine = bits;
+                                }
+                                const int n = nb + lane;
+                                if (n < N) state[(n * 4 + kstage) * SLOTS + ((v + n) % HALF)] = mine;
+                            }
+                        }
+                    }
+                }
             }
+            __syncthreads();
+            for (int n = n_lo; n < n_hi; ++n)
+                at(k, n) = state[(n * 4 + kstage) * SLOTS + ((slot + n) % HALF)];
+        };
+        auto load_data = [&](int k, int kstage) {
+            if (IS_GATHER) {
+                load_cells(args.planes_t, k, kstage);
+                return;
+            }
+            for (int n = n_lo; n < n_hi; ++n)
+                at(k, n) = word_ok ? __ldg(args.planes + (size_t)n * wpad + word) : 0u;
         };
         // next value of node n for my slot, reading state copy k
         auto step_node = [&](int k, int n) {
@@ -277,11 +537,23 @@ sweep_kernel(const SweepArgs args) {
         // 2 when the unperturbed run showed no longer cycles; anything else is settled later).
         if (MODE != MODE_CLEANUP) {
             const bool deep = deep_ring;
-            load_data(kRing - 1);
+            SCB_SWEEP_PHASE(0);
+            load_data(kRing - 1, 0);
             __syncthreads();
+            SCB_SWEEP_PHASE(1);
             uint32_t frozen = ~cellmask;
             const int t_fast = MODE == MODE_KOKI ? min(steps, args.fast_steps) : steps;
-            for (int t = 0; t < t_fast; ++t) {
+            const bool reg_ring = DEFERS && SLOTS == 64 && kSweepThreads == 512 && !deep && N <= 16 * 13 && kRegRing;
+            if (reg_ring) {
+                xs = N <= 64    ? ring2_registers<4>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid)
+                     : N <= 128 ? ring2_registers<8>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid)
+                                : ring2_registers<13>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid);
+                frozen = votes[slot];
+                lam[0] = votes[64 + slot];
+                lam[1] = votes[128 + slot];
+                __syncthreads();  // votes is reused below
+            }
+            for (int t = 0; t < (reg_ring ? 0 : t_fast); ++t) {
                 const int ks = (t + 3) & 3, kd = t & 3, k2 = (t + 2) & 3, k3 = (t + 1) & 3;
                 uint32_t neq1 = 0, neq2 = 0, neq3 = 0, neq4 = 0;
                 if (deep) {
@@ -335,6 +607,7 @@ sweep_kernel(const SweepArgs args) {
             xn = (xs + 1) & 3;
             found = frozen & cellmask;
             unresolved = ~frozen;
+            SCB_SWEEP_PHASE(2);
         }
 
         // ------------------------------------- KO/KI, recheck: hand unsettled cells to the next pass
@@ -366,6 +639,7 @@ sweep_kernel(const SweepArgs args) {
             found &= cellmask;
             unresolved = both & ~deferred;
             __syncthreads();  // xchg is reused below
+            SCB_SWEEP_PHASE(3);
         }
 
         // -------------------------------------------------------------------- slow path
@@ -376,7 +650,7 @@ sweep_kernel(const SweepArgs args) {
             const int cur0 = 0, nxt0 = 1, chk = 2;
             int cur = cur0, nxt = nxt0;
             for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
-            load_data(cur);
+            load_data(cur, nxt);
             __syncthreads();
             uint32_t resolved = ~cellmask;
 #pragma unroll
@@ -427,8 +701,8 @@ sweep_kernel(const SweepArgs args) {
             if (__syncthreads_or(cyc != 0)) {
                 int pc_ = 0, pn_ = 1;  // P: runs lambda ahead
                 int qc_ = 2, qn_ = 3;  // Q: freezes at state_mu
-                load_data(pc_);
-                load_data(qc_);
+                load_data(pc_, pn_);
+                load_data(qc_, qn_);
                 for (int i = tid; i < 2 * kRing * SLOTS; i += blockDim.x) votes[i] = 0;
                 __syncthreads();
                 const uint32_t has_lam = planes_ge(lam, 1) & cellmask;
@@ -479,6 +753,17 @@ sweep_kernel(const SweepArgs args) {
             found &= cellmask;
         }
 
+        SCB_SWEEP_PHASE(4);
+#ifdef SCB_TRACE
+        if (MODE == MODE_CLEANUP && part == 0) {  // histogram of what the general scheme had to settle
+            const uint32_t f = found & cellmask;
+            atomicAdd(&g_sweep_phase[MODE][8], (unsigned long long)__popc(~found & cellmask));           // no repeat
+            atomicAdd(&g_sweep_phase[MODE][9], (unsigned long long)__popc(f & ~planes_ge(lam, 3)));        // 1, 2
+            atomicAdd(&g_sweep_phase[MODE][10], (unsigned long long)__popc(f & planes_ge(lam, 3) & ~planes_ge(lam, 5)));  // 3, 4
+            atomicAdd(&g_sweep_phase[MODE][11], (unsigned long long)__popc(f & planes_ge(lam, 5) & ~planes_ge(lam, 9)));  // 5..8
+            atomicAdd(&g_sweep_phase[MODE][12], (unsigned long long)__popc(f & planes_ge(lam, 9)));        // > 8
+        }
+#endif
         // -------------------------------------------------------------------- outputs
         if (MODE == MODE_NORMAL) {
             if (part == 0 && word_ok) {
@@ -489,6 +774,13 @@ sweep_kernel(const SweepArgs args) {
                 if (miss) atomicAdd(args.out_missing, (unsigned long long)miss);
                 // tell the KO/KI pass whether the short ring is enough for this data set
                 if ((~found & cellmask) || (planes_ge(lam, 3) & found)) atomicOr(&args.counters[1], 1u);
+                // last slice of np_states any cell of this word needs (offsets 0..lambda): an upper bound
+                // from the highest lambda plane in use is enough
+                int hb = -1;
+#pragma unroll
+                for (int b = 0; b < kLamPlanes; ++b)
+                    if (lam[b] & found) hb = b;
+                if (hb >= 0) atomicMax(&args.counters[2], (unsigned int)min(steps - 1, (2 << hb) - 1));
             }
             for (int t = 0; t < steps; ++t) {
                 uint32_t need = found & planes_ge(lam, t);
@@ -511,10 +803,17 @@ sweep_kernel(const SweepArgs args) {
             uint32_t found_n;
             uint32_t lamn[kLamPlanes];
             if (IS_GATHER) {
-                // thread (slot < HALF, part q) assembles plane q of the normal run for its virtual word
-                if (slot < HALF && part < 1 + kLamPlanes)
-                    nrm[part * HALF + slot] = gather_bits(
-                        part == 0 ? args.np_found : args.np_lam + (size_t)(part - 1) * wpad, cellmask);
+                // one warp per virtual word: lane = cell, its normal-run record (bit 0..5 = lambda, bit 6 =
+                // found) is one 4-byte load; seven ballots make the planes
+                for (int v = tid >> 5; v < HALF; v += blockDim.x >> 5) {
+                    const int c = cellidx[v * 32 + (tid & 31)];
+                    const uint32_t rec = c >= 0 ? __ldg(args.np_info_t + c) : 0u;
+#pragma unroll
+                    for (int b = 0; b <= kLamPlanes; ++b) {
+                        const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (rec >> b) & 1u);
+                        if ((tid & 31) == 0) nrm[(b == kLamPlanes ? 0 : 1 + b) * HALF + v] = bits;
+                    }
+                }
                 __syncthreads();
                 found_n = nrm[slot % HALF];
 #pragma unroll
@@ -540,11 +839,18 @@ sweep_kernel(const SweepArgs args) {
             for (int t = 0; t < steps; ++t) {
                 uint32_t act = valid & planes_ge(lam, t) & planes_ge(lamn, t);
                 if (!__syncthreads_or(act != 0)) break;
+                // gather modes: the normal-run states of the batch's cells at offset t, assembled in the
+                // state copy that neither xs nor xn uses
+                const int kref = xs ^ 2;
+                if (IS_GATHER) {
+                    load_cells(args.np_states_t + (size_t)t * wpad * 32 * args.nwp, kref, xn ^ 2);
+                    __syncthreads();
+                }
                 if (act) {
                     uint32_t sc = 0;
                     for (int n = n_lo; n < n_hi; ++n) {
-                        const uint32_t* row = args.np_states + ((size_t)t * N + n) * wpad;
-                        uint32_t ref = IS_GATHER ? gather_bits(row, act) : __ldg(row + word);
+                        const uint32_t ref =
+                            IS_GATHER ? at(kref, n) : __ldg(args.np_states + ((size_t)t * N + n) * wpad + word);
                         sc += __popc((at(xs, n) ^ ref) & act);
                     }
                     score += sc;
@@ -565,6 +871,10 @@ sweep_kernel(const SweepArgs args) {
             for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
             if ((tid & 31) == 0 && score) atomicAdd(args.out_raw + forced_node, score);
         }
+        SCB_SWEEP_PHASE(5);
+#ifdef SCB_TRACE
+        if (tid == 0) atomicAdd(&g_sweep_phase[MODE][15], 1ull);
+#endif
         batch += gridDim.x;
         if (IS_GATHER) __syncthreads();
     } while (IS_GATHER);
@@ -622,8 +932,12 @@ trajectories_kernel(const uint32_t* __restrict__ planes, int n_nodes, int64_t wp
     }
 }
 
+// words of a cell-major record: one bit per node, padded to whole 128-bit loads
+static int record_words(int n_nodes) { return (((n_nodes + 31) / 32) + 3) & ~3; }
+
 static size_t sweep_smem_bytes(int n_nodes, int slots) {
     return (size_t)4 * n_nodes * slots * 4 + (size_t)n_nodes * (sizeof(NodeOffsets) + sizeof(LutMasks)) +
+           (size_t)kMaskPad * (sizeof(NodeOffsets) + sizeof(LutMasks)) +
            (size_t)2 * kRing * slots * 4 + (size_t)2 * slots * 4 +
            (size_t)(slots / 2) * 32 * 4 + (size_t)(1 + kLamPlanes) * (slots / 2) * 4 + (size_t)(n_nodes + 1) * 4;
 }
@@ -635,7 +949,7 @@ static int64_t sweep_list_capacity(int64_t n_cells, int div) {
     if (cap < 65536) cap = 65536;
     return cap < n_cells ? cap : n_cells;
 }
-constexpr int kListDivA = 4, kListDivB = 8;
+constexpr int kListDivA = 1, kListDivB = 1;
 
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB
 
@@ -675,6 +989,21 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, cudaStream_t st
     dim3 grid_n((unsigned)((n_words + SLOTS - 1) / SLOTS));
     sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<normal>");
+    // cell-major copies of the data and of the normal-run states for the compacted passes
+    {
+        const int n_blocks_j = (args.n_nodes + 31) / 32;
+        dim3 grid_t((unsigned)((args.wpad + 31) / 32), (unsigned)n_blocks_j, 1);
+        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes, args.n_nodes, args.wpad, args.planes_t, args.nwp, nullptr);
+        SCB_LAUNCH_CHECK("cell_major_kernel<data>");
+        grid_t.y = 1;   // np_lam[6][wpad] and np_found[wpad] are contiguous: a 7-row matrix, one word per cell
+        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.np_lam, kLamPlanes + 1, args.wpad, args.np_info_t, 1, nullptr);
+        SCB_LAUNCH_CHECK("cell_major_kernel<normal info>");
+        grid_t.y = (unsigned)n_blocks_j;
+        grid_t.z = (unsigned)args.steps;
+        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.np_states, args.n_nodes, args.wpad, args.np_states_t, args.nwp,
+                                                      args.counters + 2);
+        SCB_LAUNCH_CHECK("cell_major_kernel<normal run>");
+    }
     if (const char* ring = getenv("SCB_SWEEP_RING")) {  // experiments: force the KO/KI ring depth
         if (ring[0] == '4') SCB_CUDA(cudaMemsetAsync(args.counters + 1, 1, 1, stream));
         if (ring[0] == '2') SCB_CUDA(cudaMemsetAsync(args.counters + 1, 0, 1, stream));
@@ -716,11 +1045,24 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, cudaStream_t st
 
 using namespace scb;
 
+#ifdef SCB_TRACE
+extern "C" int scb_debug_sweep_phases(unsigned long long* out /*HOST [4][16]*/, int reset) {
+    SCB_CUDA(cudaDeviceSynchronize());
+    SCB_CUDA(cudaMemcpyFromSymbol(out, g_sweep_phase, sizeof(unsigned long long) * 64));
+    if (reset) {
+        unsigned long long zero[64] = {0};
+        SCB_CUDA(cudaMemcpyToSymbol(g_sweep_phase, zero, sizeof(zero)));
+    }
+    return SCB_OK;
+}
+#endif
+
 extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int steps) {
     if (n_nodes <= 0 || wpad <= 0 || steps <= 0) return 0;
     // normal-run states + lambda planes + found plane + the two per-node lists of deferred cells +
     // their fill counts + counters
     return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4 +
+           (int64_t)(steps + 1) * wpad * 32 * record_words(n_nodes) * 4 + wpad * 32 * 4 +
            (int64_t)n_nodes * (sweep_list_capacity(wpad * 32, kListDivA) + sweep_list_capacity(wpad * 32, kListDivB)) * 4 +
            (int64_t)n_nodes * 8 + 16;
 }
@@ -755,7 +1097,11 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     SweepLists lists;
     lists.cap_a = sweep_list_capacity(wpad * 32, kListDivA);
     lists.cap_b = sweep_list_capacity(wpad * 32, kListDivB);
-    lists.cells_a = reinterpret_cast<int32_t*>(args.np_found + wpad);
+    args.nwp = record_words(n_nodes);
+    args.planes_t = args.np_found + wpad;
+    args.np_states_t = args.planes_t + (size_t)wpad * 32 * args.nwp;
+    args.np_info_t = args.np_states_t + (size_t)steps * wpad * 32 * args.nwp;
+    lists.cells_a = reinterpret_cast<int32_t*>(args.np_info_t + (size_t)wpad * 32);
     lists.cells_b = lists.cells_a + (size_t)n_nodes * lists.cap_a;
     lists.count_a = reinterpret_cast<unsigned int*>(lists.cells_b + (size_t)n_nodes * lists.cap_b);
     lists.count_b = lists.count_a + n_nodes;

@@ -14,8 +14,9 @@ planes_np = synth.relax_and_flip(specs, synth.random_planes(200, cells, 1000), c
 nodes = bench.make_nodes(specs)
 planes = device.BitPlanes.from_packed(planes_np, cells)
 par, lut = compile_network(nodes)
-for i in range(3):
+iters = int(os.environ.get("ITERS", 3))
+for i in range(iters):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    out = device.ko_ki_sweep(planes, par, lut, stats=(i == 2))
+    out = device.ko_ki_sweep(planes, par, lut, stats=(i == iters - 1))
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
 print(f"ring={os.environ.get('SCB_SWEEP_RING','auto')} sweep {dt*1e3:.1f} ms  raw {int(out[0].sum().item())}  {device.LAST_SWEEP_STATS}")
