@@ -64,16 +64,33 @@ __device__ __forceinline__ void planes_set(uint32_t (&v)[kLamPlanes], uint32_t l
         if ((value >> b) & 1) v[b] |= lanes;
 }
 
-// fold unused parent slots (-1 reads constant 0) into the table and alias them to row 0
+// Canonical form of a node: the bound parent slots packed to the left (A, AB, ABC) in their
+// original order, the truth table rewritten for the new slots with every unbound slot reading
+// constant 0 (the reference's missing parents), unbound slots aliased to row 0.  The new table does
+// not depend on the unbound slots, so the general three-input evaluation stays valid, and a node
+// with `arity` bound parents can be evaluated from table entries 0/4 (one parent) or 0/2/4/6 (two).
 __device__ __forceinline__ NodeEntry make_entry(const int32_t* __restrict__ net_parent,
-                                                const uint8_t* __restrict__ net_lut, int n) {
+                                                const uint8_t* __restrict__ net_lut, int n, int* arity = nullptr) {
     NodeEntry e;
-    uint32_t lut = net_lut[n];
-    int pa = net_parent[3 * n], pb = net_parent[3 * n + 1], pc = net_parent[3 * n + 2];
-    if (pa < 0) { lut = (lut & 0x0Fu) | ((lut & 0x0Fu) << 4); pa = 0; }
-    if (pb < 0) { lut = (lut & 0x33u) | ((lut & 0x33u) << 2); pb = 0; }
-    if (pc < 0) { lut = (lut & 0x55u) | ((lut & 0x55u) << 1); pc = 0; }
-    e.pa = pa; e.pb = pb; e.pc = pc; e.lut = lut;
+    const uint32_t lut = net_lut[n];
+    int real[3], k = 0, p[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        p[s] = net_parent[3 * n + s];
+        if (p[s] >= 0) real[k++] = s;
+    }
+    uint32_t canon = 0;
+#pragma unroll
+    for (int idx = 0; idx < 8; ++idx) {
+        int orig = 0;  // index into the original table: slot s is bit (2 - s)
+        for (int j = 0; j < k; ++j) orig |= ((idx >> (2 - j)) & 1) << (2 - real[j]);
+        canon |= ((lut >> orig) & 1u) << idx;
+    }
+    e.pa = k > 0 ? p[real[0]] : 0;
+    e.pb = k > 1 ? p[real[1]] : 0;
+    e.pc = k > 2 ? p[real[2]] : 0;
+    e.lut = canon;
+    if (arity) *arity = k;
     return e;
 }
 
@@ -88,7 +105,7 @@ __device__ __forceinline__ uint32_t eval_node(const NodeEntry& e, const uint32_t
 // three parent rows inside the state array and the truth table expanded to 8 full-word masks.
 // Everything is warp-uniform, so each load is a broadcast.
 struct __align__(16) NodeOffsets {
-    int pa, pb, pc, pad;
+    int pa, pb, pc, arity;  // arity: bound parents (packed left); the others alias row 0
 };
 
 
@@ -117,11 +134,28 @@ struct SweepArgs {
     int64_t out_cap;
     unsigned int* out_count;        // [N]
     unsigned int* counters;         // [1] flags (bit 0: normal run has lambda >= 3 or an unsettled cell)
-    int fast_steps;                 // KO/KI: steps of the ring fast path before open cells are deferred
+    int fast_steps;                 // KO/KI: steps of the ring fast path before open cells are deferred;
+                                    // <= 0: chosen on the device from the normal run (counters[3])
+    unsigned int* settle_hist;      // [64] normal run: cells whose first repeat the ring saw in step t
     unsigned long long* out_raw;
     unsigned long long* out_missing;
     unsigned long long* out_keyerror;
 };
+
+// 32 x 32 bit transpose across a warp: lane i passes row i (bit j = element (i, j)) and receives
+// column i (bit j = element (j, i)).  Five exchange steps: at distance d the lanes i and i^d swap the
+// off-diagonal d x d blocks.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        // bits whose index has bit d clear: 0x0000FFFF, 0x00FF00FF, 0x0F0F0F0F, 0x33333333, 0x55555555
+        const uint32_t lo_mask = d == 16 ? 0x0000FFFFu : d == 8 ? 0x00FF00FFu : d == 4 ? 0x0F0F0F0Fu : d == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xFFFFFFFFu, x, d);
+        if (lane & d) x = (x & ~lo_mask) | ((y >> d) & lo_mask);   // upper row: keep its high block, take the partner's high block as low
+        else x = (x & lo_mask) | ((y << d) & ~lo_mask);            // lower row: keep its low block, take the partner's low block as high
+    }
+    return x;
+}
 
 // Bit-matrix transpose: node-major bitplanes src[slice][n_rows][wpad] (bit c%32 of word c/32 of row
 // n) -> cell-major records dst[slice][wpad*32][nwp] (bit n%32 of word n/32 of cell c).  One CTA
@@ -171,6 +205,32 @@ __device__ unsigned long long g_sweep_phase[4][16];
 #else
 #define SCB_SWEEP_PHASE(i) do { } while (0)
 #endif
+
+// How many ring steps the KO/KI pass runs on the plane words before it hands the cells that are
+// still open to the compacted recheck pass.  A step on the plane words costs the same whether one
+// lane of a word is open or all 32, a rechecked cell is simulated again from the start: with u(T) the
+// share of cells still open after T steps the work is ~ T + kRecheckSteps * u(T) plane-word steps.
+// u is taken from the NORMAL run (settle-time histogram), the KO/KI runs of a cell settle at about
+// the same time as its unperturbed run.  Any choice gives the same results.
+constexpr int kRecheckSteps = 115;  // cost of rechecking every cell, in plane-word steps (measured, H1M)
+__global__ void choose_fast_steps_kernel(const unsigned int* __restrict__ hist, int steps, int64_t n_cells,
+                                         unsigned int* __restrict__ counters) {
+    if (threadIdx.x != 0) return;
+    long long open = n_cells;
+    long long best_cost = (long long)steps * n_cells;  // T = steps: nothing is rechecked for being slow
+    int best = steps;
+    for (int t = 0; t < steps; ++t) {
+        open -= hist[t];  // open after T = t + 1 steps
+        const int T = t + 1;
+        if (T < 4) continue;
+        const long long cost = (long long)T * n_cells + (long long)kRecheckSteps * open;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = T;
+        }
+    }
+    counters[3] = (unsigned int)best;
+}
 
 // MODE_NORMAL  the unperturbed run (ring fast path, slow path in place)
 // MODE_KOKI    KO/KI of every node on the plane words: ring fast path for the first `fast_steps`
@@ -261,14 +321,28 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
                 // padded with zero entries) has an all-zero truth table and all-zero registers: it votes
                 // "equal" and only its stores are suppressed
                 const NodeOffsets o = offs[n0 + i];
-                const uint4 lo = *reinterpret_cast<const uint4*>(&masks[n0 + i].m[0]);
-                const uint4 hi = *reinterpret_cast<const uint4*>(&masks[n0 + i].m[4]);
-                const uint32_t a0 = srd[o.pa], b0 = srd[o.pb], c0 = srd[o.pc];
-                const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32], c1 = srd[o.pc + 32];
-                uint32_t f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
-                                         lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
-                uint32_t f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
-                                         lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
+                const LutMasks& mk = masks[n0 + i];
+                uint32_t f0, f1;
+                if (o.arity <= 1) {  // warp-uniform: 2 rows and 2 table words instead of 6 and 8
+                    const uint32_t m0 = mk.m[0], m4 = mk.m[4];
+                    f0 = lop3<0xCA>(srd[o.pa], m4, m0);
+                    f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
+                } else {
+                    const uint4 lo = *reinterpret_cast<const uint4*>(&mk.m[0]);
+                    const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
+                    const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
+                    const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
+                    if (o.arity == 2) {
+                        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
+                        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
+                    } else {
+                        const uint32_t c0 = srd[o.pc], c1 = srd[o.pc + 32];
+                        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
+                                        lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
+                        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
+                                        lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
+                    }
+                }
                 if (i == forced_i) {  // never true past the end
                     f0 = 0u;
                     f1 = 0xFFFFFFFFu;
@@ -341,7 +415,7 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
 // State layout in shared memory: word (node n, copy k, slot s) lives at ((n*4 + k)*SLOTS + s), so
 // the four copies of a node sit at compile-time offsets from each other.
 template <int SLOTS, int MODE>
-__global__ void __launch_bounds__(kSweepThreads, SLOTS >= 64 ? 1 : 2)
+__global__ void __launch_bounds__(kSweepThreads, (SLOTS >= 64 || kSweepThreads > 512) ? 1 : 2)
 sweep_kernel(const SweepArgs args) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = args.n_nodes;
@@ -378,13 +452,14 @@ sweep_kernel(const SweepArgs args) {
     if (tid < kMaskPad) {  // all-zero entries past the end (ring2_registers)
         masks[N + tid] = expand_lut(0u);
         NodeOffsets z;
-        z.pa = z.pb = z.pc = z.pad = 0;
+        z.pa = z.pb = z.pc = z.arity = 0;
         offs[N + tid] = z;
     }
     for (int n = tid; n < N; n += blockDim.x) {
-        NodeEntry e = make_entry(args.net_parent, args.net_lut, n);
+        int arity;
+        NodeEntry e = make_entry(args.net_parent, args.net_lut, n, &arity);
         NodeOffsets o;
-        o.pa = e.pa * NODE_STRIDE; o.pb = e.pb * NODE_STRIDE; o.pc = e.pc * NODE_STRIDE; o.pad = 0;
+        o.pa = e.pa * NODE_STRIDE; o.pb = e.pb * NODE_STRIDE; o.pc = e.pc * NODE_STRIDE; o.arity = arity;
         offs[n] = o;
         masks[n] = expand_lut(e.lut);
     }
@@ -421,8 +496,10 @@ sweep_kernel(const SweepArgs args) {
             word = (int64_t)blockIdx.x * SLOTS + slot;
             cellmask = word < wpad ? tail_mask(word, args.n_cells) : 0u;
         } else if (MODE == MODE_KOKI) {
-            word = (int64_t)blockIdx.x * HALF + (slot % HALF);
-            forced_node = blockIdx.y;
+            // consecutive CTAs take the SAME 32 words under consecutive forced nodes: the rows of the
+            // data and of the normal-run states they read stay in L2 (and L1) for all N of them
+            word = (int64_t)(blockIdx.x / (unsigned)N) * HALF + (slot % HALF);
+            forced_node = (int)(blockIdx.x % (unsigned)N);
             forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
             cellmask = word < wpad ? tail_mask(word, args.n_cells) : 0u;
         } else {
@@ -456,8 +533,8 @@ sweep_kernel(const SweepArgs args) {
         auto at = [&](int k, int n) -> uint32_t& { return state[(n * 4 + k) * SLOTS + slot]; };
         // gather modes: copy k of every node, both halves, from the cell-major records of the batch's
         // cells; `kstage` names a state copy that is dead at the call (staging area).  One warp per
-        // virtual word: lane = cell, 128-bit loads fetch its record, every record word goes through 32
-        // ballots (lane b keeps the word of node 32j + b) and is parked in copy kstage at a rotated slot
+        // virtual word: lane = cell, 128-bit loads fetch its record, every record word goes through a
+        // 32x32 warp transpose (lane b gets the word of node 32j + b) and is parked in copy kstage at a rotated slot
         // position -- lanes hold different nodes, whose rows all start on the same bank, and the
         // rotation by the node index spreads them over the banks.  After a barrier every thread
         // moves the words of its own (slot, nodes) into copy k, again conflict-free.
@@ -483,12 +560,9 @@ sweep_kernel(const SweepArgs args) {
                         for (int q = 0; q < 4; ++q) {
                             const int nb = (j4 + q) * 32;
                             if (nb < N) {
-                                uint32_t mine = 0;
-#pragma unroll
-                                for (int b = 0; b < 32; ++b) {
-                                    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (xw[h][q] >> b) & 1u);
-                                    if (lane == b) mine = bits;
-                                }
+                                // lane = cell holds 32 node bits; after the transpose lane b holds the 32
+                                // cell bits of node nb + b
+                                const uint32_t mine = warp_transpose32(xw[h][q], lane);
                                 const int n = nb + lane;
                                 if (n < N) state[(n * 4 + kstage) * SLOTS + ((v + n) % HALF)] = mine;
                             }
@@ -542,12 +616,17 @@ sweep_kernel(const SweepArgs args) {
             __syncthreads();
             SCB_SWEEP_PHASE(1);
             uint32_t frozen = ~cellmask;
-            const int t_fast = MODE == MODE_KOKI ? min(steps, args.fast_steps) : steps;
-            const bool reg_ring = DEFERS && SLOTS == 64 && kSweepThreads == 512 && !deep && N <= 16 * 13 && kRegRing;
+            const int t_fast = MODE != MODE_KOKI      ? steps
+                               : args.fast_steps > 0 ? min(steps, args.fast_steps)
+                                                     : min(steps, (int)args.counters[3]);
+            // nodes per warp of the register ring: 13 / 8 / 4 with 16 warps, 7 / 4 / 2 with 32
+            constexpr int kWarps = kSweepThreads / 32;
+            constexpr int CH_L = (208 + kWarps - 1) / kWarps, CH_M = (128 + kWarps - 1) / kWarps, CH_S = (64 + kWarps - 1) / kWarps;
+            const bool reg_ring = DEFERS && SLOTS == 64 && kWarps >= 16 && !deep && N <= kWarps * CH_L && kRegRing;
             if (reg_ring) {
-                xs = N <= 64    ? ring2_registers<4>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid)
-                     : N <= 128 ? ring2_registers<8>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid)
-                                : ring2_registers<13>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid);
+                xs = N <= kWarps * CH_S   ? ring2_registers<CH_S>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid)
+                     : N <= kWarps * CH_M ? ring2_registers<CH_M>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid)
+                                          : ring2_registers<CH_L>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid);
                 frozen = votes[slot];
                 lam[0] = votes[64 + slot];
                 lam[1] = votes[128 + slot];
@@ -599,6 +678,10 @@ sweep_kernel(const SweepArgs args) {
                 lam[1] |= e2 | e3;
                 lam[2] |= e4;
                 frozen |= e1 | e2 | e3 | e4;
+                if (MODE == MODE_NORMAL && part == 0) {  // settle-time histogram (choose_fast_steps_kernel)
+                    const unsigned int c = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)__popc(e1 | e2 | e3 | e4));
+                    if ((tid & 31) == 0 && c) atomicAdd(&args.settle_hist[t], c);
+                }
                 // the other accumulator set is idle between the two barriers: clear it for step t+1
                 if (part < kRing) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
                 xs = kd;
@@ -835,36 +918,56 @@ sweep_kernel(const SweepArgs args) {
                     if (bad) atomicAdd(args.out_keyerror, (unsigned long long)bad);
                 }
             }
+#ifdef SCB_TRACE
+            if (part == 0) {  // scoring statistics: lanes scored, lanes where either run cycles, lanes with lambda 2
+                atomicAdd(&g_sweep_phase[MODE][8 + 5], (unsigned long long)__popc(valid));
+                atomicAdd(&g_sweep_phase[MODE][8 + 6],
+                          (unsigned long long)__popc(valid & (planes_ge(lam, 2) | planes_ge(lamn, 2))));
+            }
+#endif
             unsigned long long score = 0;
-            for (int t = 0; t < steps; ++t) {
-                uint32_t act = valid & planes_ge(lam, t) & planes_ge(lamn, t);
-                if (!__syncthreads_or(act != 0)) break;
-                // gather modes: the normal-run states of the batch's cells at offset t, assembled in the
-                // state copy that neither xs nor xn uses
-                const int kref = xs ^ 2;
+            // offset 0: the frozen states against the normal run's state_mu.  Gather modes assemble the
+            // normal-run states of the batch's cells in the state copy that neither xs nor xn uses.
+            if (__syncthreads_or(valid != 0)) {
                 if (IS_GATHER) {
-                    load_cells(args.np_states_t + (size_t)t * wpad * 32 * args.nwp, kref, xn ^ 2);
+                    load_cells(args.np_states_t, xs ^ 2, xn ^ 2);
                     __syncthreads();
                 }
-                if (act) {
+                if (valid) {
                     uint32_t sc = 0;
+#pragma unroll 4
                     for (int n = n_lo; n < n_hi; ++n) {
-                        const uint32_t ref =
-                            IS_GATHER ? at(kref, n) : __ldg(args.np_states + ((size_t)t * N + n) * wpad + word);
-                        sc += __popc((at(xs, n) ^ ref) & act);
+                        const uint32_t ref = IS_GATHER ? at(xs ^ 2, n) : __ldg(args.np_states + (size_t)n * wpad + word);
+                        sc += __popc((at(xs, n) ^ ref) & valid);
                     }
-                    score += sc;
+                    score = sc;
                 }
-                if (t == 0 && !__syncthreads_or((valid & (planes_ge(lam, 2) | planes_ge(lamn, 2))) != 0)) {
-                    score *= 2;  // every counted cell: fixed point vs fixed point, t = 1 repeats t = 0
-                    break;
-                }
-                uint32_t act_next = valid & planes_ge(lam, t + 1) & planes_ge(lamn, t + 1);
-                if (!__syncthreads_or(act_next != 0)) break;
+                if (!__syncthreads_or((valid & (planes_ge(lam, 2) | planes_ge(lamn, 2))) != 0)) {
+                    score *= 2;  // every counted cell: fixed point vs fixed point, offset 1 repeats offset 0
+                } else {
+                    // offsets 1..min(lambda_x, lambda_n): step, and compare the new state while it is made
+                    for (int t = 1; t < steps; ++t) {
+                        const uint32_t act = valid & planes_ge(lam, t) & planes_ge(lamn, t);
+                        if (!__syncthreads_or(act != 0)) break;
+                        const int kref = xs ^ 2;
+                        if (IS_GATHER) {
+                            load_cells(args.np_states_t + (size_t)t * wpad * 32 * args.nwp, kref, xn ^ 2);
+                            __syncthreads();
+                        }
+                        uint32_t sc = 0;
 #pragma unroll 2
-                for (int n = n_lo; n < n_hi; ++n) at(xn, n) = step_node(xs, n);
-                __syncthreads();
-                int tmp = xs; xs = xn; xn = tmp;
+                        for (int n = n_lo; n < n_hi; ++n) {
+                            const uint32_t ref =
+                                IS_GATHER ? at(kref, n) : __ldg(args.np_states + ((size_t)t * N + n) * wpad + word);
+                            const uint32_t f = step_node(xs, n);
+                            at(xn, n) = f;
+                            sc += __popc((f ^ ref) & act);
+                        }
+                        score += sc;
+                        __syncthreads();
+                        int tmp = xs; xs = xn; xn = tmp;
+                    }
+                }
             }
             // one node per CTA (and per cleanup batch): fold the warp first
 #pragma unroll
@@ -978,8 +1081,8 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, cudaStream_t st
         SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_CLEANUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    // count_a | count_b | counters are contiguous
-    SCB_CUDA(cudaMemsetAsync(lists.count_a, 0, (size_t)args.n_nodes * 8 + 16, stream));
+    // settle_hist | count_a | count_b | counters are contiguous
+    SCB_CUDA(cudaMemsetAsync(args.settle_hist, 0, 64 * 4 + (size_t)args.n_nodes * 8 + 16, stream));
     args.in_cells = nullptr;
     args.in_cap = 0;
     args.in_count = nullptr;
@@ -989,6 +1092,10 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, cudaStream_t st
     dim3 grid_n((unsigned)((n_words + SLOTS - 1) / SLOTS));
     sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<normal>");
+    if (args.fast_steps <= 0) {
+        choose_fast_steps_kernel<<<1, 32, 0, stream>>>(args.settle_hist, args.steps, args.n_cells, args.counters);
+        SCB_LAUNCH_CHECK("choose_fast_steps_kernel");
+    }
     // cell-major copies of the data and of the normal-run states for the compacted passes
     {
         const int n_blocks_j = (args.n_nodes + 31) / 32;
@@ -1009,12 +1116,17 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, cudaStream_t st
         if (ring[0] == '2') SCB_CUDA(cudaMemsetAsync(args.counters + 1, 0, 1, stream));
     }
     constexpr int HALF = SLOTS / 2;
-    const bool two_level = args.fast_steps < args.steps;
+    const bool two_level = args.fast_steps < args.steps;  // also when the device chooses (fast_steps <= 0)
     // KO/KI on the plane words; open cells go to list A (or straight to B without a recheck pass)
     args.out_cells = two_level ? lists.cells_a : lists.cells_b;
     args.out_cap = two_level ? lists.cap_a : lists.cap_b;
     args.out_count = two_level ? lists.count_a : lists.count_b;
-    dim3 grid_k((unsigned)((n_words + HALF - 1) / HALF), (unsigned)args.n_nodes);
+    const int64_t n_koki = ((n_words + HALF - 1) / HALF) * args.n_nodes;
+    if (n_koki >= ((int64_t)1 << 31)) {
+        set_error("ko_ki_sweep: %lld (word block, node) pairs exceed one grid; shard the cells", (long long)n_koki);
+        return SCB_ERR_UNSUPPORTED;
+    }
+    dim3 grid_k((unsigned)n_koki);
     sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<koki>");
     int per_sm = smem <= kMaxDynSmem / 2 ? 2 : 1;
@@ -1064,7 +1176,7 @@ extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int 
     return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4 +
            (int64_t)(steps + 1) * wpad * 32 * record_words(n_nodes) * 4 + wpad * 32 * 4 +
            (int64_t)n_nodes * (sweep_list_capacity(wpad * 32, kListDivA) + sweep_list_capacity(wpad * 32, kListDivB)) * 4 +
-           (int64_t)n_nodes * 8 + 16;
+           64 * 4 + (int64_t)n_nodes * 8 + 16;
 }
 
 extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
@@ -1103,16 +1215,17 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.np_info_t = args.np_states_t + (size_t)steps * wpad * 32 * args.nwp;
     lists.cells_a = reinterpret_cast<int32_t*>(args.np_info_t + (size_t)wpad * 32);
     lists.cells_b = lists.cells_a + (size_t)n_nodes * lists.cap_a;
-    lists.count_a = reinterpret_cast<unsigned int*>(lists.cells_b + (size_t)n_nodes * lists.cap_b);
+    args.settle_hist = reinterpret_cast<unsigned int*>(lists.cells_b + (size_t)n_nodes * lists.cap_b);
+    lists.count_a = args.settle_hist + 64;
     lists.count_b = lists.count_a + n_nodes;
     args.counters = lists.count_b + n_nodes;  // followed by 16 spare bytes
-    // Default: the KO/KI pass runs the ring for all `steps` and only cells the ring cannot settle are
-    // deferred (list B).  SCB_SWEEP_FAST_STEPS=k cuts the pass after k steps and sends the open cells
-    // through the compacted recheck pass first -- measured on imp-1M: 254 ms (default), 297 ms (k=32),
-    // 331 ms (k=24): gathering a compacted cell's bits costs ~10 ns per (cell, node) against 1.1 ns
-    // for leaving it where it is, so the early cut does not pay on this data.
-    args.fast_steps = steps;
-    if (const char* e = getenv("SCB_SWEEP_FAST_STEPS")) args.fast_steps = atoi(e) > 0 ? atoi(e) : steps;
+    // Default: the KO/KI pass runs the ring on the plane words for a number of steps chosen on the
+    // device from the normal run (choose_fast_steps_kernel), cells still open go through the compacted
+    // recheck pass (deep ring, all `steps`), what that leaves open through the general scheme.
+    // SCB_SWEEP_FAST_STEPS=k fixes the number (k >= steps: no recheck pass).  Measured on imp-1M:
+    // 186 ms (k=50), 164 ms (k=24).
+    args.fast_steps = 0;
+    if (const char* e = getenv("SCB_SWEEP_FAST_STEPS")) args.fast_steps = atoi(e) > 0 ? atoi(e) : 0;
     if (args.fast_steps > steps) args.fast_steps = steps;
     args.out_raw = reinterpret_cast<unsigned long long*>(out_raw);
     args.out_missing = reinterpret_cast<unsigned long long*>(out_missing);

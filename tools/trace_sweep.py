@@ -29,3 +29,5 @@ for mode, mname in enumerate(["normal", "koki", "cleanup", "recheck"]):
     print(f"{mname}: {n} CTAs/batches; mean cycles per phase:",
           ", ".join(f"{names[i]} {buf[mode, i] / n:.0f}" for i in range(6)))
 print("cleanup cells by outcome: no repeat %d, lambda<=2 %d, 3-4 %d, 5-8 %d, >8 %d" % tuple(int(x) for x in buf[2, 8:13]))
+for mode, mname in ((1, "koki"), (3, "recheck"), (2, "cleanup")):
+    print(f"{mname}: scored lanes {int(buf[mode, 13])}, of them cycling (either run) {int(buf[mode, 14])}")
