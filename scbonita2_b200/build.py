@@ -43,6 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-DSCB_DIRECT_RED=" + os.environ["SCB_DIRECT_RED"]]
     if os.environ.get("SCB_SWEEP_THREADS"):   # experiments
         cmd += ["-DSCB_SWEEP_THREADS=" + os.environ["SCB_SWEEP_THREADS"]]
+    for d in os.environ.get("SCB_DEFINES", "").split():   # experiments: SCB_DEFINES="NAME=VALUE ..."
+        cmd += ["-D" + d]
     if os.environ.get("SCB_CONSUMER_WARPS"):   # experiments
         cmd += ["-DSCB_CONSUMER_WARPS=" + os.environ["SCB_CONSUMER_WARPS"]]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -243,6 +243,10 @@ enum { MODE_NORMAL = 0, MODE_KOKI = 1, MODE_CLEANUP = 2, MODE_RECHECK = 3 };
 #ifndef SCB_REG_RING
 #define SCB_REG_RING 1
 #endif
+#ifndef SCB_RING_ARITY
+#define SCB_RING_ARITY 1
+#endif
+constexpr bool kRingArity = SCB_RING_ARITY != 0;  // experiments: 0 evaluates every node as a three-parent one
 constexpr bool kRegRing = SCB_REG_RING != 0;  // experiments: 0 keeps the ring of the fast path in shared memory
 constexpr int kMaskPad = 15;  // all-zero truth tables after the last node
 constexpr int kRing = 4;  // state copies per slot: ring of the fast path, P/Q pairs of the slow path
@@ -312,8 +316,10 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
                     uint32_t (&prv1)[CH], int t) -> bool {
         constexpr int RD = decltype(rd_tag)::value ? 3 : 0, WR = decltype(rd_tag)::value ? 0 : 3;
         uint32_t q10 = 0, q20 = 0, q11 = 0, q21 = 0;
-        const uint32_t* srd = state + RD * SL + lane;
-        uint32_t* swr = state + (n0 * 4 + WR) * SL + lane;
+        // copy RD is only read and copy WR only written in a step: telling the compiler lets it start
+        // the loads of the next node before the stores of the current one
+        const uint32_t* __restrict__ srd = state + RD * SL + lane;
+        uint32_t* __restrict__ swr = state + (n0 * 4 + WR) * SL + lane;
         if (n_mine > 0) {  // warps past the last node only join the barrier
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
@@ -323,7 +329,7 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
                 const NodeOffsets o = offs[n0 + i];
                 const LutMasks& mk = masks[n0 + i];
                 uint32_t f0, f1;
-                if (o.arity <= 1) {  // warp-uniform: 2 rows and 2 table words instead of 6 and 8
+                if (kRingArity && o.arity <= 1) {  // warp-uniform: 2 rows and 2 table words instead of 6 and 8
                     const uint32_t m0 = mk.m[0], m4 = mk.m[4];
                     f0 = lop3<0xCA>(srd[o.pa], m4, m0);
                     f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
@@ -332,7 +338,7 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
                     const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
                     const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
                     const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
-                    if (o.arity == 2) {
+                    if (kRingArity && o.arity == 2) {
                         f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
                         f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
                     } else {

@@ -1,8 +1,2 @@
-python -m pytest tests/test_gpu_sweep.py -x -q -m gpu 2>&1 | tail -2
-python tools/time_sweep.py 2>&1 | tail -1
-SCB_SWEEP_THREADS=1024 python -m scbonita2_b200.build --force | tail -1
-python -m pytest tests/test_gpu_sweep.py -x -q -m gpu 2>&1 | tail -2
-SCB_SWEEP_FAST_STEPS=6 python -m pytest tests/test_gpu_sweep.py -x -q -m gpu 2>&1 | tail -2
-python tools/time_sweep.py 2>&1 | tail -1
-SCB_TRACE=1 SCB_SWEEP_THREADS=1024 python -m scbonita2_b200.build --force | tail -1
-python tools/trace_sweep.py 2>&1 | tail -8 | head -4
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench8.json 2> gpurun_out/bench8.err; tail -c 600 gpurun_out/bench8.err; cat gpurun_out/bench8.json
