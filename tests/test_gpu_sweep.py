@@ -202,3 +202,55 @@ def test_attractor_dumps_cross_check_the_sweep(cuda, tmp_path):
     with open(f"{calc.intermediate_dir}/knockout_results_{nodes[0].name}.pkl", "rb") as fh:
         back = pickle.load(fh)
     assert set(back) == set(calc.vectorized_run_simulation(knockout_node=nodes[0].name))
+
+
+@pytest.mark.parametrize("n_nodes,n_cells,steps,fast,tame", [
+    (100, 1500, 50, None, 0.7), (100, 1500, 50, "3", 0.7), (100, 900, 30, "50", 0.7), (128, 700, 50, None, 0.7),
+    (129, 700, 50, "5", 0.7), (208, 600, 50, None, 0.7), (212, 500, 50, "4", 0.7), (64, 2100, 50, None, 0.7),
+    (65, 1000, 17, None, 0.7), (90, 800, 50, None, 0.2), (150, 500, 50, "8", 0.2), (200, 400, 50, None, 0.0)])
+def test_sweep_general_tables_and_parent_holes_vs_c_oracle(cuda, monkeypatch, n_nodes, n_cells, steps, fast, tame):
+    """Arbitrary 8-bit truth tables and parent slots bound in any pattern (e.g. only B, or A and C):
+    the kernels canonicalise the node (bound slots packed left, table rewritten) and, per node count,
+    take the register ring with 4 / 8 / 13 nodes per warp or the shared-memory ring (> 208 nodes);
+    every combination of passes (SCB_SWEEP_FAST_STEPS) must give the cell-by-cell oracle's integers."""
+    from oracle import cport
+    from scbonita2_b200 import device
+    rng = np.random.default_rng(n_nodes * 1000 + steps)
+    parents = np.full((n_nodes, 3), -1, dtype=np.int32)
+    for n in range(n_nodes):
+        bound = rng.random(3) < 0.6
+        parents[n, bound] = rng.integers(0, n_nodes, int(bound.sum()))
+    # `tame` = share of monotone-ish tables (the dynamics settle); the rest are arbitrary (long cycles)
+    luts = np.where(rng.random(n_nodes) < tame, rng.choice([0xF0, 0xCC, 0xAA, 0x80, 0xFE, 0xE8, 0x0F, 0x33], n_nodes),
+                    rng.integers(0, 256, n_nodes)).astype(np.uint8)
+    planes_np = synth.random_planes(n_nodes, n_cells, 7 + n_nodes, density=0.4)
+    if fast is None:
+        monkeypatch.delenv("SCB_SWEEP_FAST_STEPS", raising=False)
+    else:
+        monkeypatch.setenv("SCB_SWEEP_FAST_STEPS", fast)
+    raw, missing, keyerr = device.ko_ki_sweep(device.BitPlanes.from_packed(planes_np, n_cells), parents, luts, steps)
+    w_raw, w_missing, w_key = cport.importance_raw(synth.planes_to_dense(planes_np, n_cells), parents, luts, steps)
+    assert int(keyerr.item()) == w_key
+    assert (missing.cpu().numpy() == w_missing).all()
+    if w_key == 0:
+        assert (raw.cpu().numpy() == w_raw).all()
+
+
+def test_trajectories_with_parent_holes_vs_c_oracle(cuda):
+    """Parent slots bound in any pattern and arbitrary tables through scb_trajectories_forced."""
+    from oracle import cport
+    from scbonita2_b200 import device
+    rng = np.random.default_rng(5)
+    n_nodes, n_cells = 45, 300
+    parents = np.full((n_nodes, 3), -1, dtype=np.int32)
+    for n in range(n_nodes):
+        bound = rng.random(3) < 0.5
+        parents[n, bound] = rng.integers(0, n_nodes, int(bound.sum()))
+    luts = rng.integers(0, 256, n_nodes).astype(np.uint8)
+    planes_np = synth.random_planes(n_nodes, n_cells, 21, density=0.5)
+    dense = synth.planes_to_dense(planes_np, n_cells)
+    cells = [0, 1, 31, 32, 33, 150, 299]
+    got = device.trajectories(device.BitPlanes.from_packed(planes_np, n_cells), cells, parents, luts, 20).cpu().numpy()
+    for k, c in enumerate(cells):
+        want = cport.trajectory(dense[:, c], parents, luts, 20)     # (steps, nodes)
+        assert (got[k] == np.asarray(want).T).all()
