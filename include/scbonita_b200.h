@@ -218,6 +218,23 @@ int scb_trajectories_forced(const uint32_t* planes, int n_nodes, int64_t wpad, i
                             int steps, int forced_node, int forced_value,
                             uint8_t* out /*[M][N][steps]*/, scb_stream_t stream);
 
+/* ---- (3c) pairwise trajectory distances ---------------------------------
+ * compute_dtw_distance_pair / compute_dtw_distances (attractor_analysis.py:304-377): per pair of
+ * cells the sum over the genes of the squared difference of the two down-sampled 0/1 series if it
+ * is below `threshold` (EUCLIDEAN_THRESHOLD = 5, :41), else fastdtw(radius, squared distance).
+ * A down-sampled series is a pattern of `bits` points (10 for 20 steps, every 2nd), so the per-gene
+ * distance is a table over two patterns.  fastdtw 0.3.4 is a third-party package absent from the
+ * reference tree: its algorithm is restated, parity of that branch is unpinned. */
+/* HOST: table[2^bits][2^bits] bytes; host code only, no GPU needed */
+int scb_dtw_table_build(int bits, int radius, int threshold, uint8_t* host_table);
+/* traj [M][N][steps] bytes (scb_trajectories) -> patterns [M][N]: bit k = traj[..][k * factor] */
+int scb_trajectory_patterns(const uint8_t* traj, int64_t n_cells, int n_genes, int steps, int factor,
+                            uint16_t* out /*[M][N]*/, scb_stream_t stream);
+/* out[a][b] = sum_g table[patterns[a][g]][patterns[b][g]] (symmetric, diagonal included) */
+int scb_pattern_pair_distances(const uint16_t* patterns /*[M][N]*/, int64_t n_cells, int n_genes,
+                               const uint8_t* table /*DEVICE [2^bits][2^bits]*/, int bits,
+                               int32_t* out /*[M][M]*/, scb_stream_t stream);
+
 /* ---- host-buffer entry points (the end-to-end path; all pointers HOST) ---------------------
  * One workspace owns the device buffers of one (device, stream); not thread-safe. */
 typedef struct scb_workspace scb_workspace;

@@ -237,3 +237,106 @@ def population_fitness(nodes, candidate_logics, selections, dataset: np.ndarray,
         raws.append(raw)
         fits.append((raw + 0.002 * n_rules * current_gen / max_gen,))
     return raws, fits
+
+
+# --------------------------------------------------------------------------------------
+# next-3  trajectory distance                          code/attractor_analysis.py:289-377
+# --------------------------------------------------------------------------------------
+EUCLIDEAN_THRESHOLD = 5   # attractor_analysis.py:41
+
+
+def _fastdtw_reduce_by_half(x):
+    return [(x[i] + x[i + 1]) / 2 for i in range(0, len(x) - len(x) % 2, 2)]
+
+
+def _fastdtw_expand_window(path, len_x, len_y, radius):
+    path_ = set(path)
+    for i, j in path:
+        for a in range(-radius, radius + 1):
+            for b in range(-radius, radius + 1):
+                path_.add((i + a, j + b))
+    window_ = set()
+    for i, j in path_:
+        for a, b in ((i * 2, j * 2), (i * 2, j * 2 + 1), (i * 2 + 1, j * 2), (i * 2 + 1, j * 2 + 1)):
+            window_.add((a, b))
+    window = []
+    start_j = 0
+    for i in range(0, len_x):
+        new_start_j = None
+        for j in range(start_j, len_y):
+            if (i, j) in window_:
+                window.append((i, j))
+                if new_start_j is None:
+                    new_start_j = j
+            elif new_start_j is not None:
+                break
+        start_j = new_start_j
+    return window
+
+
+def _fastdtw_dtw(x, y, window, dist):
+    len_x, len_y = len(x), len(y)
+    if window is None:
+        window = [(i, j) for i in range(len_x) for j in range(len_y)]
+    inf = float("inf")
+    D = {(0, 0): (0, 0, 0)}
+    for i, j in ((i + 1, j + 1) for i, j in window):
+        dt = dist(x[i - 1], y[j - 1])
+        # first minimum in the order (up, left, diagonal), like Python's min() over that tuple
+        best = None
+        for pi, pj in ((i - 1, j), (i, j - 1), (i - 1, j - 1)):
+            cost = D.get((pi, pj), (inf,))[0] + dt
+            if best is None or cost < best[0]:
+                best = (cost, pi, pj)
+        D[i, j] = best
+    path = []
+    i, j = len_x, len_y
+    while not (i == j == 0):
+        path.append((i - 1, j - 1))
+        i, j = D[i, j][1], D[i, j][2]
+    path.reverse()
+    return D[len_x, len_y][0], path
+
+
+def fastdtw(x, y, radius: int = 1, dist=lambda a, b: abs(a - b)):
+    """Restatement of ``fastdtw.fastdtw`` (package ``fastdtw`` 0.3.4, ``environment.yml:103``; pure-Python
+    module ``fastdtw/fastdtw.py``: Salvador & Chan's FastDTW -- halve both series by pair averages
+    down to ``radius + 2`` points, exact DTW there, then project the path, widen it by ``radius``
+    and run the windowed DTW one level up).  The package is NOT in the reference tree nor in this
+    image: PARITY UNPINNED for this function (the recursion, the window construction and the
+    up / left / diagonal tie order are restated from the published source; no golden vector).
+    """
+    x = [float(v) for v in np.asarray(x, dtype=float).reshape(-1)]
+    y = [float(v) for v in np.asarray(y, dtype=float).reshape(-1)]
+
+    def rec(xs, ys):
+        min_time_size = radius + 2
+        if len(xs) < min_time_size or len(ys) < min_time_size:
+            return _fastdtw_dtw(xs, ys, None, dist)
+        _, path = rec(_fastdtw_reduce_by_half(xs), _fastdtw_reduce_by_half(ys))
+        window = _fastdtw_expand_window(path, len(xs), len(ys), radius)
+        return _fastdtw_dtw(xs, ys, window, dist)
+
+    return rec(x, y)
+
+
+def dtw_distance_pair(traj1: dict, traj2: dict, radius: int = 1, downsample_factor: int = 2):
+    """``compute_dtw_distance_pair`` (attractor_analysis.py:304-345) for two cells' ``{gene: series}``
+    dicts: per shared gene, every ``downsample_factor``-th point; squared difference if it is below
+    ``EUCLIDEAN_THRESHOLD``, else FastDTW with squared pointwise distance; the sum over the genes
+    (``inf`` without a shared gene).  The squared-difference branch is plain NumPy (pinned by
+    construction); the FastDTW branch inherits ``fastdtw``'s "parity unpinned".
+    """
+    total, any_gene = 0, False
+    for gene, ts1 in traj1.items():
+        if gene not in traj2:
+            continue
+        any_gene = True
+        d1 = np.array(np.array(ts1)[::downsample_factor]).flatten()
+        d2 = np.array(np.array(traj2[gene])[::downsample_factor]).flatten()
+        squared = np.sum((d1 - d2) ** 2)
+        if squared < EUCLIDEAN_THRESHOLD:
+            total += squared
+        else:
+            total += fastdtw(d1, d2, radius, dist=lambda a, b: (a - b) ** 2)[0]
+    return total if any_gene else float("inf")

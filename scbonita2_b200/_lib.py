@@ -64,6 +64,9 @@ SIGNATURES = {
                                  c_void_p, c_int, c_void_p, c_void_p]),
     "scb_trajectories_forced": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p,
                                         c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "scb_dtw_table_build": (c_int, [c_int, c_int, c_int, c_void_p]),
+    "scb_trajectory_patterns": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "scb_pattern_pair_distances": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "scb_workspace_create": (c_int, [POINTER(c_void_p)]),
     "scb_workspace_destroy": (None, [c_void_p]),
     "scb_host_load_dense": (c_int, [c_void_p, _U8P, c_int, c_int64]),

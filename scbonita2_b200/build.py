@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(CSRC, "libscbonita_b200.so")
-SOURCES = ["scb_api.cu", "scb_pack.cu", "scb_counts.cu", "scb_rules.cu", "scb_sweep.cu", "scb_peer.cu"]
+SOURCES = ["scb_api.cu", "scb_pack.cu", "scb_counts.cu", "scb_rules.cu", "scb_sweep.cu", "scb_peer.cu", "scb_dtw.cu"]
 
 
 def _nvcc() -> str:

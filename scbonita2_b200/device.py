@@ -364,6 +364,50 @@ def trajectories(planes: BitPlanes, cell_idx, net_parent, net_lut, steps: int = 
 
 
 # --------------------------------------------------------------------------------------
+_DTW_TABLES = {}
+
+
+def dtw_table(bits: int, radius: int = 1, threshold: int = 5, device=None):
+    """Device copy of the per-gene distance table over two ``bits``-point 0/1 patterns
+    (``scb_dtw_table_build``; built once per (bits, radius, threshold, device))."""
+    torch = _torch()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    key = (bits, radius, threshold, str(dev))
+    if key not in _DTW_TABLES:
+        host = np.zeros((1 << bits, 1 << bits), dtype=np.uint8)
+        _lib.check(_lib.lib().scb_dtw_table_build(bits, radius, threshold, host.ctypes.data), "scb_dtw_table_build")
+        _DTW_TABLES[key] = torch.from_numpy(host).to(dev)
+    return _DTW_TABLES[key]
+
+
+def trajectory_patterns(traj, factor: int = 2):
+    """uint16 ``[M, N]`` patterns of a uint8 ``[M, N, steps]`` trajectory tensor: bit k = point
+    ``k * factor`` (the reference's ``downsample``, attractor_analysis.py:289-291)."""
+    torch = _torch()
+    if traj.dtype != torch.uint8 or traj.dim() != 3:
+        raise ValueError("trajectories must be a uint8 [cells, nodes, steps] tensor")
+    traj = traj.contiguous()
+    m, n, steps = (int(v) for v in traj.shape)
+    out = torch.empty((m, n), dtype=torch.int16, device=traj.device)   # bit patterns; torch has no uint16 arithmetic
+    with torch.cuda.device(traj.device):
+        _lib.check(_lib.lib().scb_trajectory_patterns(traj.data_ptr(), m, n, steps, factor, out.data_ptr(), _stream()),
+                   "scb_trajectory_patterns")
+    return out
+
+
+def pattern_pair_distances(patterns, bits: int, radius: int = 1, threshold: int = 5):
+    """int32 ``[M, M]`` symmetric matrix: entry (a, b), a <= b, is the reference's
+    ``compute_dtw_distance_pair(cell a, cell b)`` total over the genes."""
+    torch = _torch()
+    m, n = (int(v) for v in patterns.shape)
+    table = dtw_table(bits, radius, threshold, patterns.device)
+    out = torch.zeros((m, m), dtype=torch.int32, device=patterns.device)
+    with torch.cuda.device(patterns.device):
+        _lib.check(_lib.lib().scb_pattern_pair_distances(patterns.data_ptr(), m, n, table.data_ptr(), bits,
+                                                         out.data_ptr(), _stream()), "scb_pattern_pair_distances")
+    return out
+
+
 class HostWorkspace:
     """The host-buffer ("end-to-end") entry points: NumPy in, NumPy out, no torch."""
 

@@ -254,3 +254,30 @@ def test_trajectories_with_parent_holes_vs_c_oracle(cuda):
     for k, c in enumerate(cells):
         want = cport.trajectory(dense[:, c], parents, luts, 20)     # (steps, nodes)
         assert (got[k] == np.asarray(want).T).all()
+
+
+def test_trajectory_distances_vs_oracle(cuda):
+    """next-3: compute_dtw_distances (attractor_analysis.py:347-377) from one pair-distance kernel,
+    against the oracle's per-pair restatement; inputs are real simulated trajectories plus random
+    ones (the latter reach the FastDTW branch often)."""
+    from scbonita2_b200 import attractor_analysis as aa
+    specs = _cyclic_specs(3, 30)
+    planes_np = synth.random_planes(30, 400, 17, density=0.5)
+    dense = synth.planes_to_dense(planes_np, 400)
+    nodes = nodes_of(specs, with_logic=True)
+    cells = list(range(0, 400, 9))
+    traj = aa.simulate_trajectories(nodes, dense, cells)               # [M, N, 20]
+    rng = np.random.default_rng(0)
+    noise = (rng.random((23, 30, 20)) < 0.5).astype(np.uint8)
+    for data, label in ((traj, "sim"), (noise, "rnd")):
+        trajectories = {f"cell_{label}_{m}": {n.name: [int(v) for v in data[m, g]] for g, n in enumerate(nodes)}
+                        for m in range(data.shape[0])}
+        got = aa.compute_dtw_distances(trajectories)
+        names = list(trajectories)
+        assert list(got) == [(a, b) for i, a in enumerate(names) for b in names[i + 1:]]
+        for (a, b), total in got.items():
+            assert total == ref_port.dtw_distance_pair(trajectories[a], trajectories[b]), (a, b)
+        a, b = names[0], names[-1]
+        assert aa.compute_dtw_distance_pair(a, b, trajectories) == (a, b, got[(a, b)])
+        matrix = aa.create_distance_matrix(got, names)
+        assert (matrix == matrix.T).all() and matrix[0, len(names) - 1] == got[(a, b)]

@@ -100,3 +100,33 @@ def test_aliases_make_pickles_reference_compatible():
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_dtw_table_matches_the_restated_fastdtw():
+    """scb_dtw_table_build is HOST code (no GPU): its entries must equal the oracle's restatement of
+    compute_dtw_distance_pair's per-gene distance (attractor_analysis.py:332-343) -- squared difference
+    below EUCLIDEAN_THRESHOLD, FastDTW (restated, parity unpinned) from there on."""
+    import ctypes
+    import numpy as np
+    from oracle import ref_port
+    from scbonita2_b200 import _lib
+    for bits in (10, 9, 4):
+        n = 1 << bits
+        table = np.zeros((n, n), dtype=np.uint8)
+        _lib.check(_lib.lib().scb_dtw_table_build(bits, 1, 5, table.ctypes.data), "scb_dtw_table_build")
+        rng = np.random.default_rng(bits)
+        n_dtw = 0
+        for _ in range(1500):
+            px, py = int(rng.integers(0, n)), int(rng.integers(0, n))
+            x = np.array([(px >> k) & 1 for k in range(bits)])
+            y = np.array([(py >> k) & 1 for k in range(bits)])
+            squared = int(np.sum((x - y) ** 2))
+            want = squared if squared < 5 else ref_port.fastdtw(x, y, 1, dist=lambda a, b: (a - b) ** 2)[0]
+            n_dtw += squared >= 5
+            assert int(table[px, py]) == want, (bits, px, py)
+        assert bits < 9 or n_dtw > 500
+        assert (np.diag(table) == 0).all()
+    # FastDTW is not symmetric in its arguments; the product keeps the reference's argument order
+    big = np.zeros((1024, 1024), dtype=np.uint8)
+    _lib.check(_lib.lib().scb_dtw_table_build(10, 1, 5, big.ctypes.data), "scb_dtw_table_build")
+    assert (big != big.T).any()

@@ -1,2 +1,2 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench8.json 2> gpurun_out/bench8.err; tail -c 600 gpurun_out/bench8.err; cat gpurun_out/bench8.json
+python -m pytest tests/test_gpu_sweep.py -x -q -m gpu 2>&1 | tail -5
+ITERS=1 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/sweep_launch_v5.csv python tools/time_sweep.py 2>&1 | tail -1
