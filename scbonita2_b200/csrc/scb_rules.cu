@@ -16,6 +16,33 @@ __device__ __forceinline__ long long diff_from_counts(const int64_t* __restrict_
     return d;
 }
 
+// thread-block cluster helpers (population_fitness_kernel with sharded cells)
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_size() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_map(const void* p, uint32_t rank) {
+    uint32_t local = (uint32_t)__cvta_generic_to_shared(p), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t addr, unsigned long long v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void error_table_kernel(const int64_t* __restrict__ counts, int64_t n_tasks,
                                    const int32_t* __restrict__ task_group,
                                    const uint8_t* __restrict__ task_lut,
@@ -79,9 +106,17 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     }
     // one thread per (group, minterm): the two counts of the minterm in (one 16-byte load per rank),
     // the delta out; the target-1 counts are parked in the nibble area until base[] is summed
+    // Sharded cells: summing the slots of R ranks costs every CTA R x 25.6 KB of L2 reads.  The CTAs
+    // of a thread-block cluster split the (group, minterm) pairs among them and store each sum into
+    // the shared memory of ALL of them (distributed shared memory), so a CTA reads 1/C of the slots.
+    // Without a cluster attribute the cluster is this CTA alone and the same code runs.
+    const uint32_t c_rank = cluster_cta_rank(), c_size = cluster_size();
+    __shared__ unsigned int s_wide;
+    if (threadIdx.x == 0) s_wide = 0u;
+    if (c_size > 1) cluster_sync_all();  // every CTA of the cluster is running (and s_wide is cleared) before a peer stores into it
     int wide = 0;
     long long* ones = reinterpret_cast<long long*>(nib);
-    for (int e = threadIdx.x; e < n_groups * 8; e += blockDim.x) {
+    for (int e = threadIdx.x * (int)c_size + (int)c_rank; e < n_groups * 8; e += blockDim.x * (int)c_size) {
         const int g = e >> 3, k = e & 7;
         longlong2 v;  // (minterm k, target 0), (minterm k, target 1)
         if (!slots) {
@@ -112,11 +147,22 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
                 v.y += (long long)(unsigned int)t[r].y;
             }
         }
-        wide |= (int)(((unsigned long long)v.x | (unsigned long long)v.y) >> 31 != 0);
-        delta[k * n_groups + g] = v.x - v.y;
-        ones[k * n_groups + g] = v.y;
+        const int w = (int)(((unsigned long long)v.x | (unsigned long long)v.y) >> 31 != 0);
+        wide |= w;
+        if (c_size == 1) {
+            delta[k * n_groups + g] = v.x - v.y;
+            ones[k * n_groups + g] = v.y;
+        } else {
+            for (uint32_t r = 0; r < c_size; ++r) {
+                st_cluster_u64(cluster_map(&delta[k * n_groups + g], r), (unsigned long long)(v.x - v.y));
+                st_cluster_u64(cluster_map(&ones[k * n_groups + g], r), (unsigned long long)v.y);
+                if (w) st_cluster_u32(cluster_map(&s_wide, r), 1u);
+            }
+        }
     }
-    __syncthreads();
+    if (c_size > 1) cluster_sync_all();  // release / acquire: the peers' stores are visible from here on
+    else __syncthreads();
+    wide |= (int)s_wide;
     for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
         long long b = 0;
 #pragma unroll
@@ -285,11 +331,29 @@ static int launch_population_fitness(const int64_t* counts, int n_groups, int64_
     cfg.blockDim = dim3(1024);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = as_stream(stream);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (!getenv("SCB_NO_PDL")) {
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        ++n_attr;
+    }
+    // Sharded cells, experiment (SCB_FITNESS_CLUSTER=1): clusters of up to 8 CTAs share the summing of
+    // the ranks' slots.  Measured at N=8 on H1M: 37.5 us per step against 28.7 us without clusters --
+    // a cluster only starts when 8 SMs of one GPC are free of rule_counts CTAs, and the two cluster
+    // barriers cost more than the 7/8 of the L2 reads they save.  Off by default.
+    int cluster = 1;
+    if (region && n_ranks > 1 && getenv("SCB_FITNESS_CLUSTER"))
+        for (cluster = 8; cluster > 1 && blocks % cluster != 0; cluster >>= 1) {}
+    if (cluster > 1) {
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = (unsigned)cluster;
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("SCB_NO_PDL") ? 0 : 1;
+    cfg.numAttrs = n_attr;
     SCB_CUDA(cudaLaunchKernelEx(&cfg, population_fitness_kernel, counts, n_groups, n_individuals, lut, active,
                                 out_diff, out_diff_pg, region, rank, n_ranks));
     return SCB_OK;
