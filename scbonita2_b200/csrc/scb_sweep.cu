@@ -939,20 +939,32 @@ sweep_kernel(const SweepArgs args) {
                     load_cells(args.np_states_t, xs ^ 2, xn ^ 2);
                     __syncthreads();
                 }
+                // lanes whose perturbed AND normal run have period 2: offset 2 repeats offset 0
+                const uint32_t both2 = valid & planes_ge(lam, 2) & planes_ge(lamn, 2);
+                uint32_t sc_both2 = 0;
                 if (valid) {
                     uint32_t sc = 0;
 #pragma unroll 4
                     for (int n = n_lo; n < n_hi; ++n) {
                         const uint32_t ref = IS_GATHER ? at(xs ^ 2, n) : __ldg(args.np_states + (size_t)n * wpad + word);
-                        sc += __popc((at(xs, n) ^ ref) & valid);
+                        const uint32_t x = (at(xs, n) ^ ref) & valid;
+                        sc += __popc(x);
+                        sc_both2 += __popc(x & both2);
                     }
                     score = sc;
                 }
                 if (!__syncthreads_or((valid & (planes_ge(lam, 2) | planes_ge(lamn, 2))) != 0)) {
                     score *= 2;  // every counted cell: fixed point vs fixed point, offset 1 repeats offset 0
                 } else {
-                    // offsets 1..min(lambda_x, lambda_n): step, and compare the new state while it is made
+                    // offsets 1..min(lambda_x, lambda_n): step, and compare the new state while it is made.
+                    // With no period above 2 in the CTA, offset 2 is offset 0 again for the period-2 pairs
+                    // (state_mu+2 = state_mu on both sides) and nothing else is active: one step suffices.
+                    const bool short_cycles = !__syncthreads_or((valid & (planes_ge(lam, 3) | planes_ge(lamn, 3))) != 0);
                     for (int t = 1; t < steps; ++t) {
+                        if (short_cycles && t == 2) {
+                            score += sc_both2;
+                            break;
+                        }
                         const uint32_t act = valid & planes_ge(lam, t) & planes_ge(lamn, t);
                         if (!__syncthreads_or(act != 0)) break;
                         const int kref = xs ^ 2;
