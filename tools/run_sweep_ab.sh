@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_sweep.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -2
-SCB_SWEEP_FAST_STEPS=6 python -m pytest tests/test_gpu_sweep.py -x -q -m gpu 2>&1 | tail -2
-python tools/time_sweep.py 2>&1 | tail -1
+python bench.py --steps 2 --warmup 3 > gpurun_out/b_pre_ncu2.json 2> gpurun_out/b_pre_ncu2.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_v6.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_v6.log 2>&1
+tail -2 gpurun_out/ncu_v6.log | cut -c1-300
