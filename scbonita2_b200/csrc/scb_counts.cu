@@ -112,13 +112,21 @@ __device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, 
 // 1, one of weight 2 and one of weight 4; the eighth is counted as it is (8 LOP3 + 4 POPC; the
 // weighted sum is finished arithmetically).  POPC issues on the quarter-rate XU pipe, LOP3 on the
 // half-rate ALU pipe: with the eight ANDs that form a term this split keeps the two equally busy.
+#ifndef SCB_POPC8_VARIANT
+#define SCB_POPC8_VARIANT 0
+#endif
 __device__ __forceinline__ uint32_t popc8(const uint32_t (&x)[8]) {
     uint32_t o1, t1, o2, t2, o3, t3, tt, f1;
     csa(t1, o1, x[0], x[1], x[2]);
     csa(t2, o2, x[3], x[4], x[5]);
     csa(t3, o3, o1, o2, x[6]);
+#if SCB_POPC8_VARIANT == 1
+    // experiment: 6 LOP3 + 5 POPC (the three weight-2 words are counted as they are)
+    return __popc(o3) + __popc(x[7]) + 2 * (__popc(t1) + __popc(t2) + __popc(t3));
+#else
     csa(f1, tt, t1, t2, t3);
     return __popc(o3) + __popc(x[7]) + 2 * __popc(tt) + 4 * __popc(f1);
+#endif
 }
 
 // number of parent slots a group binds when they are packed to the left (A, AB, ABC); any other
