@@ -136,7 +136,12 @@ struct SweepArgs {
     unsigned int* counters;         // [1] flags (bit 0: normal run has lambda >= 3 or an unsettled cell)
     int fast_steps;                 // KO/KI: steps of the ring fast path before open cells are deferred;
                                     // <= 0: chosen on the device from the normal run (counters[3])
-    unsigned int* settle_hist;      // [64] normal run: cells whose first repeat the ring saw in step t
+    unsigned int* settle_hist;      // [64] normal run: cells whose first repeat (period <= 2) the ring saw in step t
+    uint32_t* np_hard;              // [wpad] normal run: cells the deep ring could not settle (long cycle / no repeat)
+    int32_t* hard_cells;            // KO/KI pass: such cells go straight to this list (the cleanup pass's input)
+    int64_t hard_cap;
+    unsigned int* hard_count;
+    int recheck_follows;            // the KO/KI pass is followed by the compacted recheck pass (deep ring)
     unsigned long long* out_raw;
     unsigned long long* out_missing;
     unsigned long long* out_keyerror;
@@ -488,7 +493,11 @@ sweep_kernel(const SweepArgs args) {
     // The compacted recheck pass always runs the deep ring: a perturbation often creates cycles of
     // length 3 or 4 (half of the cells the short ring leaves open on the H1M data), and the ring settles
     // them at a fifth of the cost of the general scheme.
-    const bool deep_ring = MODE == MODE_KOKI ? (args.counters[1] & 1u) != 0 : true;
+    // When the recheck pass follows and the register ring applies, the KO/KI pass keeps the short
+    // ring whatever the normal run showed: periods 3 and 4 are the recheck pass's business.
+    const bool koki_short = SLOTS == 64 && kSweepThreads >= 512 && kRegRing && args.recheck_follows &&
+                            N <= (kSweepThreads / 32) * ((208 + kSweepThreads / 32 - 1) / (kSweepThreads / 32));
+    const bool deep_ring = MODE == MODE_KOKI ? (!koki_short && (args.counters[1] & 1u) != 0) : true;
 
     int batch = blockIdx.x;
     do {
@@ -508,6 +517,18 @@ sweep_kernel(const SweepArgs args) {
             forced_node = (int)(blockIdx.x % (unsigned)N);
             forced_value = slot >= HALF ? 0xFFFFFFFFu : 0u;
             cellmask = word < wpad ? tail_mask(word, args.n_cells) : 0u;
+            // Cells whose UNPERTURBED run already needed the general scheme (period > 4 or no repeat)
+            // almost always need it under a perturbation too: they skip both ring passes and go
+            // straight to the cleanup list.  (Any split of the cells among the passes gives the same
+            // result -- every pass is exact -- so this is only about where the time goes.)
+            const uint32_t hard = word < wpad ? __ldg(args.np_hard + word) & cellmask : 0u;
+            if (hard && part == 0 && slot < HALF) {
+                const unsigned int k = __popc(hard);
+                const unsigned int at0 = atomicAdd(&args.hard_count[forced_node], k);
+                int32_t* dst = args.hard_cells + (size_t)forced_node * args.hard_cap + at0;  // cap = n_cells: always room
+                for (uint32_t m = hard; m; m &= m - 1) *dst++ = (int32_t)(word * 32 + (__ffs(m) - 1));
+            }
+            cellmask &= ~hard;
         } else {
             // a virtual word: 32 deferred cells of one node, gathered from anywhere in the data
             if (tid == 0) {
@@ -685,7 +706,8 @@ sweep_kernel(const SweepArgs args) {
                 lam[2] |= e4;
                 frozen |= e1 | e2 | e3 | e4;
                 if (MODE == MODE_NORMAL && part == 0) {  // settle-time histogram (choose_fast_steps_kernel)
-                    const unsigned int c = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)__popc(e1 | e2 | e3 | e4));
+                    // only periods <= 2 count as settled: that is what the KO/KI pass's short ring can see
+                    const unsigned int c = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)__popc(e1 | e2));
                     if ((tid & 31) == 0 && c) atomicAdd(&args.settle_hist[t], c);
                 }
                 // the other accumulator set is idle between the two barriers: clear it for step t+1
@@ -696,6 +718,7 @@ sweep_kernel(const SweepArgs args) {
             xn = (xs + 1) & 3;
             found = frozen & cellmask;
             unresolved = ~frozen;
+            if (MODE == MODE_NORMAL && part == 0 && word_ok) args.np_hard[word] = unresolved & cellmask;
             SCB_SWEEP_PHASE(2);
         }
 
@@ -1135,6 +1158,10 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, cudaStream_t st
     }
     constexpr int HALF = SLOTS / 2;
     const bool two_level = args.fast_steps < args.steps;  // also when the device chooses (fast_steps <= 0)
+    args.hard_cells = lists.cells_b;
+    args.hard_cap = lists.cap_b;
+    args.hard_count = lists.count_b;
+    args.recheck_follows = two_level ? 1 : 0;
     // KO/KI on the plane words; open cells go to list A (or straight to B without a recheck pass)
     args.out_cells = two_level ? lists.cells_a : lists.cells_b;
     args.out_cap = two_level ? lists.cap_a : lists.cap_b;
@@ -1191,7 +1218,7 @@ extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int 
     if (n_nodes <= 0 || wpad <= 0 || steps <= 0) return 0;
     // normal-run states + lambda planes + found plane + the two per-node lists of deferred cells +
     // their fill counts + counters
-    return ((int64_t)steps * n_nodes + kLamPlanes + 1) * wpad * 4 +
+    return ((int64_t)steps * n_nodes + kLamPlanes + 2) * wpad * 4 +
            (int64_t)(steps + 1) * wpad * 32 * record_words(n_nodes) * 4 + wpad * 32 * 4 +
            (int64_t)n_nodes * (sweep_list_capacity(wpad * 32, kListDivA) + sweep_list_capacity(wpad * 32, kListDivB)) * 4 +
            64 * 4 + (int64_t)n_nodes * 8 + 16;
@@ -1228,7 +1255,8 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     lists.cap_a = sweep_list_capacity(wpad * 32, kListDivA);
     lists.cap_b = sweep_list_capacity(wpad * 32, kListDivB);
     args.nwp = record_words(n_nodes);
-    args.planes_t = args.np_found + wpad;
+    args.np_hard = args.np_found + wpad;
+    args.planes_t = args.np_hard + wpad;
     args.np_states_t = args.planes_t + (size_t)wpad * 32 * args.nwp;
     args.np_info_t = args.np_states_t + (size_t)steps * wpad * 32 * args.nwp;
     lists.cells_a = reinterpret_cast<int32_t*>(args.np_info_t + (size_t)wpad * 32);

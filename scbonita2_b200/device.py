@@ -338,7 +338,8 @@ def ko_ki_sweep(planes: BitPlanes, net_parent, net_lut, steps: int = 50, out=Non
             LAST_SWEEP_STATS.update(rechecked_cells=int(tail[:n].sum()), rechecked_max_per_node=int(tail[:n].max()),
                                     deferred_cells=int(tail[n:2 * n].sum()),
                                     deferred_max_per_node=int(tail[n:2 * n].max()),
-                                    deep_ring=bool(tail[2 * n + 1] & 1), cell_node_pairs=int(planes.n_cells) * n)
+                                    deep_ring=bool(tail[2 * n + 1] & 1), fast_steps=int(tail[2 * n + 3]),
+                                    cell_node_pairs=int(planes.n_cells) * n)
     return out
 
 
