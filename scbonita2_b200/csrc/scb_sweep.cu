@@ -214,21 +214,25 @@ __device__ unsigned long long g_sweep_phase[4][16];
 // How many ring steps the KO/KI pass runs on the plane words before it hands the cells that are
 // still open to the compacted recheck pass.  A step on the plane words costs the same whether one
 // lane of a word is open or all 32, a rechecked cell is simulated again from the start: with u(T) the
-// share of cells still open after T steps the work is ~ T + kRecheckSteps * u(T) plane-word steps.
+// share of cells still open after T steps the work is ~ T + kRecheckSteps * (u(T) - u(steps)) plane-word steps.
 // u is taken from the NORMAL run (settle-time histogram), the KO/KI runs of a cell settle at about
 // the same time as its unperturbed run.  Any choice gives the same results.
 constexpr int kRecheckSteps = 115;  // cost of rechecking every cell, in plane-word steps (measured, H1M)
 __global__ void choose_fast_steps_kernel(const unsigned int* __restrict__ hist, int steps, int64_t n_cells,
                                          unsigned int* __restrict__ counters) {
     if (threadIdx.x != 0) return;
+    // cells that never settle within the window are rechecked whatever T is: only the cells that
+    // WOULD have settled between T and `steps` are the price of stopping early
+    long long never = n_cells;
+    for (int t = 0; t < steps; ++t) never -= hist[t];
     long long open = n_cells;
-    long long best_cost = (long long)steps * n_cells;  // T = steps: nothing is rechecked for being slow
+    long long best_cost = (long long)steps * n_cells;  // T = steps
     int best = steps;
     for (int t = 0; t < steps; ++t) {
         open -= hist[t];  // open after T = t + 1 steps
         const int T = t + 1;
         if (T < 4) continue;
-        const long long cost = (long long)T * n_cells + (long long)kRecheckSteps * open;
+        const long long cost = (long long)T * n_cells + (long long)kRecheckSteps * (open - never);
         if (cost < best_cost) {
             best_cost = cost;
             best = T;
