@@ -773,9 +773,11 @@ sweep_kernel(const SweepArgs args) {
             for (int b = 0; b < kLamPlanes; ++b) lam[b] = 0;
             uint32_t cyc = 0, found_fp = 0;
             int chk_time = -1;
-            int t_need = 1;
-            while (t_need - 1 < steps - 2) t_need <<= 1;  // smallest 2^k - 1 >= steps - 2
-            const int t1_max = (t_need - 1) + steps;
+            // Checkpoints at t = 2^k - 1 < steps - 1 and a LAST one at t = steps - 1: a cell with a
+            // repeat inside the window (mu + lambda <= steps - 1) is on its cycle by then and is back
+            // at that state lambda <= steps - 1 steps later, so 2 * steps - 1 steps settle every cell
+            // (a power-of-two schedule alone needs up to 2^k - 1 + steps with 2^k - 1 >= steps - 2).
+            const int t1_max = 2 * steps - 1;
             for (int t = 0; t < t1_max; ++t) {
                 uint32_t neq_prev = 0, neq_chk = 0;
 #pragma unroll 2
@@ -806,7 +808,7 @@ sweep_kernel(const SweepArgs args) {
                     }
                     resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
                 }
-                if (((t + 1) & t) == 0) {  // t = 2^k - 1: new checkpoint = state_t (own nodes only)
+                if ((((t + 1) & t) == 0 && t < steps - 1) || t == steps - 1) {  // new checkpoint = state_t (own nodes only)
                     for (int n = n_lo; n < n_hi; ++n) at(chk, n) = at(nxt, n);
                     chk_time = t;
                 }
