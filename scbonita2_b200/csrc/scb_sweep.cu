@@ -1092,8 +1092,9 @@ static size_t sweep_smem_bytes(int n_nodes, int slots) {
            (size_t)(slots / 2) * 32 * 4 + (size_t)(1 + kLamPlanes) * (slots / 2) * 4 + (size_t)(n_nodes + 1) * 4;
 }
 
-// room per node for deferred cells (list A: a quarter of the cells, list B: an eighth); a full list
-// only means its cells are settled in place
+// room per node for deferred cells: every cell (div = 1) -- single nodes send up to 89 % of the
+// cells to the cleanup pass on the H1M data, and a list that overflowed would settle its cells
+// inside the plane-word CTAs at many times the cost
 static int64_t sweep_list_capacity(int64_t n_cells, int div) {
     int64_t cap = n_cells / div;
     if (cap < 65536) cap = 65536;
@@ -1104,9 +1105,9 @@ constexpr int kListDivA = 1, kListDivB = 1;
 constexpr size_t kMaxDynSmem = 232448;  // 227 KB
 
 // Lists of deferred cells: list A takes what the KO/KI pass leaves open after `fast_steps` ring steps
-// (slow convergers and hard cells alike), list B what the recheck pass leaves open after the full
-// number of steps (cycles longer than the ring, no repeat).  A full list only means that its cells
-// are settled in place.
+// (slow convergers, periods 3 and 4, hard cells alike), list B the cells the normal run could not
+// settle with the ring (straight from the KO/KI pass) and what the recheck pass leaves open after
+// the full number of steps (cycles longer than the ring, no repeat).
 struct SweepLists {
     int32_t* cells_a;
     int64_t cap_a;
