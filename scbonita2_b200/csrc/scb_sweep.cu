@@ -256,6 +256,10 @@ enum { MODE_NORMAL = 0, MODE_KOKI = 1, MODE_CLEANUP = 2, MODE_RECHECK = 3 };
 #define SCB_RING_ARITY 1
 #endif
 constexpr bool kRingArity = SCB_RING_ARITY != 0;  // experiments: 0 evaluates every node as a three-parent one
+#ifndef SCB_REG_BRENT
+#define SCB_REG_BRENT 1
+#endif
+constexpr bool kRegBrent = SCB_REG_BRENT != 0;  // experiments: 0 keeps the Brent phase's compare operands in shared memory
 constexpr bool kRegRing = SCB_REG_RING != 0;  // experiments: 0 keeps the ring of the fast path in shared memory
 constexpr int kMaskPad = 15;  // all-zero truth tables after the last node
 constexpr int kRing = 4;  // state copies per slot: ring of the fast path, P/Q pairs of the slow path
@@ -425,6 +429,164 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
     }
     __syncthreads();
     return result_copy;
+}
+
+// Brent phase of the general scheme with the compare operands in REGISTERS (same thread layout as
+// ring2_registers: thread (lane, warp p) owns nodes [p*CH, p*CH + CH) of slots `lane` and
+// `lane + 32`).  The previous state and the checkpoint of the thread's own nodes stay in its
+// registers, shared memory only carries the current and the next state (copies 0 and 1), and there
+// is one CTA barrier per step.  Per slot it delivers lambda (6 planes), `cyc` (lanes with a
+// period > 1 found through a checkpoint) and `found_fp` (lanes that reached a fixed point inside
+// the window) in res[plane * 64 + slot], planes 0..5 = lambda, 6 = cyc, 7 = found_fp; returns the copy
+// that holds the last state.  No lane is frozen here: the replay that follows restarts from the data.
+template <int CH>
+__device__ __forceinline__ int brent_registers(uint32_t* __restrict__ state, const NodeOffsets* __restrict__ offs,
+                                               const LutMasks* __restrict__ masks, uint32_t* __restrict__ votes,
+                                               int N, int forced_node, uint32_t cellmask, int steps, int tid) {
+    constexpr int SL = 64, STRIDE = 4 * SL, SET = 2 * SL;
+    const int lane = tid & 31;
+    const int n0 = (tid >> 5) * CH;
+    const int n_mine = N - n0;
+    const int forced_i = forced_node - n0;
+    uint32_t cur0[CH], cur1[CH], chk0[CH], chk1[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        cur0[i] = cur1[i] = chk0[i] = chk1[i] = 0u;
+        if (i < n_mine) {
+            cur0[i] = state[((n0 + i) * 4 + 0) * SL + lane];
+            cur1[i] = state[((n0 + i) * 4 + 0) * SL + lane + 32];
+        }
+    }
+    for (int i = tid; i < 3 * SET; i += blockDim.x) votes[i] = 0;
+    __syncthreads();
+    uint32_t resolved0 = ~cellmask, resolved1 = ~cellmask;
+    uint32_t lam0[kLamPlanes], lam1[kLamPlanes];
+#pragma unroll
+    for (int b = 0; b < kLamPlanes; ++b) lam0[b] = lam1[b] = 0u;
+    uint32_t cyc0 = 0, cyc1 = 0, fp0 = 0, fp1 = 0;
+    int chk_time = -1;
+    bool all_prev = false;
+    int vset = 0;
+    const int t1_max = 2 * steps - 1;  // see the checkpoint schedule below
+
+    auto step = [&](auto rd_tag, int t) -> bool {
+        constexpr int RD = decltype(rd_tag)::value ? 0 : 1, WR = decltype(rd_tag)::value ? 1 : 0;
+        uint32_t qp0 = 0, qp1 = 0, qc0 = 0, qc1 = 0;
+        const uint32_t* __restrict__ srd = state + RD * SL + lane;
+        uint32_t* __restrict__ swr = state + (n0 * 4 + WR) * SL + lane;
+        if (n_mine > 0) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const NodeOffsets o = offs[n0 + i];  // padded with all-zero entries past the last node
+                const LutMasks& mk = masks[n0 + i];
+                uint32_t f0, f1;
+                if (kRingArity && o.arity <= 1) {
+                    const uint32_t m0 = mk.m[0], m4 = mk.m[4];
+                    f0 = lop3<0xCA>(srd[o.pa], m4, m0);
+                    f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
+                } else {
+                    const uint4 lo = *reinterpret_cast<const uint4*>(&mk.m[0]);
+                    const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
+                    const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
+                    const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
+                    if (kRingArity && o.arity == 2) {
+                        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
+                        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
+                    } else {
+                        const uint32_t c0 = srd[o.pc], c1 = srd[o.pc + 32];
+                        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
+                                        lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
+                        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
+                                        lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
+                    }
+                }
+                if (i == forced_i) {
+                    f0 = 0u;
+                    f1 = 0xFFFFFFFFu;
+                }
+                qp0 |= f0 ^ cur0[i];
+                qp1 |= f1 ^ cur1[i];
+                qc0 |= f0 ^ chk0[i];
+                qc1 |= f1 ^ chk1[i];
+                if (i < n_mine) {
+                    swr[i * STRIDE] = f0;
+                    swr[i * STRIDE + 32] = f1;
+                }
+                cur0[i] = f0;
+                cur1[i] = f1;
+            }
+        }
+        uint32_t* v = votes + vset * SET;
+        if (qp0) atomicOr(v + lane, qp0);
+        if (qp1) atomicOr(v + 32 + lane, qp1);
+        if (chk_time >= 0) {
+            if (qc0) atomicOr(v + SL + lane, qc0);
+            if (qc1) atomicOr(v + SL + 32 + lane, qc1);
+        }
+        if (__syncthreads_and(all_prev)) return true;  // every lane was resolved after the step before: copy RD is the last state
+        const int l = t - chk_time;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t& resolved = h ? resolved1 : resolved0;
+            uint32_t(&lam)[kLamPlanes] = h ? lam1 : lam0;
+            uint32_t& cyc = h ? cyc1 : cyc0;
+            uint32_t& fp = h ? fp1 : fp0;
+            const uint32_t neq_prev = v[32 * h + lane], neq_chk = v[SL + 32 * h + lane];
+            if (t >= 1) {
+                const uint32_t newly = ~neq_prev & ~resolved;
+                lam[0] |= newly;  // lambda = 1
+                resolved |= newly;
+                if (t <= steps - 1) fp |= newly;
+            }
+            if (chk_time >= 0) {
+                const uint32_t newly = ~neq_chk & ~resolved;
+                if (l <= steps - 1) {
+                    planes_set(lam, newly, l);
+                    cyc |= newly;
+                }
+                resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
+            }
+        }
+        // checkpoints at t = 2^k - 1 < steps - 1 and a last one at t = steps - 1 (see the shared-memory version)
+        if ((((t + 1) & t) == 0 && t < steps - 1) || t == steps - 1) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                chk0[i] = cur0[i];
+                chk1[i] = cur1[i];
+            }
+            chk_time = t;
+        }
+        const int vclear = vset == 0 ? 2 : vset - 1;
+        if (tid < SET) votes[vclear * SET + tid] = 0;
+        vset = vset == 2 ? 0 : vset + 1;
+        all_prev = (resolved0 & resolved1) == 0xFFFFFFFFu;
+        return false;
+    };
+    using FromData = std::integral_constant<bool, true>;   // reads copy 0
+    using FromOther = std::integral_constant<bool, false>;  // reads copy 1
+    int last_copy = 0;
+    for (int t = 0; t < t1_max; t += 2) {
+        last_copy = 0;
+        if (step(FromData{}, t)) break;
+        last_copy = 1;
+        if (t + 1 >= t1_max) break;
+        if (step(FromOther{}, t + 1)) break;
+        last_copy = 0;
+    }
+    __syncthreads();  // every vote word has been read
+    if (tid < 32) {
+#pragma unroll
+        for (int b = 0; b < kLamPlanes; ++b) {
+            votes[b * SL + lane] = lam0[b];
+            votes[b * SL + 32 + lane] = lam1[b];
+        }
+        votes[6 * SL + lane] = cyc0;
+        votes[6 * SL + 32 + lane] = cyc1;
+        votes[7 * SL + lane] = fp0;
+        votes[7 * SL + 32 + lane] = fp1;
+    }
+    __syncthreads();
+    return last_copy;
 }
 
 // State layout in shared memory: word (node n, copy k, slot s) lives at ((n*4 + k)*SLOTS + s), so
@@ -773,11 +935,25 @@ sweep_kernel(const SweepArgs args) {
             for (int b = 0; b < kLamPlanes; ++b) lam[b] = 0;
             uint32_t cyc = 0, found_fp = 0;
             int chk_time = -1;
+            constexpr int kWarpsB = kSweepThreads / 32;
+            constexpr int CHB_L = (208 + kWarpsB - 1) / kWarpsB, CHB_M = (128 + kWarpsB - 1) / kWarpsB, CHB_S = (64 + kWarpsB - 1) / kWarpsB;
+            const bool reg_brent = MODE == MODE_CLEANUP && SLOTS == 64 && kWarpsB >= 16 && N <= kWarpsB * CHB_L && kRegRing && kRegBrent;
+            if (reg_brent) {
+                cur = N <= kWarpsB * CHB_S   ? brent_registers<CHB_S>(state, offs, masks, votes, N, forced_node, cellmask, steps, tid)
+                      : N <= kWarpsB * CHB_M ? brent_registers<CHB_M>(state, offs, masks, votes, N, forced_node, cellmask, steps, tid)
+                                             : brent_registers<CHB_L>(state, offs, masks, votes, N, forced_node, cellmask, steps, tid);
+                nxt = cur ^ 1;
+#pragma unroll
+                for (int b = 0; b < kLamPlanes; ++b) lam[b] = votes[b * SLOTS + slot];
+                cyc = votes[6 * SLOTS + slot];
+                found_fp = votes[7 * SLOTS + slot];
+                __syncthreads();  // votes is reused below
+            }
             // Checkpoints at t = 2^k - 1 < steps - 1 and a LAST one at t = steps - 1: a cell with a
             // repeat inside the window (mu + lambda <= steps - 1) is on its cycle by then and is back
             // at that state lambda <= steps - 1 steps later, so 2 * steps - 1 steps settle every cell
             // (a power-of-two schedule alone needs up to 2^k - 1 + steps with 2^k - 1 >= steps - 2).
-            const int t1_max = 2 * steps - 1;
+            const int t1_max = reg_brent ? 0 : 2 * steps - 1;
             for (int t = 0; t < t1_max; ++t) {
                 uint32_t neq_prev = 0, neq_chk = 0;
 #pragma unroll 2
