@@ -589,6 +589,161 @@ __device__ __forceinline__ int brent_registers(uint32_t* __restrict__ state, con
     return last_copy;
 }
 
+// Replay phase of the general scheme in the same register layout (thread (lane, warp p): nodes
+// [p*CH, p*CH + CH) of slots `lane` and `lane + 32`).  On entry copies 0 and 2 hold the data, the
+// lambda planes of every slot sit in res[b * 64 + slot] (brent_registers).  P (copies 0/1) first
+// runs lambda_cell steps ahead under per-cell stall masks, then P and Q (copies 2/3) step together
+// -- one fetch of a node's table serves both and both slots -- until they meet: the first j with
+// P == Q is mu; a repeat counts iff mu + lambda <= steps - 1; Q freezes at state_mu.  The own-node
+// words that the stall / freeze merges need stay in registers.  Leaves `found` per slot in
+// res[slot]; returns the copy that holds Q (its partner is that copy ^ 1).
+template <int CH>
+__device__ __forceinline__ int replay_registers(uint32_t* __restrict__ state, const NodeOffsets* __restrict__ offs,
+                                                const LutMasks* __restrict__ masks, uint32_t* __restrict__ votes,
+                                                int N, int forced_node, uint32_t cellmask, int steps, int tid) {
+    constexpr int SL = 64, STRIDE = 4 * SL;
+    const int lane = tid & 31;
+    const int n0 = (tid >> 5) * CH;
+    const int n_mine = N - n0;
+    const int forced_i = forced_node - n0;
+    uint32_t lam0[kLamPlanes], lam1[kLamPlanes];
+#pragma unroll
+    for (int b = 0; b < kLamPlanes; ++b) {
+        lam0[b] = votes[b * SL + lane];
+        lam1[b] = votes[b * SL + 32 + lane];
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * SL; i += blockDim.x) votes[i] = 0;  // two sets of one vote word per slot
+    uint32_t pq0[CH], pq1[CH];  // own nodes: P during the advance, Q afterwards
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        pq0[i] = pq1[i] = 0u;
+        if (i < n_mine) {
+            pq0[i] = state[((n0 + i) * 4 + 0) * SL + lane];
+            pq1[i] = state[((n0 + i) * 4 + 0) * SL + lane + 32];
+        }
+    }
+    __syncthreads();
+    const uint32_t has0 = planes_ge(lam0, 1) & cellmask, has1 = planes_ge(lam1, 1) & cellmask;
+
+    // value of node n0 + i for both slots, reading copy `rd`
+    auto eval2 = [&](int i, const uint32_t* __restrict__ srd, uint32_t& f0, uint32_t& f1) {
+        const NodeOffsets o = offs[n0 + i];
+        const LutMasks& mk = masks[n0 + i];
+        if (kRingArity && o.arity <= 1) {
+            const uint32_t m0 = mk.m[0], m4 = mk.m[4];
+            f0 = lop3<0xCA>(srd[o.pa], m4, m0);
+            f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
+        } else {
+            const uint4 lo = *reinterpret_cast<const uint4*>(&mk.m[0]);
+            const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
+            const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
+            const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
+            if (kRingArity && o.arity == 2) {
+                f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
+                f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
+            } else {
+                const uint32_t c0 = srd[o.pc], c1 = srd[o.pc + 32];
+                f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
+                                lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
+                f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
+                                lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
+            }
+        }
+        if (i == forced_i) {
+            f0 = 0u;
+            f1 = 0xFFFFFFFFu;
+        }
+    };
+
+    int pc_ = 0, pn_ = 1;
+    for (int s = 0; s < steps; ++s) {
+        const uint32_t adv0 = planes_gt(lam0, s) & has0, adv1 = planes_gt(lam1, s) & has1;  // lanes that still owe P a step
+        if (!__syncthreads_or((adv0 | adv1) != 0)) break;
+        if (n_mine > 0) {
+            const uint32_t* __restrict__ srd = state + pc_ * SL + lane;
+            uint32_t* __restrict__ swr = state + (n0 * 4 + pn_) * SL + lane;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                uint32_t f0, f1;
+                eval2(i, srd, f0, f1);
+                pq0[i] = (f0 & adv0) | (pq0[i] & ~adv0);
+                pq1[i] = (f1 & adv1) | (pq1[i] & ~adv1);
+                if (i < n_mine) {
+                    swr[i * STRIDE] = pq0[i];
+                    swr[i * STRIDE + 32] = pq1[i];
+                }
+            }
+        }
+        __syncthreads();
+        const int tmp = pc_;
+        pc_ = pn_;
+        pn_ = tmp;
+    }
+    // from here on the registers hold Q's own nodes (copy 2 = the data)
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        pq0[i] = pq1[i] = 0u;
+        if (i < n_mine) {
+            pq0[i] = state[((n0 + i) * 4 + 2) * SL + lane];
+            pq1[i] = state[((n0 + i) * 4 + 2) * SL + lane + 32];
+        }
+    }
+    int qc_ = 2, qn_ = 3;
+    uint32_t done0 = ~has0, done1 = ~has1, found0 = 0, found1 = 0;
+    for (int j = 0; j <= steps - 2; ++j) {
+        uint32_t neq0 = 0, neq1 = 0;
+        if (n_mine > 0) {
+            const uint32_t* __restrict__ prd = state + pc_ * SL + lane;
+            const uint32_t* __restrict__ qrd = state + qc_ * SL + lane;
+            uint32_t* __restrict__ pwr = state + (n0 * 4 + pn_) * SL + lane;
+            uint32_t* __restrict__ qwr = state + (n0 * 4 + qn_) * SL + lane;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                uint32_t fp0, fp1, fq0, fq1;
+                eval2(i, prd, fp0, fp1);
+                eval2(i, qrd, fq0, fq1);
+                neq0 |= fp0 ^ fq0;
+                neq1 |= fp1 ^ fq1;
+                pq0[i] = (pq0[i] & done0) | (fq0 & ~done0);
+                pq1[i] = (pq1[i] & done1) | (fq1 & ~done1);
+                if (i < n_mine) {
+                    pwr[i * STRIDE] = fp0;
+                    pwr[i * STRIDE + 32] = fp1;
+                    qwr[i * STRIDE] = pq0[i];
+                    qwr[i * STRIDE + 32] = pq1[i];
+                }
+            }
+        }
+        uint32_t* v = votes + (j & 1) * SL;
+        if (neq0) atomicOr(v + lane, neq0);
+        if (neq1) atomicOr(v + 32 + lane, neq1);
+        __syncthreads();
+        // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
+        uint32_t newly = ~v[lane] & ~done0;
+        found0 |= newly & ~planes_gt(lam0, steps - 1 - j);
+        done0 |= newly;
+        newly = ~v[32 + lane] & ~done1;
+        found1 |= newly & ~planes_gt(lam1, steps - 1 - j);
+        done1 |= newly;
+        if (tid < SL) votes[((j + 1) & 1) * SL + tid] = 0;
+        int tmp = pc_;
+        pc_ = pn_;
+        pn_ = tmp;
+        tmp = qc_;
+        qc_ = qn_;
+        qn_ = tmp;
+        if (__syncthreads_and((done0 & done1) == 0xFFFFFFFFu)) break;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        votes[lane] = found0;
+        votes[32 + lane] = found1;
+    }
+    __syncthreads();
+    return qc_;
+}
+
 // State layout in shared memory: word (node n, copy k, slot s) lives at ((n*4 + k)*SLOTS + s), so
 // the four copies of a node sit at compile-time offsets from each other.
 template <int SLOTS, int MODE>
@@ -947,7 +1102,7 @@ sweep_kernel(const SweepArgs args) {
                 for (int b = 0; b < kLamPlanes; ++b) lam[b] = votes[b * SLOTS + slot];
                 cyc = votes[6 * SLOTS + slot];
                 found_fp = votes[7 * SLOTS + slot];
-                __syncthreads();  // votes is reused below
+                __syncthreads();  // (the lambda planes stay in `votes` for replay_registers)
             }
             // Checkpoints at t = 2^k - 1 < steps - 1 and a LAST one at t = steps - 1: a cell with a
             // repeat inside the window (mu + lambda <= steps - 1) is on its cycle by then and is back
@@ -992,7 +1147,17 @@ sweep_kernel(const SweepArgs args) {
                 int tmp = cur; cur = nxt; nxt = tmp;
                 if (__syncthreads_and(resolved == 0xFFFFFFFFu)) break;
             }
-            if (__syncthreads_or(cyc != 0)) {
+            if (reg_brent && __syncthreads_or(cyc != 0)) {
+                load_data(0, 1);
+                load_data(2, 3);
+                __syncthreads();
+                xs = N <= kWarpsB * CHB_S   ? replay_registers<CHB_S>(state, offs, masks, votes, N, forced_node, cellmask, steps, tid)
+                     : N <= kWarpsB * CHB_M ? replay_registers<CHB_M>(state, offs, masks, votes, N, forced_node, cellmask, steps, tid)
+                                            : replay_registers<CHB_L>(state, offs, masks, votes, N, forced_node, cellmask, steps, tid);
+                xn = xs ^ 1;
+                found = votes[slot];
+                __syncthreads();
+            } else if (!reg_brent && __syncthreads_or(cyc != 0)) {
                 int pc_ = 0, pn_ = 1;  // P: runs lambda ahead
                 int qc_ = 2, qn_ = 3;  // Q: freezes at state_mu
                 load_data(pc_, pn_);
