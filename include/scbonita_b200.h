@@ -193,7 +193,10 @@ int scb_bitstring_fitness(const int64_t* task_diff /*[T]*/, int64_t n_tasks, int
  *   out_keyerror     : #(cell,node) pairs that repeat under KO and KI but NOT under normal
  *                      (the reference raises KeyError there, importance_scores.py:281)
  * All outputs are ACCUMULATED INTO (+=), so shards of cells can share one buffer; zero them
- * first.  scratch: scb_ko_ki_sweep_scratch_bytes(...) bytes. */
+ * first.  scratch: scb_ko_ki_sweep_scratch_bytes(...) bytes, 16-byte aligned, private to the call
+ * while it runs (normal-run states node-major and cell-major, two per-node lists of deferred cells:
+ * about (2 * steps * N / 8 + 8 * N) bytes per cell, 4.5 GB for 200 nodes x 1M cells x 50 steps).
+ * Environment knobs for experiments only: SCB_SWEEP_FAST_STEPS, SCB_SWEEP_RING, SCB_SWEEP_SLOTS. */
 int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int steps);
 int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
                     const int32_t* net_parent /*[N][3]*/, const uint8_t* net_lut /*[N]*/,
