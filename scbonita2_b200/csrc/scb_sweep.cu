@@ -264,6 +264,34 @@ constexpr bool kRegRing = SCB_REG_RING != 0;  // experiments: 0 keeps the ring o
 constexpr int kMaskPad = 15;  // all-zero truth tables after the last node
 constexpr int kRing = 4;  // state copies per slot: ring of the fast path, P/Q pairs of the slow path
 
+// Value of one canonical node (NodeOffsets / LutMasks entry) for the two slots a thread of the
+// register layouts owns: `srd` points at (node 0, copy, slot lane), the second slot is 32 words on.
+// The node index is warp-uniform, so is the branch on its arity: one- and two-parent nodes read 2 / 4
+// rows and 2 / 4 table words and take 1 / 3 LOP3 per slot instead of 7.
+__device__ __forceinline__ void eval_pair(const NodeOffsets& o, const LutMasks& mk, const uint32_t* __restrict__ srd,
+                                          uint32_t& f0, uint32_t& f1) {
+    if (kRingArity && o.arity <= 1) {
+        const uint32_t m0 = mk.m[0], m4 = mk.m[4];
+        f0 = lop3<0xCA>(srd[o.pa], m4, m0);
+        f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
+        return;
+    }
+    const uint4 lo = *reinterpret_cast<const uint4*>(&mk.m[0]);
+    const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
+    const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
+    const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
+    if (kRingArity && o.arity == 2) {
+        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
+        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
+        return;
+    }
+    const uint32_t c0 = srd[o.pc], c1 = srd[o.pc + 32];
+    f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
+                    lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
+    f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
+                    lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
+}
+
 // Ring-of-2 fast path with the ring in REGISTERS (KO/KI and recheck passes, 64-slot CTAs of 16 warps,
 // N <= 16 * CH, N <= 256).  Thread (lane, warp p) owns nodes [p*CH, p*CH + CH) of the KO slot `lane`
 // AND the KI slot `lane + 32` of the same word: the truth-table masks are fetched once for both, the
@@ -339,29 +367,8 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
                 // a node past the end (only in the last warp with nodes: the offset and mask tables are
                 // padded with zero entries) has an all-zero truth table and all-zero registers: it votes
                 // "equal" and only its stores are suppressed
-                const NodeOffsets o = offs[n0 + i];
-                const LutMasks& mk = masks[n0 + i];
                 uint32_t f0, f1;
-                if (kRingArity && o.arity <= 1) {  // warp-uniform: 2 rows and 2 table words instead of 6 and 8
-                    const uint32_t m0 = mk.m[0], m4 = mk.m[4];
-                    f0 = lop3<0xCA>(srd[o.pa], m4, m0);
-                    f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
-                } else {
-                    const uint4 lo = *reinterpret_cast<const uint4*>(&mk.m[0]);
-                    const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
-                    const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
-                    const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
-                    if (kRingArity && o.arity == 2) {
-                        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
-                        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
-                    } else {
-                        const uint32_t c0 = srd[o.pc], c1 = srd[o.pc + 32];
-                        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
-                                        lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
-                        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
-                                        lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
-                    }
-                }
+                eval_pair(offs[n0 + i], masks[n0 + i], srd, f0, f1);
                 if (i == forced_i) {  // never true past the end
                     f0 = 0u;
                     f1 = 0xFFFFFFFFu;
@@ -477,29 +484,8 @@ __device__ __forceinline__ int brent_registers(uint32_t* __restrict__ state, con
         if (n_mine > 0) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
-                const NodeOffsets o = offs[n0 + i];  // padded with all-zero entries past the last node
-                const LutMasks& mk = masks[n0 + i];
                 uint32_t f0, f1;
-                if (kRingArity && o.arity <= 1) {
-                    const uint32_t m0 = mk.m[0], m4 = mk.m[4];
-                    f0 = lop3<0xCA>(srd[o.pa], m4, m0);
-                    f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
-                } else {
-                    const uint4 lo = *reinterpret_cast<const uint4*>(&mk.m[0]);
-                    const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
-                    const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
-                    const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
-                    if (kRingArity && o.arity == 2) {
-                        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
-                        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
-                    } else {
-                        const uint32_t c0 = srd[o.pc], c1 = srd[o.pc + 32];
-                        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
-                                        lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
-                        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
-                                        lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
-                    }
-                }
+                eval_pair(offs[n0 + i], masks[n0 + i], srd, f0, f1);  // tables padded with all-zero entries past the last node
                 if (i == forced_i) {
                     f0 = 0u;
                     f1 = 0xFFFFFFFFu;
@@ -628,28 +614,7 @@ __device__ __forceinline__ int replay_registers(uint32_t* __restrict__ state, co
 
     // value of node n0 + i for both slots, reading copy `rd`
     auto eval2 = [&](int i, const uint32_t* __restrict__ srd, uint32_t& f0, uint32_t& f1) {
-        const NodeOffsets o = offs[n0 + i];
-        const LutMasks& mk = masks[n0 + i];
-        if (kRingArity && o.arity <= 1) {
-            const uint32_t m0 = mk.m[0], m4 = mk.m[4];
-            f0 = lop3<0xCA>(srd[o.pa], m4, m0);
-            f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
-        } else {
-            const uint4 lo = *reinterpret_cast<const uint4*>(&mk.m[0]);
-            const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
-            const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
-            const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
-            if (kRingArity && o.arity == 2) {
-                f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
-                f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
-            } else {
-                const uint32_t c0 = srd[o.pc], c1 = srd[o.pc + 32];
-                f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
-                                lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
-                f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
-                                lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
-            }
-        }
+        eval_pair(offs[n0 + i], masks[n0 + i], srd, f0, f1);
         if (i == forced_i) {
             f0 = 0u;
             f1 = 0xFFFFFFFFu;
