@@ -30,11 +30,34 @@ import tempfile
 import types
 
 REFERENCE_CODE_DIR = "/root/reference/code"
+# git-ignored install of the unmodified reference sources (``install_baseline`` below, run by
+# ``__graft_entry__.build()`` in the build container): unlike /root/reference it travels to the GPU
+# box, where ``bench.py --impl reference`` and the sweep's ``cpu_baseline`` time it
+BASELINE_CODE_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "code")
 _STATE: dict = {}
 
 
+def code_dir():
+    for cand in (REFERENCE_CODE_DIR, BASELINE_CODE_DIR):
+        if os.path.isfile(os.path.join(cand, "importance_scores.py")):
+            return cand
+    return None
+
+
 def available() -> bool:
-    return os.path.isdir(REFERENCE_CODE_DIR)
+    return code_dir() is not None
+
+
+def install_baseline() -> bool:
+    """Copy the reference's ``code/*.py`` (unmodified) into git-ignored ``baseline/_ref/code``.
+    The reference is plain Python without a setup script, so this copy IS its install.  Returns
+    whether the install exists afterwards."""
+    if os.path.isdir(REFERENCE_CODE_DIR):
+        os.makedirs(BASELINE_CODE_DIR, exist_ok=True)
+        for name in sorted(os.listdir(REFERENCE_CODE_DIR)):
+            if name.endswith(".py"):
+                shutil.copyfile(os.path.join(REFERENCE_CODE_DIR, name), os.path.join(BASELINE_CODE_DIR, name))
+    return os.path.isfile(os.path.join(BASELINE_CODE_DIR, "importance_scores.py"))
 
 
 class _Anything:
@@ -99,15 +122,17 @@ def load() -> types.SimpleNamespace:
     """Return a namespace with the reference modules (imported once per process)."""
     if "ns" in _STATE:
         return _STATE["ns"]
-    if not available():
-        raise RuntimeError("reference sources are not mounted at " + REFERENCE_CODE_DIR)
+    src = code_dir()
+    if src is None:
+        raise RuntimeError("reference sources are neither mounted at " + REFERENCE_CODE_DIR +
+                           " nor installed at " + BASELINE_CODE_DIR)
     _install_shims()
     root = tempfile.mkdtemp(prefix="scbonita_ref_")
     atexit.register(shutil.rmtree, root, ignore_errors=True)
     code = os.path.join(root, "code")
-    shutil.copytree(REFERENCE_CODE_DIR, code, ignore=shutil.ignore_patterns("__pycache__"))
+    shutil.copytree(src, code, ignore=shutil.ignore_patterns("__pycache__"))
     sys.path.insert(0, code)
-    ns = types.SimpleNamespace(root=root, code_dir=code)
+    ns = types.SimpleNamespace(root=root, code_dir=code, source=src)
     for name in ("file_paths", "node_class", "network_class", "cell_class",
                  "rule_determination", "importance_scores", "rule_inference"):
         # a product alias of the same top-level name must not shadow the reference

@@ -37,6 +37,27 @@ int sm_count();
 
 static inline cudaStream_t as_stream(scb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: the high-water mark a call
+// site keeps (so the enqueue path stays free of non-stream API calls, e.g. under graph capture) is
+// kept per device, or a thread that has served cuda:0 would skip the call on cuda:1.
+struct SmemMarks {
+    size_t mark[64];  // zero-initialised (static thread_local at the call site); 0 = the 48 KB default
+};
+static inline int ensure_dynamic_smem(const void* kernel, size_t smem, SmemMarks& marks) {
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {  // no cache slot: set it every time
+        SCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return SCB_OK;
+    }
+    const size_t have = marks.mark[dev] ? marks.mark[dev] : (size_t)48 * 1024;
+    if (smem > have) {
+        SCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        marks.mark[dev] = smem;
+    }
+    return SCB_OK;
+}
+
 // lop3.b32 with a compile-time truth table: bit (a<<2|b<<1|c) of IMM
 template <int IMM>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {

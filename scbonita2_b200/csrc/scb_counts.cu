@@ -804,13 +804,10 @@ static int counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t 
             if (c >= 1 && c <= n_stages && kConsumerWarps % c == 0) n_teams = c;
         }
         const size_t smem = fixed + (size_t)n_stages * stage_bytes;
-        // the attribute is raised once per thread to the largest size seen (keeps the enqueue
+        // the attribute is raised once per thread and device to the largest size seen (keeps the enqueue
         // path free of non-stream API calls, e.g. under CUDA-graph capture)
-        static thread_local size_t attr_smem = 0;
-        if (smem > attr_smem) {
-            SCB_CUDA(cudaFuncSetAttribute(rule_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_smem = smem;
-        }
+        static thread_local SmemMarks marks;
+        if (int rc = ensure_dynamic_smem((const void*)rule_counts_kernel, smem, marks)) return rc;
         int64_t grid = sm_count();
         if (grid > n_tiles) grid = n_tiles;
         const int64_t n_acc = (int64_t)n_rows + (int64_t)kTermsPerGroup * gn;

@@ -230,11 +230,8 @@ extern "C" int scb_pattern_pair_distances(const uint16_t* patterns, int64_t n_ce
     SCB_REQUIRE(smem <= 200 * 1024, "pattern_pair_distances: %d genes exceed the shared-memory tile", n_genes);
     const int64_t blocks = (n_cells + kPairTile - 1) / kPairTile;
     SCB_REQUIRE(blocks <= 65535, "pattern_pair_distances: at most %d cells per call", 65535 * kPairTile);
-    static thread_local size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        SCB_CUDA(cudaFuncSetAttribute(pair_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    static thread_local SmemMarks marks;
+    if (int rc = ensure_dynamic_smem((const void*)pair_distance_kernel, smem, marks)) return rc;
     pair_distance_kernel<<<dim3((unsigned)blocks, (unsigned)blocks), kPairTile * kPairTile, smem, as_stream(stream)>>>(
         patterns, n_cells, n_genes, table, bits, out);
     SCB_LAUNCH_CHECK("pair_distance_kernel");

@@ -316,11 +316,8 @@ static int launch_population_fitness(const int64_t* counts, int n_groups, int64_
         set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 200));
         return SCB_ERR_UNSUPPORTED;
     }
-    static thread_local size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        SCB_CUDA(cudaFuncSetAttribute(population_fitness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    static thread_local SmemMarks marks;
+    if (int rc = ensure_dynamic_smem((const void*)population_fitness_kernel, smem, marks)) return rc;
     int64_t blocks = (n_individuals + 31) / 32;  // 32 warps per CTA, one individual per warp and round
     int64_t cap = (int64_t)sm_count();
     if (blocks > cap) blocks = cap;

@@ -142,6 +142,14 @@ struct SweepArgs {
     int64_t hard_cap;
     unsigned int* hard_count;
     int recheck_follows;            // the KO/KI pass is followed by the compacted recheck pass (deep ring)
+    // cells sorted by the settle time of their unperturbed run (launch_sweep): a probe run of MODE_NORMAL on
+    // the caller's planes writes a 6-bit key per cell (bit-sliced) and the histogram of the keys
+    int probe;                      // MODE_NORMAL: only write key_planes / key_hist
+    uint32_t* key_planes;           // [6][wpad]
+    unsigned int* key_hist;         // [64]
+    // KO/KI register ring: a CTA stops stepping when at most `stop_open` of its lanes are still open, or when
+    // lanes have started to settle and none did for `stop_stall` steps; open lanes go to the next pass
+    int stop_open, stop_stall;
     unsigned long long* out_raw;
     unsigned long long* out_missing;
     unsigned long long* out_keyerror;
@@ -196,6 +204,68 @@ cell_major_kernel(const uint32_t* __restrict__ src, int n_rows, int64_t wpad, ui
     }
 }
 
+// Inverse of cell_major_kernel for one slice: cell-major records src[wpad*32][nwp] -> node-major
+// bitplanes dst[n_rows][wpad].  One CTA makes 32 rows x 32 words: lane l of a warp reads word j of
+// cell 32w + l's record, the warp transpose hands lane b the 32 cell bits of node 32j + b, and the
+// tile goes out as coalesced row segments.  Cells at and past n_cells read as zero.
+__global__ void __launch_bounds__(256)
+node_major_kernel(const uint32_t* __restrict__ src, int nwp, int n_rows, int64_t wpad, int64_t n_cells,
+                  uint32_t* __restrict__ dst) {
+    __shared__ uint32_t tile[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w0 = (int64_t)blockIdx.x * 32;
+    const int j = blockIdx.y;
+    for (int wc = warp; wc < 32; wc += 8) {
+        const int64_t cell = (w0 + wc) * 32 + lane;
+        const uint32_t x = (w0 + wc < wpad && cell < n_cells) ? __ldg(src + (size_t)cell * nwp + j) : 0u;
+        tile[lane][wc] = warp_transpose32(x, lane);
+    }
+    __syncthreads();
+    for (int r = warp; r < 32; r += 8) {
+        const int row = 32 * j + r;
+        if (row < n_rows && w0 + lane < wpad) dst[(size_t)row * wpad + w0 + lane] = tile[r][lane];
+    }
+}
+
+// Counting sort of the cells by their 6-bit key (settle step of the unperturbed run, MODE_NORMAL probe):
+// cell c's record moves to position base[key] + (arrival order within the key).  The order inside a
+// key is arbitrary -- every output of the sweep is a sum over cells.
+__global__ void __launch_bounds__(256)
+sort_scatter_kernel(const uint32_t* __restrict__ key_planes, int64_t wpad, int64_t n_cells,
+                    const unsigned int* __restrict__ key_hist, unsigned int* __restrict__ bucket_fill,
+                    const uint32_t* __restrict__ rec_in, uint32_t* __restrict__ rec_out, int nwp) {
+    __shared__ unsigned int base[64];
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int k = 0; k < 64; ++k) {
+            base[k] = acc;
+            acc += key_hist[k];
+        }
+    }
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t w = c >> 5;
+    const bool active = c < n_cells;
+    unsigned int key = 0;
+    if (active) {
+#pragma unroll
+        for (int b = 0; b < 6; ++b) key |= ((__ldg(key_planes + (size_t)b * wpad + w) >> lane) & 1u) << b;
+    }
+    const unsigned int peers = __match_any_sync(0xFFFFFFFFu, active ? key : 0x100u + lane);
+    const int leader = __ffs(peers) - 1;
+    const unsigned int rank = __popc(peers & ((1u << lane) - 1u));
+    unsigned int start = 0;
+    if (active && lane == leader) start = atomicAdd(&bucket_fill[key], (unsigned int)__popc(peers));
+    start = __shfl_sync(0xFFFFFFFFu, start, leader);
+    if (active) {
+        const size_t pos = (size_t)base[key] + start + rank;
+        const uint4* in = reinterpret_cast<const uint4*>(rec_in + (size_t)c * nwp);
+        uint4* out = reinterpret_cast<uint4*>(rec_out + pos * nwp);
+        for (int q = 0; q < nwp / 4; ++q) out[q] = __ldg(in + q);
+    }
+}
+
 #ifdef SCB_TRACE
 // phase clock sums per MODE (tools/trace_sweep.py): [mode][phase] cycles of thread 0, [mode][15] CTAs/batches
 __device__ unsigned long long g_sweep_phase[4][16];
@@ -219,8 +289,12 @@ __device__ unsigned long long g_sweep_phase[4][16];
 // the same time as its unperturbed run.  Any choice gives the same results.
 constexpr int kRecheckSteps = 115;  // cost of rechecking every cell, in plane-word steps (measured, H1M)
 __global__ void choose_fast_steps_kernel(const unsigned int* __restrict__ hist, int steps, int64_t n_cells,
-                                         unsigned int* __restrict__ counters) {
+                                         unsigned int* __restrict__ counters, int sorted) {
     if (threadIdx.x != 0) return;
+    if (sorted) {  // cells sorted by settle step: every CTA stops at its own cells' pace (ring2_registers)
+        counters[3] = (unsigned int)steps;
+        return;
+    }
     // cells that never settle within the window are rechecked whatever T is: only the cells that
     // WOULD have settled between T and `steps` are the price of stopping early
     long long never = n_cells;
@@ -252,44 +326,80 @@ enum { MODE_NORMAL = 0, MODE_KOKI = 1, MODE_CLEANUP = 2, MODE_RECHECK = 3 };
 #ifndef SCB_REG_RING
 #define SCB_REG_RING 1
 #endif
-#ifndef SCB_RING_ARITY
-#define SCB_RING_ARITY 1
-#endif
-constexpr bool kRingArity = SCB_RING_ARITY != 0;  // experiments: 0 evaluates every node as a three-parent one
 #ifndef SCB_REG_BRENT
 #define SCB_REG_BRENT 1
 #endif
 constexpr bool kRegBrent = SCB_REG_BRENT != 0;  // experiments: 0 keeps the Brent phase's compare operands in shared memory
 constexpr bool kRegRing = SCB_REG_RING != 0;  // experiments: 0 keeps the ring of the fast path in shared memory
+#ifndef SCB_RING_ARITY
+#define SCB_RING_ARITY 1
+#endif
+// experiments: 0 evaluates every node of the register layouts as a three-parent one (branch-free: the
+// loads of all of a thread's nodes can fly together, at the price of unused rows and table words)
+constexpr bool kRingArity = SCB_RING_ARITY != 0;
 constexpr int kMaskPad = 15;  // all-zero truth tables after the last node
 constexpr int kRing = 4;  // state copies per slot: ring of the fast path, P/Q pairs of the slow path
 
-// Value of one canonical node (NodeOffsets / LutMasks entry) for the two slots a thread of the
+// Truth table of a canonical node as the sweep kernels evaluate it.  The table words of the mux tree
+// are all-ones or all-zeros and warp-uniform, so the FIRST mux level -- "x ? m1 : m0" on such words --
+// is one of 0, ~0, x, ~x, i.e. the affine map x * S + O with S = (m1 & 1) - (m0 & 1) and O = m0: an
+// IMAD on the FMA pipe instead of a LOP3 on the ALU pipe, which the ring compares and freeze merges
+// already keep busy.  Only the deeper levels mix two non-constant words and need LOP3.
+//   arity <= 1: t[0], t[1]       = S, O of (m4, m0)                        f = a * S + O
+//   arity == 2: t[0..3]          = S, O of (m2, m0) and (m6, m4)           f = a ? (b*S1+O1) : (b*S0+O0)
+//   arity == 3: t[2k], t[2k + 1] = S, O of (m[2k+1], m[2k]), k = 0..3      g_k = c*S_k+O_k, then two mux levels
+__device__ __forceinline__ uint32_t affine(uint32_t x, uint32_t s, uint32_t o) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(s), "r"(o));
+    return r;
+}
+__device__ __forceinline__ LutMasks affine_table(uint32_t lut, int arity) {
+    const LutMasks m = expand_lut(lut);
+    LutMasks t;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t.m[k] = 0u;
+    auto put = [&](int at, uint32_t m1, uint32_t m0) {
+        t.m[at] = (m1 & 1u) - (m0 & 1u);
+        t.m[at + 1] = m0;
+    };
+    if (arity <= 1) {
+        put(0, m.m[4], m.m[0]);
+    } else if (arity == 2) {
+        put(0, m.m[2], m.m[0]);
+        put(2, m.m[6], m.m[4]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) put(2 * k, m.m[2 * k + 1], m.m[2 * k]);
+    }
+    return t;
+}
+
+// Value of one canonical node (NodeOffsets / affine_table entry) for the two slots a thread of the
 // register layouts owns: `srd` points at (node 0, copy, slot lane), the second slot is 32 words on.
 // The node index is warp-uniform, so is the branch on its arity: one- and two-parent nodes read 2 / 4
-// rows and 2 / 4 table words and take 1 / 3 LOP3 per slot instead of 7.
+// rows and 2 / 4 table words.
 __device__ __forceinline__ void eval_pair(const NodeOffsets& o, const LutMasks& mk, const uint32_t* __restrict__ srd,
                                           uint32_t& f0, uint32_t& f1) {
     if (kRingArity && o.arity <= 1) {
-        const uint32_t m0 = mk.m[0], m4 = mk.m[4];
-        f0 = lop3<0xCA>(srd[o.pa], m4, m0);
-        f1 = lop3<0xCA>(srd[o.pa + 32], m4, m0);
+        const uint32_t s = mk.m[0], c = mk.m[1];
+        f0 = affine(srd[o.pa], s, c);
+        f1 = affine(srd[o.pa + 32], s, c);
         return;
     }
     const uint4 lo = *reinterpret_cast<const uint4*>(&mk.m[0]);
-    const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
     const uint32_t a0 = srd[o.pa], b0 = srd[o.pb];
     const uint32_t a1 = srd[o.pa + 32], b1 = srd[o.pb + 32];
     if (kRingArity && o.arity == 2) {
-        f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, hi.z, hi.x), lop3<0xCA>(b0, lo.z, lo.x));
-        f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, hi.z, hi.x), lop3<0xCA>(b1, lo.z, lo.x));
+        f0 = lop3<0xCA>(a0, affine(b0, lo.z, lo.w), affine(b0, lo.x, lo.y));
+        f1 = lop3<0xCA>(a1, affine(b1, lo.z, lo.w), affine(b1, lo.x, lo.y));
         return;
     }
+    const uint4 hi = *reinterpret_cast<const uint4*>(&mk.m[4]);
     const uint32_t c0 = srd[o.pc], c1 = srd[o.pc + 32];
-    f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, lop3<0xCA>(c0, hi.w, hi.z), lop3<0xCA>(c0, hi.y, hi.x)),
-                    lop3<0xCA>(b0, lop3<0xCA>(c0, lo.w, lo.z), lop3<0xCA>(c0, lo.y, lo.x)));
-    f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, lop3<0xCA>(c1, hi.w, hi.z), lop3<0xCA>(c1, hi.y, hi.x)),
-                    lop3<0xCA>(b1, lop3<0xCA>(c1, lo.w, lo.z), lop3<0xCA>(c1, lo.y, lo.x)));
+    f0 = lop3<0xCA>(a0, lop3<0xCA>(b0, affine(c0, hi.z, hi.w), affine(c0, hi.x, hi.y)),
+                    lop3<0xCA>(b0, affine(c0, lo.z, lo.w), affine(c0, lo.x, lo.y)));
+    f1 = lop3<0xCA>(a1, lop3<0xCA>(b1, affine(c1, hi.z, hi.w), affine(c1, hi.x, hi.y)),
+                    lop3<0xCA>(b1, affine(c1, lo.z, lo.w), affine(c1, lo.x, lo.y)));
 }
 
 // Ring-of-2 fast path with the ring in REGISTERS (KO/KI and recheck passes, 64-slot CTAs of 16 warps,
@@ -329,7 +439,8 @@ __device__ __forceinline__ uint32_t shared_addr(const void* p) {
 template <int CH>
 __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, const NodeOffsets* __restrict__ offs,
                                                const LutMasks* __restrict__ masks, uint32_t* __restrict__ votes,
-                                               int N, int forced_node, uint32_t cellmask, int t_fast, int tid) {
+                                               int N, int forced_node, uint32_t cellmask, int t_fast, int tid,
+                                               int stop_open, int stop_stall) {
     constexpr int SL = 64, STRIDE = 4 * SL, SET = 2 * SL;
     const int lane = tid & 31;
     const int n0 = (tid >> 5) * CH;
@@ -348,11 +459,15 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
     __syncthreads();
     uint32_t frozen0 = ~cellmask, frozen1 = ~cellmask;
     uint32_t lam0_0 = 0, lam1_0 = 0, lam0_1 = 0, lam1_1 = 0;
-    bool all_prev = false;
     int vset = 0;  // t % 3
+    // every warp holds the frozen masks of all 64 slots, so "how many lanes are still open" is one warp
+    // reduction and the same number everywhere: the CTA leaves the loop without another barrier
+    unsigned int last_open = 0xFFFFFFFFu;
+    int stall = 0;
+    bool moved = false;
 
     // one step: reads copy RD, writes copy WR; cur* hold state_{t-1} of the own nodes, prv* state_{t-2}
-    // and receive state_t.  Returns true when the CTA is done.
+    // and receive state_t.  Returns true when the CTA is done (copy WR holds the result).
     auto step = [&](auto rd_tag, uint32_t (&cur0)[CH], uint32_t (&prv0)[CH], uint32_t (&cur1)[CH],
                     uint32_t (&prv1)[CH], int t) -> bool {
         constexpr int RD = decltype(rd_tag)::value ? 3 : 0, WR = decltype(rd_tag)::value ? 0 : 3;
@@ -392,7 +507,7 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
         if (q11) atomicOr(v + 32 + lane, q11);
         if (q20) atomicOr(v + SL + lane, q20);
         if (q21) atomicOr(v + SL + 32 + lane, q21);
-        if (__syncthreads_and(all_prev)) return true;  // nothing moved in this step: copy RD holds the result
+        __syncthreads();
         // state_{t-d} exists for t >= d only (the raw data state is never compared)
         uint32_t open = ~frozen0;
         uint32_t e1 = t >= 1 ? ~v[lane] & open : 0u;
@@ -408,22 +523,32 @@ __device__ __forceinline__ int ring2_registers(uint32_t* __restrict__ state, con
         lam0_1 |= e1;
         lam1_1 |= e2;
         frozen1 |= e1 | e2;
+        // A step costs the same whether one lane of the CTA is open or all 2048: stop when few are left
+        // (they are re-simulated, compacted, by the next pass), or when lanes had started to settle and
+        // none did for a while (what is left then are cycles this ring cannot see).
+        const unsigned int n_open = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)(__popc(~frozen0) + __popc(~frozen1)));
+        if (n_open <= (unsigned int)stop_open) return true;
+        if (n_open < last_open) {
+            moved = last_open != 0xFFFFFFFFu;
+            last_open = n_open;
+            stall = 0;
+        } else if (moved && ++stall >= stop_stall) {
+            return true;
+        }
         const int vclear = vset == 0 ? 2 : vset - 1;  // (t + 2) % 3
         if (tid < SET) votes[vclear * SET + tid] = 0;
         vset = vset == 2 ? 0 : vset + 1;
-        all_prev = (frozen0 & frozen1) == 0xFFFFFFFFu;
         return false;
     };
     using Odd = std::integral_constant<bool, true>;    // reads copy 3
     using Even = std::integral_constant<bool, false>;  // reads copy 0
     int result_copy = 3;
     for (int t = 0; t < t_fast; t += 2) {
-        result_copy = 3;
-        if (step(Odd{}, xa0, xb0, xa1, xb1, t)) break;  // xa = state_{t-1}, xb <- state_t, written to copy 0
         result_copy = 0;
+        if (step(Odd{}, xa0, xb0, xa1, xb1, t)) break;  // xa = state_{t-1}, xb <- state_t, written to copy 0
         if (t + 1 >= t_fast) break;
-        if (step(Even{}, xb0, xa0, xb1, xa1, t + 1)) break;  // xb = state_t, xa <- state_{t+1}, written to copy 3
         result_copy = 3;
+        if (step(Even{}, xb0, xa0, xb1, xa1, t + 1)) break;  // xb = state_t, xa <- state_{t+1}, written to copy 3
     }
     __syncthreads();  // every vote word has been read
     if (tid < 32) {
@@ -747,7 +872,7 @@ sweep_kernel(const SweepArgs args) {
     constexpr int BATCH_CELLS = HALF * 32;  // cells of one node a cleanup batch simulates
 
     if (tid < kMaskPad) {  // all-zero entries past the end (ring2_registers)
-        masks[N + tid] = expand_lut(0u);
+        masks[N + tid] = affine_table(0u, 0);
         NodeOffsets z;
         z.pa = z.pb = z.pc = z.arity = 0;
         offs[N + tid] = z;
@@ -756,9 +881,10 @@ sweep_kernel(const SweepArgs args) {
         int arity;
         NodeEntry e = make_entry(args.net_parent, args.net_lut, n, &arity);
         NodeOffsets o;
+        if (!kRingArity) arity = 3;  // (the canonical table does not depend on the unbound slots, which alias row 0)
         o.pa = e.pa * NODE_STRIDE; o.pb = e.pb * NODE_STRIDE; o.pc = e.pc * NODE_STRIDE; o.arity = arity;
         offs[n] = o;
-        masks[n] = expand_lut(e.lut);
+        masks[n] = affine_table(e.lut, arity);
     }
     int total_batches = 0;
     if (IS_GATHER) {
@@ -898,13 +1024,22 @@ sweep_kernel(const SweepArgs args) {
         // next value of node n for my slot, reading state copy k
         auto step_node = [&](int k, int n) {
             const NodeOffsets o = offs[n];
-            const uint4 lo = *reinterpret_cast<const uint4*>(&masks[n].m[0]);
-            const uint4 hi = *reinterpret_cast<const uint4*>(&masks[n].m[4]);
             const uint32_t* st = state + k * SLOTS + slot;
-            const uint32_t a = st[o.pa], b = st[o.pb], c = st[o.pc];
-            uint32_t g0 = lop3<0xCA>(c, lo.y, lo.x), g1 = lop3<0xCA>(c, lo.w, lo.z);
-            uint32_t g2 = lop3<0xCA>(c, hi.y, hi.x), g3 = lop3<0xCA>(c, hi.w, hi.z);
-            uint32_t f = lop3<0xCA>(a, lop3<0xCA>(b, g3, g2), lop3<0xCA>(b, g1, g0));
+            uint32_t f;
+            if (o.arity <= 1) {
+                f = affine(st[o.pa], masks[n].m[0], masks[n].m[1]);
+            } else {
+                const uint4 lo = *reinterpret_cast<const uint4*>(&masks[n].m[0]);
+                const uint32_t a = st[o.pa], b = st[o.pb];
+                if (o.arity == 2) {
+                    f = lop3<0xCA>(a, affine(b, lo.z, lo.w), affine(b, lo.x, lo.y));
+                } else {
+                    const uint4 hi = *reinterpret_cast<const uint4*>(&masks[n].m[4]);
+                    const uint32_t c = st[o.pc];
+                    f = lop3<0xCA>(a, lop3<0xCA>(b, affine(c, hi.z, hi.w), affine(c, hi.x, hi.y)),
+                                   lop3<0xCA>(b, affine(c, lo.z, lo.w), affine(c, lo.x, lo.y)));
+                }
+            }
             if (MODE != MODE_NORMAL && n == forced_node) f = forced_value;
             return f;
         };
@@ -929,6 +1064,7 @@ sweep_kernel(const SweepArgs args) {
             __syncthreads();
             SCB_SWEEP_PHASE(1);
             uint32_t frozen = ~cellmask;
+            uint32_t key[6] = {0u, 0u, 0u, 0u, 0u, 0u};  // probe: settle step of every lane, bit-sliced
             const int t_fast = MODE != MODE_KOKI      ? steps
                                : args.fast_steps > 0 ? min(steps, args.fast_steps)
                                                      : min(steps, (int)args.counters[3]);
@@ -937,9 +1073,11 @@ sweep_kernel(const SweepArgs args) {
             constexpr int CH_L = (208 + kWarps - 1) / kWarps, CH_M = (128 + kWarps - 1) / kWarps, CH_S = (64 + kWarps - 1) / kWarps;
             const bool reg_ring = DEFERS && SLOTS == 64 && kWarps >= 16 && !deep && N <= kWarps * CH_L && kRegRing;
             if (reg_ring) {
-                xs = N <= kWarps * CH_S   ? ring2_registers<CH_S>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid)
-                     : N <= kWarps * CH_M ? ring2_registers<CH_M>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid)
-                                          : ring2_registers<CH_L>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid);
+                // the recheck pass is the last ring pass: it only stops early when nothing is left
+                const int so = MODE == MODE_KOKI ? args.stop_open : 0, ss = MODE == MODE_KOKI ? args.stop_stall : (1 << 30);
+                xs = N <= kWarps * CH_S   ? ring2_registers<CH_S>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid, so, ss)
+                     : N <= kWarps * CH_M ? ring2_registers<CH_M>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid, so, ss)
+                                          : ring2_registers<CH_L>(state, offs, masks, votes, N, forced_node, cellmask, t_fast, tid, so, ss);
                 frozen = votes[slot];
                 lam[0] = votes[64 + slot];
                 lam[1] = votes[128 + slot];
@@ -994,7 +1132,17 @@ sweep_kernel(const SweepArgs args) {
                 if (MODE == MODE_NORMAL && part == 0) {  // settle-time histogram (choose_fast_steps_kernel)
                     // only periods <= 2 count as settled: that is what the KO/KI pass's short ring can see
                     const unsigned int c = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)__popc(e1 | e2));
-                    if ((tid & 31) == 0 && c) atomicAdd(&args.settle_hist[t], c);
+                    if (args.probe) {
+                        // sort key: the settle step for periods 1 and 2 (at most 61), 62 for periods 3 and 4
+                        const int kt = min(t, 61);
+                        const unsigned int c34 = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)__popc(e3 | e4));
+#pragma unroll
+                        for (int b = 0; b < 6; ++b) key[b] |= (((kt >> b) & 1) ? (e1 | e2) : 0u) | (((62 >> b) & 1) ? (e3 | e4) : 0u);
+                        if ((tid & 31) == 0 && c) atomicAdd(&args.key_hist[kt], c);
+                        if ((tid & 31) == 0 && c34) atomicAdd(&args.key_hist[62], c34);
+                    } else if ((tid & 31) == 0 && c) {
+                        atomicAdd(&args.settle_hist[t], c);
+                    }
                 }
                 // the other accumulator set is idle between the two barriers: clear it for step t+1
                 if (part < kRing) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
@@ -1004,6 +1152,18 @@ sweep_kernel(const SweepArgs args) {
             xn = (xs + 1) & 3;
             found = frozen & cellmask;
             unresolved = ~frozen;
+            if (MODE == MODE_NORMAL && args.probe) {
+                // key 63: the ring settled nothing (long cycle or no repeat); such cells end up last
+                if (part == 0) {
+                    const unsigned int c = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)__popc(unresolved & cellmask));
+                    if ((tid & 31) == 0 && c) atomicAdd(&args.key_hist[63], c);
+                    if (word_ok) {
+#pragma unroll
+                        for (int b = 0; b < 6; ++b) args.key_planes[(size_t)b * wpad + word] = key[b] | (unresolved & cellmask);
+                    }
+                }
+                return;
+            }
             if (MODE == MODE_NORMAL && part == 0 && word_ok) args.np_hard[word] = unresolved & cellmask;
             SCB_SWEEP_PHASE(2);
         }
@@ -1424,38 +1584,61 @@ struct SweepLists {
 };
 
 template <int SLOTS>
-static int launch_sweep(SweepArgs args, const SweepLists& lists, cudaStream_t stream) {
+static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* planes_sorted, unsigned int* bucket_fill,
+                        bool sort_cells, cudaStream_t stream) {
     size_t smem = sweep_smem_bytes(args.n_nodes, SLOTS);
     int64_t n_words = (args.n_cells + 31) / 32;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_KOKI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_RECHECK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SCB_CUDA(cudaFuncSetAttribute(sweep_kernel<SLOTS, MODE_CLEANUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    {
+        const void* kernels[4] = {(const void*)sweep_kernel<SLOTS, MODE_NORMAL>, (const void*)sweep_kernel<SLOTS, MODE_KOKI>,
+                                  (const void*)sweep_kernel<SLOTS, MODE_RECHECK>, (const void*)sweep_kernel<SLOTS, MODE_CLEANUP>};
+        static thread_local SmemMarks marks[4];
+        for (int k = 0; k < 4; ++k)
+            if (int rc = ensure_dynamic_smem(kernels[k], smem, marks[k])) return rc;
     }
-    // settle_hist | count_a | count_b | counters are contiguous
-    SCB_CUDA(cudaMemsetAsync(args.settle_hist, 0, 64 * 4 + (size_t)args.n_nodes * 8 + 16, stream));
+    // settle_hist | key_hist | bucket_fill | count_a | count_b | counters are contiguous
+    SCB_CUDA(cudaMemsetAsync(args.settle_hist, 0, 3 * 64 * 4 + (size_t)args.n_nodes * 8 + 16, stream));
     args.in_cells = nullptr;
     args.in_cap = 0;
     args.in_count = nullptr;
     args.out_cells = nullptr;
     args.out_cap = 0;
     args.out_count = nullptr;
+    args.probe = 0;
     dim3 grid_n((unsigned)((n_words + SLOTS - 1) / SLOTS));
+    const int n_blocks_j = (args.n_nodes + 31) / 32;
+    dim3 grid_t((unsigned)((args.wpad + 31) / 32), (unsigned)n_blocks_j, 1);
+    if (sort_cells) {
+        // Cells sorted by the settle step of their unperturbed run.  A perturbed run of a cell settles at
+        // about the same step as its unperturbed one, and a KO/KI CTA steps until (nearly) all of its 1024
+        // cells have settled: with similar cells side by side every CTA stops at its own cells' pace instead
+        // of the slowest cell's of the whole data set.  Every output is a sum over cells, so the order is
+        // free.  probe (key per cell) -> counting sort of the cell-major records -> back to bitplanes.
+        uint32_t* rec0 = args.np_states_t;  // records in the caller's order; dead before np_states_t is written
+        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes, args.n_nodes, args.wpad, rec0, args.nwp, nullptr);
+        SCB_LAUNCH_CHECK("cell_major_kernel<data>");
+        args.probe = 1;
+        sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(args);
+        SCB_LAUNCH_CHECK("sweep_kernel<probe>");
+        args.probe = 0;
+        sort_scatter_kernel<<<(unsigned)((args.n_cells + 255) / 256), 256, 0, stream>>>(
+            args.key_planes, args.wpad, args.n_cells, args.key_hist, bucket_fill, rec0, args.planes_t, args.nwp);
+        SCB_LAUNCH_CHECK("sort_scatter_kernel");
+        node_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes_t, args.nwp, args.n_nodes, args.wpad, args.n_cells, planes_sorted);
+        SCB_LAUNCH_CHECK("node_major_kernel");
+        args.planes = planes_sorted;
+    }
     sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(args);
     SCB_LAUNCH_CHECK("sweep_kernel<normal>");
     if (args.fast_steps <= 0) {
-        choose_fast_steps_kernel<<<1, 32, 0, stream>>>(args.settle_hist, args.steps, args.n_cells, args.counters);
+        choose_fast_steps_kernel<<<1, 32, 0, stream>>>(args.settle_hist, args.steps, args.n_cells, args.counters, sort_cells ? 1 : 0);
         SCB_LAUNCH_CHECK("choose_fast_steps_kernel");
     }
     // cell-major copies of the data and of the normal-run states for the compacted passes
     {
-        const int n_blocks_j = (args.n_nodes + 31) / 32;
-        dim3 grid_t((unsigned)((args.wpad + 31) / 32), (unsigned)n_blocks_j, 1);
-        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes, args.n_nodes, args.wpad, args.planes_t, args.nwp, nullptr);
-        SCB_LAUNCH_CHECK("cell_major_kernel<data>");
+        if (!sort_cells) {  // (sorted: planes_t is what the sort made)
+            cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes, args.n_nodes, args.wpad, args.planes_t, args.nwp, nullptr);
+            SCB_LAUNCH_CHECK("cell_major_kernel<data>");
+        }
         grid_t.y = 1;   // np_lam[6][wpad] and np_found[wpad] are contiguous: a 7-row matrix, one word per cell
         cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.np_lam, kLamPlanes + 1, args.wpad, args.np_info_t, 1, nullptr);
         SCB_LAUNCH_CHECK("cell_major_kernel<normal info>");
@@ -1531,10 +1714,12 @@ extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int 
     if (n_nodes <= 0 || wpad <= 0 || steps <= 0) return 0;
     // normal-run states + lambda planes + found plane + the two per-node lists of deferred cells +
     // their fill counts + counters
+    // ... + the bitplanes in sorted cell order and the 6 key planes of the sort
     return ((int64_t)steps * n_nodes + kLamPlanes + 2) * wpad * 4 +
            (int64_t)(steps + 1) * wpad * 32 * record_words(n_nodes) * 4 + wpad * 32 * 4 +
            (int64_t)n_nodes * (sweep_list_capacity(wpad * 32, kListDivA) + sweep_list_capacity(wpad * 32, kListDivB)) * 4 +
-           64 * 4 + (int64_t)n_nodes * 8 + 16;
+           ((int64_t)n_nodes + 6) * wpad * 4 +
+           3 * 64 * 4 + (int64_t)n_nodes * 8 + 16;
 }
 
 extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
@@ -1574,8 +1759,12 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.np_info_t = args.np_states_t + (size_t)steps * wpad * 32 * args.nwp;
     lists.cells_a = reinterpret_cast<int32_t*>(args.np_info_t + (size_t)wpad * 32);
     lists.cells_b = lists.cells_a + (size_t)n_nodes * lists.cap_a;
-    args.settle_hist = reinterpret_cast<unsigned int*>(lists.cells_b + (size_t)n_nodes * lists.cap_b);
-    lists.count_a = args.settle_hist + 64;
+    uint32_t* planes_sorted = reinterpret_cast<uint32_t*>(lists.cells_b + (size_t)n_nodes * lists.cap_b);
+    args.key_planes = planes_sorted + (size_t)n_nodes * wpad;
+    args.settle_hist = reinterpret_cast<unsigned int*>(args.key_planes + (size_t)6 * wpad);
+    args.key_hist = args.settle_hist + 64;
+    unsigned int* bucket_fill = args.key_hist + 64;
+    lists.count_a = bucket_fill + 64;
     lists.count_b = lists.count_a + n_nodes;
     args.counters = lists.count_b + n_nodes;  // followed by 16 spare bytes
     // Default: the KO/KI pass runs the ring on the plane words for a number of steps chosen on the
@@ -1586,13 +1775,26 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.fast_steps = 0;
     if (const char* e = getenv("SCB_SWEEP_FAST_STEPS")) args.fast_steps = atoi(e) > 0 ? atoi(e) : 0;
     if (args.fast_steps > steps) args.fast_steps = steps;
+    // SCB_SWEEP_SORT=0 keeps the caller's cell order (experiments, tests of both paths)
+    bool sort_cells = true;
+    if (const char* e = getenv("SCB_SWEEP_SORT")) sort_cells = e[0] != '0';
+    args.stop_open = 24;
+    args.stop_stall = 4;
+    if (const char* e = getenv("SCB_SWEEP_STOP_OPEN")) args.stop_open = atoi(e) >= 0 ? atoi(e) : 0;
+    if (const char* e = getenv("SCB_SWEEP_STOP_STALL")) args.stop_stall = atoi(e) > 0 ? atoi(e) : (1 << 30);
+    if (!sort_cells && !getenv("SCB_SWEEP_STOP_OPEN")) {  // unsorted: the global step cap does the stopping
+        args.stop_open = 0;
+        args.stop_stall = 1 << 30;
+    }
     args.out_raw = reinterpret_cast<unsigned long long*>(out_raw);
     args.out_missing = reinterpret_cast<unsigned long long*>(out_missing);
     args.out_keyerror = reinterpret_cast<unsigned long long*>(out_keyerror);
     const char* force = getenv("SCB_SWEEP_SLOTS");  // experiments
     const bool prefer32 = force && force[0] == '3';
-    if (!prefer32 && sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem) return launch_sweep<64>(args, lists, as_stream(stream));
-    if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem) return launch_sweep<32>(args, lists, as_stream(stream));
+    if (!prefer32 && sweep_smem_bytes(n_nodes, 64) <= kMaxDynSmem)
+        return launch_sweep<64>(args, lists, planes_sorted, bucket_fill, sort_cells, as_stream(stream));
+    if (sweep_smem_bytes(n_nodes, 32) <= kMaxDynSmem)
+        return launch_sweep<32>(args, lists, planes_sorted, bucket_fill, sort_cells, as_stream(stream));
     set_error("ko_ki_sweep: %d nodes exceed the shared-memory resident limit (%d)", n_nodes, SCB_MAX_SWEEP_NODES);
     return SCB_ERR_UNSUPPORTED;
 }
