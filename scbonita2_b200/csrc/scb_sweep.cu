@@ -150,6 +150,7 @@ struct SweepArgs {
     // KO/KI register ring: a CTA stops stepping when at most `stop_open` of its lanes are still open, or when
     // lanes have started to settle and none did for `stop_stall` steps; open lanes go to the next pass
     int stop_open, stop_stall;
+    int ring_stall;                 // the same stall rule in the shared-memory ring of the KO/KI and recheck passes
     unsigned long long* out_raw;
     unsigned long long* out_missing;
     unsigned long long* out_keyerror;
@@ -856,6 +857,7 @@ sweep_kernel(const SweepArgs args) {
     uint32_t* nrm = reinterpret_cast<uint32_t*>(cellidx + HALF * 32);  // [1 + kLamPlanes][HALF]
     int* pre = reinterpret_cast<int*>(nrm + (1 + kLamPlanes) * HALF);  // [N + 1]
     __shared__ int s_node;
+    __shared__ unsigned int s_open[2];  // DEFERS modes, shared-memory ring: lanes still open after step t (parity t & 1)
 
     constexpr bool IS_GATHER = MODE == MODE_CLEANUP || MODE == MODE_RECHECK;
     constexpr bool DEFERS = MODE == MODE_KOKI || MODE == MODE_RECHECK;
@@ -1065,6 +1067,12 @@ sweep_kernel(const SweepArgs args) {
             SCB_SWEEP_PHASE(1);
             uint32_t frozen = ~cellmask;
             uint32_t key[6] = {0u, 0u, 0u, 0u, 0u, 0u};  // probe: settle step of every lane, bit-sliced
+            // shared-memory ring of a pass that can hand lanes on: stop once lanes had started to settle and
+            // none did for a while (what is left are cycles the ring cannot see, or nothing at all)
+            unsigned int last_open = 0xFFFFFFFFu;
+            int stall = 0;
+            bool moved = false;
+            if (DEFERS && tid < 2) s_open[tid] = 0u;  // (ordered before the first add by the barrier after load_data)
             const int t_fast = MODE != MODE_KOKI      ? steps
                                : args.fast_steps > 0 ? min(steps, args.fast_steps)
                                                      : min(steps, (int)args.counters[3]);
@@ -1147,7 +1155,24 @@ sweep_kernel(const SweepArgs args) {
                 // the other accumulator set is idle between the two barriers: clear it for step t+1
                 if (part < kRing) votes[((t + 1) & 1) * kRing * SLOTS + part * SLOTS + slot] = 0;
                 xs = kd;
+                if (DEFERS) {
+                    if (part == 0) {
+                        const unsigned int c = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)__popc(~frozen));
+                        if ((tid & 31) == 0 && c) atomicAdd(&s_open[t & 1], c);
+                    }
+                    if (tid == 0) s_open[(t + 1) & 1] = 0u;  // last read after the previous step's closing barrier
+                }
                 if (__syncthreads_and(frozen == 0xFFFFFFFFu)) break;
+                if (DEFERS) {
+                    const unsigned int n_open = s_open[t & 1];  // the same number in every thread
+                    if (n_open < last_open) {
+                        moved = last_open != 0xFFFFFFFFu;
+                        last_open = n_open;
+                        stall = 0;
+                    } else if (moved && ++stall >= args.ring_stall) {
+                        break;
+                    }
+                }
             }
             xn = (xs + 1) & 3;
             found = frozen & cellmask;
@@ -1782,6 +1807,8 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.stop_stall = 4;
     if (const char* e = getenv("SCB_SWEEP_STOP_OPEN")) args.stop_open = atoi(e) >= 0 ? atoi(e) : 0;
     if (const char* e = getenv("SCB_SWEEP_STOP_STALL")) args.stop_stall = atoi(e) > 0 ? atoi(e) : (1 << 30);
+    args.ring_stall = 6;
+    if (const char* e = getenv("SCB_SWEEP_RING_STALL")) args.ring_stall = atoi(e) > 0 ? atoi(e) : (1 << 30);
     if (!sort_cells && !getenv("SCB_SWEEP_STOP_OPEN")) {  // unsorted: the global step cap does the stopping
         args.stop_open = 0;
         args.stop_stall = 1 << 30;

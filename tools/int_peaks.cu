@@ -11,7 +11,7 @@
 #include <stdio.h>
 
 #define ILP 8
-#define ITERS 4096
+#define ITERS 32768
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
