@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--sweep-steps", type=int, default=2, help="timed sweep repetitions (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="GA step = scb_rule_counts_run + scb_population_fitness (round-1 kernels)")
     ap.add_argument("--no-e2e-dense", action="store_true", help="skip the dense-uint8 variant of the end-to-end step")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling block (same 1M cells split over the ranks)")
     ap.add_argument("--cpu-leg", default="", choices=["", "fitness", "sweep"], help=argparse.SUPPRESS)
@@ -500,9 +501,14 @@ def run_ours(args):
         rot = [planes] + [device.BitPlanes(planes.words.clone(), planes.n_rows, planes.n_cells)
                           for _ in range(n_rot - 1)]
 
+        fused = plan.fused_supported and not args.unfused and (world == 1 or exchange is not None)
+
         def fitness_step(k=0):
             # two kernel launches (+ one NCCL all-reduce in the --nccl variant); nothing else is enqueued
-            counts = plan.run(rot[k % n_rot], exchange=exchange)   # sharded: the last CTA pushes to the peers
+            if fused:   # sums kernel (sharded: its last CTA pushes to the peers) + fitness kernel that inverts them
+                plan.fitness_step(rot[k % n_rot], d_lut, out=d_diff, exchange=exchange, chained=True)
+                return d_diff
+            counts = plan.run(rot[k % n_rot], exchange=exchange, chained=True)
             if exchange is not None:
                 exchange.population_fitness(d_lut, out=d_diff)
                 return d_diff
@@ -511,12 +517,20 @@ def run_ours(args):
             device.population_fitness(counts, d_lut, out=d_diff)
             return d_diff
 
+        def counts_only(k):
+            # the dominant kernel alone (its consumer is missing: the sums just pile up, the timing is the same)
+            if fused:
+                plan.sums_run(rot[k % n_rot], chained=True)
+            else:
+                plan.run(rot[k % n_rot], chained=True)
+
         for k in range(max(args.warmup, 3)):
             fitness_step(k)
         barrier()
         if exchange is not None:
             # the peer-memory sum against ncclAllReduce of the same counts, once
             exchange.check()
+            torch.cuda.synchronize()
             summed = plan.run(rot[0]).clone()
             dist.all_reduce(summed)
             want, _ = device.population_fitness(summed, d_lut)
@@ -529,7 +543,8 @@ def run_ours(args):
             try:
                 graph = capture(lambda: [fitness_step(k) for k in range(args.steps)])
                 # the dominant kernel alone, K launches, for the roofline line
-                counts_graph = capture(lambda: [plan.run(rot[k % n_rot]) for k in range(args.steps)])
+                counts_graph = capture(lambda: [counts_only(k) for k in range(args.steps)])
+                plan.scratch.zero_()
             except Exception as exc:  # capture is an optimisation, never a requirement
                 print(f"[bench] CUDA graph capture unavailable ({exc}); timing eager launches", file=sys.stderr)
                 graph = counts_graph = None
@@ -539,7 +554,8 @@ def run_ours(args):
         if counts_graph is not None:
             k_ms = timed_region(counts_graph.replay) / args.steps
         else:
-            k_ms = timed_region(lambda: [plan.run(rot[k % n_rot]) for k in range(args.steps)]) / args.steps
+            k_ms = timed_region(lambda: [counts_only(k) for k in range(args.steps)]) / args.steps
+        plan.scratch.zero_()   # (the sums kernel timed alone leaves its sums behind)
         # one step on its own (L2 flushed, its own event pair): includes the launch latency that the
         # back-to-back region hides
         iso = []
@@ -556,7 +572,8 @@ def run_ours(args):
         out = {"ms_per_step": max_over_ranks(float(total_ms)) / args.steps, "eager_ms": eager_total / args.steps,
                "counts_kernel_ms": k_ms, "isolated_ms": float(np.median([a.elapsed_time(b) for a, b in iso])),
                "wall": time.perf_counter() - wall0, "checksum": int(d_diff.sum().item()), "n_rot": n_rot,
-               "plane_bytes": plane_bytes, "graph": graph is not None, "planes": planes}
+               "plane_bytes": plane_bytes, "graph": graph is not None, "planes": planes,
+               "kernel": "rule_sums_kernel" if fused else "rule_counts_kernel"}
         del rot[1:]
         return out
 
@@ -696,7 +713,7 @@ def run_ours(args):
     traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(traffic_path) and args.nodes == 200 and args.cells == 1_000_000:
         traffic = json.load(open(traffic_path))["rule_counts_kernel"]["dram_bytes"]   # ncu --set full capture
-    roofline_hbm = {"kernel": "rule_counts_kernel", "bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9,
+    roofline_hbm = {"kernel": ga["kernel"], "bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                     "traffic": traffic, "peak_source": hbm_src, "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes}
     alu_ops, xu_ops, n_terms = counts_required_ops(parents, args.nodes, n_words)
@@ -705,7 +722,7 @@ def run_ours(args):
     t_xu = xu_ops / (pipes["popc"] * 1e9)
     binding = max((t_hbm, "hbm"), (t_alu, "alu"), (t_xu, "xu"))
     pipe_name, pipe_ops, pipe_peak = ("xu", xu_ops, pipes["popc"]) if t_xu >= t_alu else ("alu", alu_ops, pipes["lop3"])
-    roofline_pipe = {"kernel": "rule_counts_kernel", "bound": "int_pipe_" + pipe_name,
+    roofline_pipe = {"kernel": ga["kernel"], "bound": "int_pipe_" + pipe_name,
                      "achieved": pipe_ops / (k_ms * 1e-3) / 1e9, "peak": pipe_peak, "unit": "Glane-op/s",
                      "frac": pipe_ops / (k_ms * 1e-3) / 1e9 / pipe_peak, "traffic": None, "peak_source": pipe_src,
                      "kernel_ms": k_ms, "required_alu_lane_ops": alu_ops, "required_xu_lane_ops": xu_ops,

@@ -92,6 +92,11 @@ int scb_rule_counts(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_
  * scratch once (or reuses it after a successful call, in stream order) passes
  * SCB_COUNTS_SCRATCH_CLEAN and the call enqueues no memset. */
 #define SCB_COUNTS_SCRATCH_CLEAN 1
+/* SCB_COUNTS_CHAINED: the caller vouches that the kernel BEFORE this call in the stream wrote neither
+ * the bitplanes nor the plan (e.g. it is the consumer of the previous pass): the counting kernel is
+ * then launched as a programmatic dependent and its main loop overlaps that kernel's tail.  Without
+ * the flag the launch is fully serialised. */
+#define SCB_COUNTS_CHAINED 2
 int scb_rule_counts_ex(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
                        int n_groups, const int32_t* target_row /*[G]*/,
                        const int32_t* parent_row /*[G][3]*/, void* scratch, int64_t scratch_bytes,
@@ -109,6 +114,27 @@ int scb_rule_counts_plan_build(int n_rows, int n_groups, const int32_t* target_r
 int scb_rule_counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
                         int n_groups, const void* plan, void* scratch, int64_t scratch_bytes,
                         int64_t* out_counts /*[G][16]*/, int flags, scb_stream_t stream);
+
+/* The GA-step pair (one pass over the cells + the fitness of a whole population, nothing else on
+ * the critical path).  scb_rule_sums_run leaves the SUBSET SUMS of the groups (popcounts of the AND
+ * of every subset of {A, B, C, target}) in `scratch` instead of inverting them into counts;
+ * scb_population_fitness_sums consumes them -- it inverts them while it builds its tables and leaves
+ * `scratch` zeroed -- so every scb_rule_sums_run must be followed, in stream order, by exactly one
+ * scb_population_fitness_sums on the same plan / scratch (same results as scb_rule_counts_run +
+ * scb_population_fitness).  scb_rule_sums_supported: one launch of the counting kernel and a fitness
+ * kernel whose tables plus a copy of the sums fit in shared memory (about 660 groups); larger sets take
+ * scb_rule_counts_run + scb_population_fitness.  n_untargeted_rows = rows that are no group's
+ * target (informational).  With peer_regions (sharded cells) the kernel's last CTA pushes the sums to every
+ * rank's exchange region and scb_population_fitness_sums(region != NULL) sums them over the ranks. */
+int scb_rule_sums_supported(int n_rows, int n_groups, int n_untargeted_rows);
+int scb_rule_sums_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells, int n_groups,
+                      int n_untargeted_rows, const void* plan, void* scratch, int64_t scratch_bytes, int flags,
+                      void* const* peer_regions /*[n_ranks] or NULL*/, int rank, int n_ranks, scb_stream_t stream);
+int scb_population_fitness_sums(const void* plan, void* scratch, int n_rows, int n_groups, int64_t n_cells,
+                                const void* local_region /*NULL: one GPU*/, int rank, int n_ranks,
+                                int64_t n_individuals, const uint8_t* lut /*[P][G]*/,
+                                const uint8_t* active /*[P][G] or NULL*/, int64_t* out_diff /*[P]*/,
+                                int64_t* out_diff_pg /*[P][G] or NULL*/, scb_stream_t stream);
 
 /* difference for T (group, lut) tasks: the batched calculate_error.  count == n_cells. */
 int scb_rule_error_table(const int64_t* counts /*[G][16]*/, int n_groups, int64_t n_tasks,
@@ -171,8 +197,12 @@ int scb_population_fitness_peers(const void* local_region, int rank, int n_ranks
                                  int64_t n_individuals, const uint8_t* lut /*[P][G]*/,
                                  const uint8_t* active /*[P][G]|NULL*/, int64_t* out_diff /*[P]*/,
                                  int64_t* out_diff_pg /*[P][G]|NULL*/, scb_stream_t stream);
-/* 1 if a kernel gave up waiting for a peer (2 s); synchronises the device */
+/* 1 if a kernel gave up waiting for a peer since the last call (the flag is cleared by the call);
+ * synchronises the device.  Such a kernel also writes INT64_MIN into every result of its launch, so a
+ * timed-out step can never pass for a valid one.  scb_peer_set_timeout: how long a kernel waits for a
+ * peer's word (milliseconds, 0 = the default of 30 s; SCB_PEER_TIMEOUT_MS sets the process default). */
 int scb_peer_error(const void* local_region, int* out_error /*HOST*/);
+int scb_peer_set_timeout(void* local_region, unsigned int timeout_ms);
 
 /* Multi-rule individuals of the historic GA: an individual is a 0/1 string over the concatenated
  * candidate lists of all nodes; out_diff[p] = sum of task_diff[j] over its set bits, out_nsel[p] =

@@ -248,6 +248,179 @@ def golden_rule_inference(ns, tag, n_genes, n_cells, seed, extra_rows=3):
         "ruleset": [[r[0][0], [int(i) for i in r[0][1]], r[0][2], int(r[1]), float(r[2])] for r in ri.ruleset]})
 
 
+def golden_rule_check(tag, n_genes, n_cells, seed):
+    """``network_simulation/check_rules_output.py`` (imported unmodified): get_rules + check_rules on a
+    planted network's rules (with every operator shape the planted rules use, upper- and lower-case
+    spellings, parentheses) and a noisy data set, for the full set of cells and two subsets."""
+    import importlib.util
+    import tempfile
+    spec = importlib.util.spec_from_file_location(
+        "ref_check_rules_output", "/root/reference/network_simulation/check_rules_output.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(seed)
+    specs, planes = synth.synthetic_dataset(n_genes, n_cells, seed, flip=0.1, relax_steps=3, p_inhibit=0.3)
+    dense = synth.planes_to_dense(planes, n_cells)
+    lines = []
+    for s in specs:
+        names = [f"Gene{p}" for p in s.predecessors] or [f"Gene{s.index}"]
+        text = s.logic
+        for slot, name in zip("ABC", names):
+            text = text.replace(slot, "{" + slot + "}")
+        text = text.format(**{slot: name for slot, name in zip("ABC", names)})
+        if rng.random() < 0.5:
+            text = text.replace(" and ", " AND ").replace(" or ", " OR ").replace("not ", "NOT ")
+        lines.append(f"Gene{s.index} = {text}")
+    rules_text = "\n".join(lines) + "\n"
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as fh:
+        fh.write(rules_text)
+        path = fh.name
+    ruleset, raw = mod.get_rules(path)
+    os.unlink(path)
+    subsets = [list(range(n_cells)), sorted(int(c) for c in rng.choice(n_cells, int(0.8 * n_cells), replace=False)),
+               [int(c) for c in rng.choice(n_cells, 7, replace=False)]]
+    results = []
+    for cells in subsets:
+        m, t, e, k = mod.check_rules(dense, ruleset, raw, cells)
+        results.append({"cells": cells, "mismatches": int(m), "total": int(t), "error_pct": float(e), "num_rules": int(k)})
+    singles = [[int(mod.check_logic(rule, dense[:, c])) for rule in ruleset] for c in range(min(n_cells, 16))]
+    dump(f"rulecheck_{tag}.json", {"n_genes": n_genes, "n_cells": n_cells, "rules_text": rules_text,
+                                   "tokens": ruleset, "matrix": rows_to_text(dense), "results": results,
+                                   "check_logic_first_cells": singles})
+
+
+def seeded_graph(names, rng, max_in=5, p_more=0.7, specs=None):
+    """A digraph over ``names`` (node order == name order) with up to ``max_in`` incoming edges per node,
+    ~10-20 % inhibitory, edge attribute spelled ``interaction`` or ``signal`` at random."""
+    import networkx as nx
+    graph = nx.DiGraph()
+    graph.add_nodes_from(names)
+    edges = []
+    n = len(names)
+    for i in range(n):
+        parents = set(specs[i].predecessors) if specs else set()
+        if not specs:
+            for _ in range(int(rng.integers(1, 4))):
+                cand = int(rng.integers(0, n))
+                if cand != i:
+                    parents.add(cand)
+        while len(parents) < min(max_in, n - 1) and rng.random() < p_more:
+            cand = int(rng.integers(0, n))
+            if cand != i:
+                parents.add(cand)
+        for p in sorted(parents):
+            planted_inhibit = bool(specs and p in specs[i].inversions and specs[i].inversions[p])
+            kind = "i" if planted_inhibit or rng.random() < 0.15 else "a"
+            key = "interaction" if rng.random() < 0.5 else "signal"
+            graph.add_edge(names[p], names[i], **{key: kind})
+            edges.append([names[p], names[i], key, kind])
+    return graph, edges
+
+
+def hex_rows(mat) -> list:
+    """0/1 rows as hex strings of the packed bits (bit b of byte k = column 8k + b)."""
+    return [np.packbits(np.asarray(row, dtype=np.uint8), bitorder="little").tobytes().hex() for row in np.asarray(mat)]
+
+
+def golden_tutorial(ns):
+    """BASELINE.json configs[0]: the reference's tutorial data set (``input/tutorial_data/tutorial_04370_data.csv``,
+    59 genes x 3621 cells, binarised at 0.01 as ``bash_scripts/local_tutorial.sh`` does) through the
+    UNMODIFIED ``RuleInference`` (sampling, binarisation, Spearman top-3, rule determination with chunking:
+    3621 > 2000 cells) and ``CalculateImportanceScore``.  The KEGG graph of pathway 04370 cannot be fetched
+    offline, so the graph is a seeded digraph over the CSV's own 59 gene names (SURVEY 8-c fixture (i)).
+    The fixture carries the binarised matrix in the reference's sampled cell order (not the CSV)."""
+    csv_path = "/root/reference/input/tutorial_data/tutorial_04370_data.csv"
+    with open(csv_path) as fh:
+        next(fh)
+        names = [line.split(",", 1)[0] for line in fh if line.strip()]
+    rng = np.random.default_rng(4370)
+    graph, edges = seeded_graph(names, rng)
+    np.random.seed(4370)
+    ri = ns.rule_inference.RuleInference(csv_path, graph, "ds_tutorial", "net_04370", ",", list(range(len(names))),
+                                         binarize_threshold=0.01, sample_cells=True)
+    binar = np.asarray(ri.binarized_matrix.todense()).astype(np.uint8)
+    random.seed(4370)
+    mod = ns.importance_scores
+    calc = mod.CalculateImportanceScore(ri.nodes, ri.binarized_matrix.astype(bool), "net_04370", "ds_tutorial")
+    cap = _CaptureMax()
+    mod.max = cap
+    try:
+        scores = calc.calculate_importance_scores()
+    finally:
+        del mod.max
+    dump("tutorial_04370.json", {
+        "source": "input/tutorial_data/tutorial_04370_data.csv, threshold 0.01, np.random.seed(4370), random.seed(4370)",
+        "gene_names": list(ri.gene_names), "n_cells": int(binar.shape[1]), "edges": edges,
+        "binarized_hex": hex_rows(binar), "density": float(binar.mean()),
+        "predecessors": [[int(x) for x in p] for p in ri.predecessors],
+        "nodes": [{"predecessors": [[int(k), v] for k, v in n.predecessors.items()],
+                   "inversions": [[int(k), bool(v)] for k, v in n.inversions.items()],
+                   "best_rule": [n.best_rule[0], [int(i) for i in n.best_rule[1]], n.best_rule[2]],
+                   "best_rule_index": int(n.best_rule_index)} for n in ri.nodes],
+        "ruleset": [[r[0][0], [int(i) for i in r[0][1]], r[0][2], int(r[1]), float(r[2])] for r in ri.ruleset],
+        "sample": [int(i) for i in calc.cell_sample_indices],
+        "raw": [int(v) for v in cap.values], "scores": [float(scores[n.name]) for n in ri.nodes]})
+
+
+def golden_pickles(ns):
+    """Files WRITTEN BY THE REFERENCE for the interchange tests: its own
+    ``Pipeline.infer_rules`` (``pipeline_class.py:134-182``) writes ``*.ruleset.pickle`` and ``*.cells.pickle``;
+    its own ``run_full_importance_score`` (``importance_scores.py:343-427``) reads the former and writes the
+    importance text file and ``*.network.pickle``.  Copied byte for byte into tests/golden/pickles/."""
+    import importlib
+    import shutil
+    import tempfile
+    sys.modules.pop("pipeline_class", None)
+    pipeline_class = importlib.import_module("pipeline_class")
+    rng = np.random.default_rng(81)
+    n_genes, n_cells, seed = 9, 60, 81
+    specs, planes = synth.synthetic_dataset(n_genes, n_cells, seed, flip=0.08, relax_steps=3)
+    dense = synth.planes_to_dense(planes, n_cells)
+    values = dense * rng.uniform(0.5, 3.0, size=dense.shape)
+    names = [f"GENE{i}" for i in range(n_genes)]
+    graph, edges = seeded_graph(names, rng, max_in=4, p_more=0.5, specs=specs)
+    lines = ["gene," + ",".join(f"cell{c}" for c in range(n_cells))]
+    lines += [names[i] + "," + ",".join(f"{v:.6f}" for v in values[i]) for i in range(n_genes)]
+    csv_text = "\n".join(lines) + "\n"
+    with tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False) as fh:
+        fh.write(csv_text)
+        csv_path = fh.name
+    pipe = pipeline_class.Pipeline.__new__(pipeline_class.Pipeline)   # __init__ parses argv and fetches KEGG
+    pipe.data_file, pipe.dataset_name, pipe.datafile_sep = csv_path, "ds_pickle", ","
+    pipe.binarize_threshold, pipe.sample_cells, pipe.organism = 0.001, True, "hsa"
+    for path in ns.file_paths.file_paths.values():
+        os.makedirs(path, exist_ok=True)
+    np.random.seed(seed)
+    pipe.infer_rules("00081", graph, list(range(n_genes)))
+    os.unlink(csv_path)
+    random.seed(seed)
+    # the importance figure needs a real matplotlib, which this container lacks: networkx's three drawing
+    # calls (not reference code) become no-ops for the duration of the call
+    import networkx as nx
+    saved = {name: getattr(nx, name) for name in ("draw_networkx_nodes", "draw_networkx_edges", "draw_networkx_labels")}
+    for name in saved:
+        setattr(nx, name, lambda *a, **k: None)
+    try:
+        ns.importance_scores.run_full_importance_score("ds_pickle", ["hsa00081"])
+    finally:
+        for name, fn in saved.items():
+            setattr(nx, name, fn)
+    fp = ns.file_paths.file_paths
+    out = os.path.join(OUT, "pickles")
+    os.makedirs(out, exist_ok=True)
+    base = f'{fp["pickle_files"]}/ds_pickle_pickle_files'
+    copies = {f"{base}/ruleset_pickle_files/ds_pickle_hsa00081.ruleset.pickle": "ds_pickle_hsa00081.ruleset.pickle",
+              f"{base}/cells_pickle_file/ds_pickle.cells.pickle": "ds_pickle.cells.pickle",
+              f"{base}/network_pickle_files/ds_pickle_hsa00081.network.pickle": "ds_pickle_hsa00081.network.pickle",
+              f'{fp["importance_score_output"]}/ds_pickle/text_files/hsa00081_importance_score.txt': "hsa00081_importance_score.txt",
+              f'{fp["rules_output"]}/ds_pickle_rules/00081_ds_pickle_rules.txt': "00081_ds_pickle_rules.txt"}
+    for src, dst in copies.items():
+        shutil.copyfile(src, os.path.join(out, dst))
+        print(f"wrote {os.path.join(out, dst)} ({os.path.getsize(src)} bytes)")
+    dump("pickles/inputs.json", {"seed": seed, "csv": csv_text, "node_names": names, "edges": edges,
+                                 "dataset_name": "ds_pickle", "pathway": "00081", "organism": "hsa"})
+
+
 def ring_network(n, twist=True):
     """Shift ring G_i <- G_{i-1}; with ``twist`` G_0 <- not G_{n-1} (period 2n Johnson ring)."""
     specs = []
@@ -298,6 +471,11 @@ def main():
     for s, lg in zip(specs, logics):
         s.logic = lg
     golden_sweep(ns, "mixed", specs, synth.planes_to_dense(planes, 48), 41)
+
+    golden_tutorial(ns)
+    golden_pickles(ns)
+    golden_rule_check("a", 12, 90, seed=71)
+    golden_rule_check("b", 30, 257, seed=72)
 
     golden_rule_inference(ns, "a", 10, 80, seed=61)
     golden_rule_inference(ns, "b", 14, 2100, seed=62)

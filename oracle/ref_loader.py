@@ -74,11 +74,14 @@ class _Anything:
             raise AttributeError(name)
         return _Anything()
 
+    def __iter__(self):          # "fig, ax = plt.subplots(...)"
+        return iter((_Anything(), _Anything()))
+
 
 def _stub_module(name: str, **attrs) -> types.ModuleType:
     mod = types.ModuleType(name)
     mod.__dict__.update(attrs)
-    mod.__getattr__ = lambda attr: _Anything  # type: ignore[attr-defined]
+    mod.__getattr__ = lambda attr: _Anything()  # type: ignore[attr-defined]
     sys.modules[name] = mod
     return mod
 

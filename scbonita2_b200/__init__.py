@@ -15,7 +15,7 @@ __version__ = "0.1.0"
 # reference top-level module name -> our module (the reference runs its scripts from code/,
 # so its pickles name classes as e.g. ``node_class.Node``)
 _ALIASES = ("node_class", "network_class", "cell_class", "file_paths", "rule_determination",
-            "importance_scores", "attractor_analysis", "rule_inference")
+            "importance_scores", "attractor_analysis", "rule_inference", "pipeline_class")
 _PICKLED = {"node_class": ("Node",), "network_class": ("Network",),
             "cell_class": ("Cell", "CellPopulation"), "rule_inference": ("RuleInference",)}
 

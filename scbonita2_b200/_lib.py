@@ -18,6 +18,7 @@ _U8P = POINTER(c_uint8)
 _U32P = POINTER(c_uint32)
 
 SCB_COUNTS_SCRATCH_CLEAN = 1
+SCB_COUNTS_CHAINED = 2
 
 # name -> (restype, argtypes).  Device pointers are passed as integers (c_void_p).
 SIGNATURES = {
@@ -39,6 +40,11 @@ SIGNATURES = {
     "scb_rule_counts_plan_build": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "scb_rule_counts_run": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64,
                                     c_void_p, c_int, c_void_p]),
+    "scb_rule_sums_supported": (c_int, [c_int, c_int, c_int]),
+    "scb_rule_sums_run": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int,
+                                  c_void_p, c_int, c_int, c_void_p]),
+    "scb_population_fitness_sums": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int64,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_rule_error_table": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
     "scb_rule_error_table_direct": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p,
@@ -56,6 +62,7 @@ SIGNATURES = {
     "scb_population_fitness_peers": (c_int, [c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p]),
     "scb_peer_error": (c_int, [c_void_p, POINTER(c_int)]),
+    "scb_peer_set_timeout": (c_int, [c_void_p, c_uint32]),
     "scb_bitstring_fitness": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_ko_ki_sweep_scratch_bytes": (c_int64, [c_int, c_int64, c_int]),
     "scb_ko_ki_sweep": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int,

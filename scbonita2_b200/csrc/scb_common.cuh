@@ -90,6 +90,72 @@ __device__ __forceinline__ uint32_t eval_lut(const LutMasks& t, uint32_t a, uint
     return lop3<0xCA>(a, h1, h0);
 }
 
+// ---- rule-counts plan (built by scb_counts.cu, read by its kernels and by the fitness kernel) -----
+constexpr int kTermsPerGroup = 11;  // multi-variable AND terms
+constexpr int kTileWords = 32;      // words per row per tile (128 B)
+// Built once per (groups, n_rows) by a one-CTA kernel, read by every pass:
+//   header   int32[4]     {n_groups, n_rows, n_orphans, 0}
+//   desc     uint4[G]     groups sorted by arity (widest first): byte offsets of rows A, B, C, T inside a
+//                         stage; .x carries arity (bits 0-1) and "owns its target row" (bit 2)
+//   order    uint16[G]    original group index of sorted position
+//   orphans  uint16[R]    rows that are no group's target (their popcounts need items of their own)
+//   target   int32[G], parents int32[3G]   copies for the final inversion
+//   owner    uint32[R]    build-time temporary
+struct PlanLayout {
+    size_t desc, order, orphans, target, parents, owner, bytes;
+};
+__host__ __device__ inline size_t pad16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline PlanLayout plan_layout(int n_rows, int n_groups) {
+    PlanLayout L;
+    L.desc = 16;
+    L.order = L.desc + (size_t)n_groups * 16;
+    L.orphans = L.order + pad16((size_t)n_groups * 2);
+    L.target = L.orphans + pad16((size_t)n_rows * 2);
+    L.parents = L.target + pad16((size_t)n_groups * 4);
+    L.owner = L.parents + pad16((size_t)n_groups * 12);
+    L.bytes = L.owner + pad16((size_t)n_rows * 4);
+    return L;
+}
+constexpr uint32_t kDescOwn = 4u;
+// rows of a stage as the TMA boxes lay them out (a box holds at most 256 rows); the row after them is
+// the all-zero row that unbound parent slots read
+__host__ __device__ inline int plan_zero_row(int n_rows) {
+    const int n_boxes = (n_rows + 255) / 256;
+    return n_boxes * ((n_rows + n_boxes - 1) / n_boxes);
+}
+
+// Subset sum q (bit 3 = T, bit 2 = A, bit 1 = B, bit 0 = C; q = 0: every cell) of the group at sorted
+// position `pos`, gathered from the accumulators acc[n_rows + 11 G] that the counting kernels fill:
+// single-variable sums are row popcounts (rows from the descriptor; the all-zero row reads 0), the
+// rest are the group's own AND terms.  The 16 values of a group, Moebius-inverted, are its joint counts.
+// (Branch-free up to the one load: the sixteen lanes of a group take different cases, and a load inside
+// each case would be issued -- and waited for -- case by case.)
+__device__ __forceinline__ int subset_sum_index(const uint4 d, int g, int q, int n_rows, int zero_row) {
+    // term index of the multi-variable masks (SCB_TERM_MASKS order), one nibble per mask; 15 = single row / empty
+    constexpr unsigned long long kTermOfMask = 0xA784956F301F2FFFull;
+    const int term = (int)((kTermOfMask >> (4 * q)) & 15ull);
+    const uint32_t off = q == 8 ? d.w : (q == 4 ? d.x : (q == 2 ? d.y : d.z));
+    const int row = (int)(off >> 7);
+    const int idx = term != 15 ? n_rows + g * kTermsPerGroup + term : row;
+    return (q == 0 || (term == 15 && row == zero_row)) ? -1 : idx;   // -1: no load (every cell / the all-zero row)
+}
+__device__ __forceinline__ long long subset_sum_local(const uint4 d, int g, int q, const unsigned long long* acc,
+                                                      int n_rows, int zero_row, long long n_cells) {
+    const int idx = subset_sum_index(d, g, q, n_rows, zero_row);
+    const long long v = idx >= 0 ? (long long)__ldcg(acc + idx) : 0ll;
+    return q == 0 ? n_cells : v;
+}
+// Moebius inversion across the 16 lanes that hold the subset sums of one group (lane & 15 = q):
+// afterwards lane q holds #cells whose set of ones is exactly q (target = q >> 3, minterm = q & 7).
+__device__ __forceinline__ long long moebius16(long long x, int q) {
+#pragma unroll
+    for (int bit = 1; bit < 16; bit <<= 1) {
+        const long long other = __shfl_xor_sync(0xFFFFFFFFu, x, bit);
+        if (!(q & bit)) x -= other;
+    }
+    return x;
+}
+
 // ---- peer exchange region (scb_peer.cu, rule_counts_kernel, population_fitness_kernel) --------
 // One region per rank, mapped into every peer (CUDA IPC over NVLink).  Rank r stores its joint
 // counts into slot [parity][r] of EVERY rank's region as 64-bit words {tag = epoch + 1 : count}
@@ -101,8 +167,8 @@ __device__ __forceinline__ uint32_t eval_lut(const LutMasks& t, uint32_t a, uint
 constexpr int kPeerSlotsOffset = 256;
 struct PeerHeader {
     unsigned long long push_ticket;  // CTAs of every push draw tickets: epoch = ticket / n_ranks
-    unsigned int error;              // raised by a kernel that gave up waiting for a peer
-    unsigned int pad;
+    unsigned int error;              // raised by a kernel that gave up waiting for a peer (it also poisons its results)
+    unsigned int timeout_ms;         // how long such a kernel waits (0 = 30 s); scb_peer_set_timeout
 };
 static_assert(sizeof(PeerHeader) <= kPeerSlotsOffset, "peer header must fit before the slots");
 

@@ -18,8 +18,6 @@
 
 namespace scb {
 
-constexpr int kTermsPerGroup = 11;  // multi-variable AND terms
-constexpr int kTileWords = 32;      // words per row per tile (128 B)
 constexpr int kMaxStages = 8;
 constexpr int kInFlight = 3;        // bulk copies outstanding per SM
 #ifndef SCB_CONSUMER_WARPS
@@ -137,31 +135,7 @@ __host__ __device__ __forceinline__ int group_arity(int ra, int rb, int rc) {
     return ra >= 0 ? 1 : 0;
 }
 
-// ---- the plan: everything about a set of groups that does not depend on the cells --------------
-// Built once per (groups, n_rows) by a one-CTA kernel, read by every pass:
-//   header   int32[4]     {n_groups, n_rows, n_orphans, 0}
-//   desc     uint4[G]     groups sorted by arity (widest first): byte offsets of rows A, B, C, T inside a
-//                         stage; .x carries arity (bits 0-1) and "owns its target row" (bit 2)
-//   order    uint16[G]    original group index of sorted position
-//   orphans  uint16[R]    rows that are no group's target (their popcounts need items of their own)
-//   target   int32[G], parents int32[3G]   copies for the final inversion
-//   owner    uint32[R]    build-time temporary
-struct PlanLayout {
-    size_t desc, order, orphans, target, parents, owner, bytes;
-};
-__host__ __device__ inline size_t pad16(size_t x) { return (x + 15) & ~(size_t)15; }
-__host__ __device__ inline PlanLayout plan_layout(int n_rows, int n_groups) {
-    PlanLayout L;
-    L.desc = 16;
-    L.order = L.desc + (size_t)n_groups * 16;
-    L.orphans = L.order + pad16((size_t)n_groups * 2);
-    L.target = L.orphans + pad16((size_t)n_rows * 2);
-    L.parents = L.target + pad16((size_t)n_groups * 4);
-    L.owner = L.parents + pad16((size_t)n_groups * 12);
-    L.bytes = L.owner + pad16((size_t)n_rows * 4);
-    return L;
-}
-constexpr uint32_t kDescOwn = 4u;
+// (the plan layout -- PlanLayout, plan_layout(), kDescOwn -- lives in scb_common.cuh: the fitness kernel reads it too)
 
 __global__ void __launch_bounds__(256)
 rule_counts_plan_kernel(int n_rows, int n_groups, int zero_row, const int32_t* __restrict__ target_row,
@@ -402,7 +376,9 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
                    unsigned int* __restrict__ cta_ticket /*zero on entry, zero on exit*/,
                    int64_t n_cells, int64_t* __restrict__ out_counts /*[G][16]*/,
                    void* const* __restrict__ peer_regions /*[n_ranks] or NULL: also push the counts to the peers*/,
-                   int rank, int n_ranks) {
+                   int rank, int n_ranks,
+                   int sums_only /*1: leave the subset sums in acc for scb_population_fitness_sums (no inversion, no
+                                   ticket on one GPU; sharded: the last CTA pushes the sums, not the counts)*/) {
     extern __shared__ __align__(128) uint32_t smem[];
     // layout: stage[n_stages][(rows_alloc+1)][32] | desc[G] (uint4) | cta_acc[n_rows + 11*G] |
     //         full[kMaxStages], empty[kMaxStages] | s_tile[kMaxStages], s_next[kMaxStages] |
@@ -613,6 +589,9 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     if (!kDirectRed)
         for (int i = tid; i < n_acc; i += blockDim.x)
             if (cta_acc[i]) atomicAdd(acc + i, (unsigned long long)cta_acc[i]);
+    // sums_only on one GPU: that is all -- the consumer (the fitness kernel) is ordered behind this grid by
+    // the stream, inverts the sums itself and zeroes the accumulators: no ticket, no last CTA
+    if (sums_only && !peer_regions) return;
     __syncthreads();
     SCB_TRACE_AT(6, tid == 0);
     // one thread publishes the CTA: the barrier above orders every thread's adds before its
@@ -635,9 +614,23 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     }
     if (peer_regions) __syncthreads();
     const int64_t peer_slot = peer_regions ? ((int64_t)(s_epoch & 1u) * n_ranks + rank) * ((int64_t)n_groups * 16) : 0;
-    // last CTA: Moebius inversion of the subset sums (moebius_pass above)
-    moebius_pass(desc, order, acc, n_rows, rows_alloc, n_groups, n_groups, n_cells, out_counts, peer_regions, n_ranks,
-                 peer_slot, s_epoch + 1u, tid, false);
+    if (sums_only) {
+        // sharded cells: the 16 subset sums of every group go to every rank as they are; the fitness kernels
+        // sum them over the ranks and invert
+        const int q = tid & 15;
+        for (int pos = tid >> 4; pos < n_groups; pos += kCountThreads / 16) {
+            const int g = order[pos];
+            const long long v = subset_sum_local(desc[pos], g, q, acc, n_rows, rows_alloc, n_cells);
+            for (int r = 0; r < n_ranks; ++r)
+                st_peer(reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(peer_regions[r]) + kPeerSlotsOffset) +
+                            peer_slot + (size_t)g * 16 + q,
+                        peer_word(s_epoch + 1u, v));
+        }
+    } else {
+        // last CTA: Moebius inversion of the subset sums (moebius_pass above)
+        moebius_pass(desc, order, acc, n_rows, rows_alloc, n_groups, n_groups, n_cells, out_counts, peer_regions, n_ranks,
+                     peer_slot, s_epoch + 1u, tid, false);
+    }
     // leave the scratch as it was found (all zero) so the next call needs no memset
     __syncthreads();
 
@@ -755,14 +748,15 @@ extern "C" int scb_rule_counts_plan_build(int n_rows, int n_groups, const int32_
 
 static int counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells, int n_groups,
                       const void* plan, void* scratch, int64_t scratch_bytes, int64_t* out_counts, int flags,
-                      void* const* peer_regions, int rank, int n_ranks, scb_stream_t stream) {
+                      void* const* peer_regions, int rank, int n_ranks, int sums_only, scb_stream_t stream) {
     SCB_REQUIRE(n_rows > 0 && n_rows < 65536, "rule_counts: n_rows=%d out of range", n_rows);
     SCB_REQUIRE(wpad > 0 && wpad % 4 == 0 && wpad * 32 >= n_cells && n_cells >= 0, "rule_counts: wpad must be a positive multiple of 4 covering n_cells");
     SCB_REQUIRE(n_cells < ((int64_t)1 << 31), "rule_counts: at most 2^31-1 cells per call (shard the cells)");
     SCB_REQUIRE(n_groups >= 0, "rule_counts: negative n_groups");
-    SCB_REQUIRE((flags & ~SCB_COUNTS_SCRATCH_CLEAN) == 0, "rule_counts: unknown flags 0x%x", flags);
+    SCB_REQUIRE((flags & ~(SCB_COUNTS_SCRATCH_CLEAN | SCB_COUNTS_CHAINED)) == 0, "rule_counts: unknown flags 0x%x", flags);
     if (n_groups == 0) return SCB_OK;
-    SCB_REQUIRE(planes && plan && scratch && out_counts, "rule_counts: null pointer");
+    SCB_REQUIRE(planes && plan && scratch && (out_counts || sums_only), "rule_counts: null pointer");
+    SCB_REQUIRE(!sums_only || n_groups <= kMaxGroupsPerLaunch, "rule_sums: at most %d groups (one launch)", kMaxGroupsPerLaunch);
     SCB_REQUIRE(reinterpret_cast<uintptr_t>(planes) % 16 == 0, "rule_counts: planes must be 16-byte aligned");
     SCB_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 8 == 0, "rule_counts: scratch must be 8-byte aligned");
     SCB_REQUIRE(reinterpret_cast<uintptr_t>(plan) % 16 == 0, "rule_counts: plan must be 16-byte aligned");
@@ -828,21 +822,43 @@ static int counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t 
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        // only the first slice of a call may overlap the previous kernel: later slices share the scratch
-        cfg.numAttrs = (g0 == 0 && (flags & SCB_COUNTS_SCRATCH_CLEAN) && !getenv("SCB_NO_PDL")) ? 1 : 0;
+        // only the first slice of a call may overlap the previous kernel (later slices share the scratch), and
+        // only on the caller's word that that kernel produced neither the bitplanes nor the plan, which
+        // this kernel reads before its griddepcontrol.wait (SCB_COUNTS_CHAINED)
+        cfg.numAttrs = (g0 == 0 && (flags & SCB_COUNTS_SCRATCH_CLEAN) && (flags & SCB_COUNTS_CHAINED) && !getenv("SCB_NO_PDL")) ? 1 : 0;
         SCB_CUDA(cudaLaunchKernelEx(&cfg, rule_counts_kernel, tmap, box_rows, n_boxes, n_stages, n_teams, n_rows,
-                                    n_tiles, gn, plan_at, acc, ticket, n_cells, out_counts + (size_t)g0 * 16,
-                                    peer_regions, rank, n_ranks));
+                                    n_tiles, gn, plan_at, acc, ticket, n_cells, out_counts ? out_counts + (size_t)g0 * 16 : nullptr,
+                                    peer_regions, rank, n_ranks, sums_only));
         plan_at += plan_layout(n_rows, gn).bytes;
     }
     return SCB_OK;
+}
+
+extern "C" int scb_rule_sums_supported(int n_rows, int n_groups, int n_untargeted_rows) {
+    (void)n_untargeted_rows;
+    if (n_rows <= 0 || n_groups <= 0 || n_groups > kMaxGroupsPerLaunch) return 0;  // one launch of the counting kernel
+    // ... and the fitness kernel keeps its tables (200 B per group) plus a copy of the accumulators, of the
+    // descriptors and of the group order in shared memory (scb_rules.cu)
+    const size_t smem = (size_t)n_groups * 200 + ((size_t)n_rows + (size_t)kTermsPerGroup * n_groups + 3) * 8 +
+                        (size_t)n_groups * 18 + 16;
+    return smem <= 200 * 1024 ? 1 : 0;
+}
+
+extern "C" int scb_rule_sums_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells, int n_groups,
+                                 int n_untargeted_rows, const void* plan, void* scratch, int64_t scratch_bytes,
+                                 int flags, void* const* peer_regions, int rank, int n_ranks, scb_stream_t stream) {
+    (void)n_untargeted_rows;
+    SCB_REQUIRE(n_groups > 0, "rule_sums: n_groups=%d out of range", n_groups);
+    SCB_REQUIRE(!peer_regions || (n_ranks >= 1 && n_ranks <= SCB_MAX_PEERS && rank >= 0 && rank < n_ranks), "rule_sums: rank %d of %d", rank, n_ranks);
+    return counts_run(planes, n_rows, wpad, n_cells, n_groups, plan, scratch, scratch_bytes, nullptr, flags,
+                      peer_regions, rank, peer_regions ? n_ranks : 1, 1, stream);
 }
 
 extern "C" int scb_rule_counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
                                    int n_groups, const void* plan, void* scratch, int64_t scratch_bytes,
                                    int64_t* out_counts, int flags, scb_stream_t stream) {
     return counts_run(planes, n_rows, wpad, n_cells, n_groups, plan, scratch, scratch_bytes, out_counts, flags,
-                      nullptr, 0, 1, stream);
+                      nullptr, 0, 1, 0, stream);
 }
 
 extern "C" int scb_rule_counts_run_push(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,
@@ -853,7 +869,7 @@ extern "C" int scb_rule_counts_run_push(const uint32_t* planes, int n_rows, int6
     SCB_REQUIRE(peer_regions, "rule_counts_run_push: null peer table");
     SCB_REQUIRE(n_groups <= kMaxGroupsPerLaunch, "rule_counts_run_push: at most %d groups (one launch)", kMaxGroupsPerLaunch);
     return counts_run(planes, n_rows, wpad, n_cells, n_groups, plan, scratch, scratch_bytes, out_counts, flags,
-                      peer_regions, rank, n_ranks, stream);
+                      peer_regions, rank, n_ranks, 0, stream);
 }
 
 extern "C" int scb_rule_counts_ex(const uint32_t* planes, int n_rows, int64_t wpad, int64_t n_cells,

@@ -1,6 +1,8 @@
 // Peer-memory exchange of the joint counts between the GPUs of one box (cells shard across GPUs,
 // SURVEY 8-e).  The reference has no counterpart: it is single-host multiprocessing
 // (importance_scores.py:238-253).  See PeerHeader in scb_common.cuh for the protocol.
+#include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "scb_common.cuh"
@@ -43,6 +45,11 @@ extern "C" int scb_peer_region_alloc(int64_t bytes, void** region, unsigned char
     void* p = nullptr;
     SCB_CUDA(cudaMalloc(&p, (size_t)bytes));
     SCB_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    if (const char* e = getenv("SCB_PEER_TIMEOUT_MS")) {   // default for every region of this process (0 = 30 s)
+        PeerHeader hdr = {};
+        hdr.timeout_ms = (unsigned int)strtoul(e, nullptr, 10);
+        SCB_CUDA(cudaMemcpy(p, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+    }
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) {
@@ -98,5 +105,17 @@ extern "C" int scb_peer_error(const void* local_region, int* out_error) {
     PeerHeader h;
     SCB_CUDA(cudaMemcpy(&h, local_region, sizeof(h), cudaMemcpyDeviceToHost));
     *out_error = (int)h.error;
+    if (h.error) {  // reported once: the flag is cleared so that the next check speaks about the next steps
+        const unsigned int zero = 0u;
+        SCB_CUDA(cudaMemcpy(static_cast<unsigned char*>(const_cast<void*>(local_region)) + offsetof(PeerHeader, error), &zero,
+                            sizeof(zero), cudaMemcpyHostToDevice));
+    }
+    return SCB_OK;
+}
+
+extern "C" int scb_peer_set_timeout(void* local_region, unsigned int timeout_ms) {
+    SCB_REQUIRE(local_region, "peer_set_timeout: null pointer");
+    SCB_CUDA(cudaMemcpy(static_cast<unsigned char*>(local_region) + offsetof(PeerHeader, timeout_ms), &timeout_ms,
+                        sizeof(timeout_ms), cudaMemcpyHostToDevice));
     return SCB_OK;
 }

@@ -52,6 +52,26 @@ __global__ void error_table_kernel(const int64_t* __restrict__ counts, int64_t n
     out_diff[t] = diff_from_counts(counts + (size_t)task_group[t] * 16, task_lut[t]);
 }
 
+// Input of the fitness kernel when it consumes the subset sums of scb_rule_sums_run: mode 1 reads the
+// local accumulators through the plan's descriptors (and its last CTA zeroes them for the next pass),
+// mode 2 sums the ranks' slots of the exchange region, which then hold subset sums [G][16].
+struct SumsInput {
+    int mode;
+    const unsigned char* plan;
+    unsigned long long* acc;
+    unsigned int* ticket;
+    int n_rows, zero_row;
+    long long n_cells;
+};
+
+// How long a kernel waits for a peer's tagged word before it gives up (PeerHeader.timeout_ms, 0 = 30 s).
+// A kernel that gave up raises PeerHeader.error AND poisons every result it writes (INT64_MIN): a rank
+// that was merely slow can never leave plausible but wrong numbers behind.
+__device__ __forceinline__ unsigned long long peer_timeout_ns(const unsigned char* region) {
+    const unsigned int ms = reinterpret_cast<const PeerHeader*>(region)->timeout_ms;
+    return (unsigned long long)(ms ? ms : 30000u) * 1000000ull;
+}
+
 // One warp per individual.  With
 //   diff(L) = sum_k c[k][1] + sum_{k: L_k = 1} (c[k][0] - c[k][1])
 // the CTA stages base[g] and, per table nibble, the 16 partial sums of the deltas:
@@ -65,7 +85,8 @@ __global__ void __launch_bounds__(1024)
 population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int64_t n_ind,
                           const uint8_t* __restrict__ lut, const uint8_t* __restrict__ active,
                           int64_t* __restrict__ out_diff, int64_t* __restrict__ out_diff_pg,
-                          const unsigned char* region /*peer exchange region or NULL*/, int rank, int n_ranks) {
+                          const unsigned char* region /*peer exchange region or NULL*/, int rank, int n_ranks,
+                          const SumsInput sums /*sums.mode != 0: subset sums instead of counts (scb_rule_sums_run)*/) {
     extern __shared__ __align__(16) long long s_tab[];  // base[G] | delta[8][G] (int64) | lo/hi[32][G] (int32)
     long long* base = s_tab;
     long long* delta = s_tab + n_groups;
@@ -111,11 +132,123 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     // the shared memory of ALL of them (distributed shared memory), so a CTA reads 1/C of the slots.
     // Without a cluster attribute the cluster is this CTA alone and the same code runs.
     const uint32_t c_rank = cluster_cta_rank(), c_size = cluster_size();
-    __shared__ unsigned int s_wide;
-    if (threadIdx.x == 0) s_wide = 0u;
+    __shared__ unsigned int s_wide, s_timeout;
+    if (threadIdx.x == 0) s_wide = s_timeout = 0u;
+    const unsigned long long give_up_ns = region ? peer_timeout_ns(region) : 0ull;
     if (c_size > 1) cluster_sync_all();  // every CTA of the cluster is running (and s_wide is cleared) before a peer stores into it
     int wide = 0;
     long long* ones = reinterpret_cast<long long*>(nib);
+    const int sums_dbg = sums.mode >> 4;   // experiments: 1 = no ticket / zeroing, 2 = no loads
+    if ((sums.mode & 15) != 0) {
+        // ---- subset sums in: sixteen lanes per group gather (or sum over the ranks) the 16 sums, invert
+        // them through shuffles, and lanes 0..7 write the minterm's delta and target-1 count ----
+        // one GPU: the accumulators (n_rows + 11 G words, ~19 KB) are first copied into shared memory with
+        // coalesced 16-byte loads -- 128 CTAs gathering single words straight from L2 make five times the
+        // requests on the same 150 cache lines and take 6 us longer (measured)
+        const int n_acc = sums.n_rows + kTermsPerGroup * n_groups;
+        unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(s_tab + ((25 * (size_t)n_groups + 1) & ~(size_t)1));  // [n_acc | 1], 16-byte aligned
+        uint4* s_desc = reinterpret_cast<uint4*>(s_acc + ((n_acc + 1) & ~1));                               // [G]
+        unsigned short* s_order = reinterpret_cast<unsigned short*>(s_desc + n_groups);                     // [G]
+        if ((sums.mode & 15) == 1) {
+            const PlanLayout L = plan_layout(sums.n_rows, n_groups);
+            const uint4* g_desc = reinterpret_cast<const uint4*>(sums.plan + L.desc);
+            const unsigned short* g_order = reinterpret_cast<const unsigned short*>(sums.plan + L.order);
+            for (int i = threadIdx.x; i < n_groups; i += blockDim.x) {
+                s_desc[i] = __ldg(g_desc + i);
+                s_order[i] = __ldg(g_order + i);
+            }
+            if (!(sums_dbg & 2)) {
+                const ulonglong2* src = reinterpret_cast<const ulonglong2*>(sums.acc);
+                for (int i = threadIdx.x; i < n_acc / 2; i += blockDim.x) {
+                    const ulonglong2 v2 = __ldcg(src + i);
+                    s_acc[2 * i] = v2.x;
+                    s_acc[2 * i + 1] = v2.y;
+                }
+                if ((n_acc & 1) && threadIdx.x == 0) s_acc[n_acc - 1] = __ldcg(sums.acc + n_acc - 1);
+            }
+        }
+        __syncthreads();  // (also: s_wide / s_timeout are cleared)
+        if ((sums.mode & 15) == 1 && !(sums_dbg & 1) && threadIdx.x < 32) {
+            // every read of the global accumulators by this CTA is done: warp 0 of the last CTA to get here
+            // zeroes them (and the ticket) for the next pass, while everybody else goes on
+            unsigned int t = 0;
+            if (threadIdx.x == 0)
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(sums.ticket) : "memory");
+            t = __shfl_sync(0xFFFFFFFFu, t, 0);
+            if (t == gridDim.x - 1) {
+                for (int i = threadIdx.x; i < n_acc; i += 32) sums.acc[i] = 0ull;
+                if (threadIdx.x == 0) *sums.ticket = 0u;
+            }
+        }
+        const int q = threadIdx.x & 15;
+        constexpr int kBatch = 4;  // the loads of four rounds fly together (two dependent L2 trips in all)
+        const int per_round = blockDim.x >> 4;
+        for (int pos0 = 0; pos0 < n_groups; pos0 += kBatch * per_round) {  // uniform trip count: shuffles inside
+            long long v[kBatch];
+            int g[kBatch];
+            bool live[kBatch];
+            if ((sums.mode & 15) == 1) {
+                uint4 d[kBatch];
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k) {
+                    const int pos = pos0 + k * per_round + (threadIdx.x >> 4);
+                    live[k] = pos < n_groups;
+                    d[k] = s_desc[live[k] ? pos : 0];
+                    g[k] = (int)s_order[live[k] ? pos : 0];
+                }
+                int idx[kBatch];
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k)
+                    idx[k] = (live[k] && !(sums_dbg & 2)) ? subset_sum_index(d[k], g[k], q, sums.n_rows, sums.zero_row) : -1;
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k) v[k] = idx[k] >= 0 ? (long long)s_acc[idx[k]] : 0ll;
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k)
+                    if (q == 0 && live[k]) v[k] = sums.n_cells;
+            } else {
+                // (one round at a time: the eight ranks' loads of a word already fly together)
+#pragma unroll 1
+                for (int k = 0; k < kBatch; ++k) {
+                    g[k] = pos0 + k * per_round + (threadIdx.x >> 4);
+                    live[k] = g[k] < n_groups;
+                    v[k] = 0;
+                    if (!live[k]) continue;
+                    unsigned long long t[SCB_MAX_PEERS];
+#pragma unroll
+                    for (int r = 0; r < SCB_MAX_PEERS; ++r)
+                        if (r < n_ranks) t[r] = ld_peer(slots + ((int64_t)r * n_groups + g[k]) * 16 + q);
+#pragma unroll
+                    for (int r = 0; r < SCB_MAX_PEERS; ++r) {
+                        if (r >= n_ranks) continue;
+                        if ((unsigned int)(t[r] >> 32) != want) {
+                            // the peer's word has not landed yet: spin, but never hang
+                            const unsigned long long* w = slots + ((int64_t)r * n_groups + g[k]) * 16 + q;
+                            const unsigned long long t0 = global_timer_ns();
+                            do {
+                                t[r] = ld_peer(w);
+                                if (global_timer_ns() - t0 > give_up_ns) {
+                                    reinterpret_cast<PeerHeader*>(const_cast<unsigned char*>(region))->error = 1u;
+                                    s_timeout = 1u;
+                                    break;
+                                }
+                            } while ((unsigned int)(t[r] >> 32) != want);
+                        }
+                        v[k] += (long long)(unsigned int)t[r];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) {
+                const long long x = moebius16(v[k], q);
+                const long long y = __shfl_down_sync(0xFFFFFFFFu, x, 8);  // lane q < 8: (minterm q, target 1)
+                if (live[k] && q < 8) {
+                    if (((unsigned long long)(x + y) >> 28) != 0) s_wide = 1u;
+                    delta[q * n_groups + g[k]] = x - y;
+                    ones[q * n_groups + g[k]] = y;
+                }
+            }
+        }
+    } else
     for (int e = threadIdx.x * (int)c_size + (int)c_rank; e < n_groups * 8; e += blockDim.x * (int)c_size) {
         const int g = e >> 3, k = e & 7;
         longlong2 v;  // (minterm k, target 0), (minterm k, target 1)
@@ -137,8 +270,9 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
                     const unsigned long long t0 = global_timer_ns();
                     do {
                         t[r] = ld_peer2(w);
-                        if (global_timer_ns() - t0 > 2000000000ull) {
+                        if (global_timer_ns() - t0 > give_up_ns) {
                             reinterpret_cast<PeerHeader*>(const_cast<unsigned char*>(region))->error = 1u;
+                            for (uint32_t cr = 0; cr < c_size; ++cr) st_cluster_u32(cluster_map(&s_timeout, cr), 1u);
                             break;
                         }
                     } while ((unsigned int)(t[r].x >> 32) != want || (unsigned int)(t[r].y >> 32) != want);
@@ -147,7 +281,9 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
                 v.y += (long long)(unsigned int)t[r].y;
             }
         }
-        const int w = (int)(((unsigned long long)v.x | (unsigned long long)v.y) >> 31 != 0);
+        // a nibble entry sums up to four deltas and the eight minterms share the cells: with every
+        // (minterm, either target) count below 2^28 no entry can leave int32
+        const int w = (int)(((unsigned long long)(v.x + v.y) >> 28) != 0);
         wide |= w;
         if (c_size == 1) {
             delta[k * n_groups + g] = v.x - v.y;
@@ -163,6 +299,7 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     if (c_size > 1) cluster_sync_all();  // release / acquire: the peers' stores are visible from here on
     else __syncthreads();
     wide |= (int)s_wide;
+    const bool poisoned = s_timeout != 0u;
     for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
         long long b = 0;
 #pragma unroll
@@ -219,13 +356,13 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
                         d += nib[(table & 15u) * n_groups + g] + nib[(16u + (table >> 4)) * n_groups + g];
                     }
                 }
-                if (out_diff_pg) out_diff_pg[(size_t)p * n_groups + g] = d;
+                if (out_diff_pg) out_diff_pg[(size_t)p * n_groups + g] = poisoned ? (long long)0x8000000000000000ull : d;
                 total += d;
             }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, off);
-        if (lane == 0) out_diff[p] = total;
+        if (lane == 0) out_diff[p] = poisoned ? (long long)0x8000000000000000ull : total;
     }
 }
 
@@ -310,8 +447,10 @@ extern "C" int scb_rule_error_table(const int64_t* counts, int n_groups, int64_t
 static int launch_population_fitness(const int64_t* counts, int n_groups, int64_t n_individuals,
                                      const uint8_t* lut, const uint8_t* active, int64_t* out_diff,
                                      int64_t* out_diff_pg, const unsigned char* region, int rank, int n_ranks,
-                                     scb_stream_t stream) {
+                                     const SumsInput& sums, scb_stream_t stream) {
     size_t smem = (size_t)n_groups * 25 * sizeof(long long);  // base + 8 int64 deltas + 32 int32 nibble sums
+    if ((sums.mode & 15) == 1)   // + a copy of the accumulators, of the descriptors and of the group order
+        smem += ((size_t)sums.n_rows + (size_t)kTermsPerGroup * n_groups + 3) * 8 + (size_t)n_groups * 18 + 16;
     if (smem > 200 * 1024) {
         set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 200));
         return SCB_ERR_UNSUPPORTED;
@@ -352,8 +491,19 @@ static int launch_population_fitness(const int64_t* counts, int n_groups, int64_
     cfg.attrs = attr;
     cfg.numAttrs = n_attr;
     SCB_CUDA(cudaLaunchKernelEx(&cfg, population_fitness_kernel, counts, n_groups, n_individuals, lut, active,
-                                out_diff, out_diff_pg, region, rank, n_ranks));
+                                out_diff, out_diff_pg, region, rank, n_ranks, sums));
     return SCB_OK;
+}
+
+static SumsInput no_sums() {
+    SumsInput s;
+    s.mode = 0;
+    s.plan = nullptr;
+    s.acc = nullptr;
+    s.ticket = nullptr;
+    s.n_rows = s.zero_row = 0;
+    s.n_cells = 0;
+    return s;
 }
 
 extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64_t n_individuals,
@@ -363,7 +513,29 @@ extern "C" int scb_population_fitness(const int64_t* counts, int n_groups, int64
     if (n_individuals == 0) return SCB_OK;
     SCB_REQUIRE(counts && lut && out_diff, "population_fitness: null pointer");
     return launch_population_fitness(counts, n_groups, n_individuals, lut, active, out_diff, out_diff_pg, nullptr,
-                                     0, 1, stream);
+                                     0, 1, no_sums(), stream);
+}
+
+extern "C" int scb_population_fitness_sums(const void* plan, void* scratch, int n_rows, int n_groups, int64_t n_cells,
+                                           const void* local_region, int rank, int n_ranks, int64_t n_individuals,
+                                           const uint8_t* lut, const uint8_t* active, int64_t* out_diff,
+                                           int64_t* out_diff_pg, scb_stream_t stream) {
+    SCB_REQUIRE(n_groups > 0 && n_rows > 0 && n_individuals >= 0 && n_cells >= 0, "population_fitness_sums: bad size");
+    SCB_REQUIRE(plan && scratch && lut && out_diff, "population_fitness_sums: null pointer");
+    SCB_REQUIRE(!local_region || (n_ranks >= 1 && n_ranks <= SCB_MAX_PEERS && rank >= 0 && rank < n_ranks), "population_fitness_sums: rank %d of %d", rank, n_ranks);
+    // (an empty population still has to consume -- and clear -- the sums of its pass)
+    SumsInput sums;
+    sums.mode = local_region ? 2 : 1;
+    if (const char* e = getenv("SCB_SUMS_DBG")) sums.mode |= atoi(e) << 4;
+    sums.plan = static_cast<const unsigned char*>(plan);
+    sums.acc = static_cast<unsigned long long*>(scratch);
+    sums.ticket = reinterpret_cast<unsigned int*>(sums.acc + (size_t)n_rows + (size_t)kTermsPerGroup * n_groups);
+    sums.n_rows = n_rows;
+    sums.zero_row = plan_zero_row(n_rows);
+    sums.n_cells = n_cells;
+    return launch_population_fitness(nullptr, n_groups, n_individuals, lut, active, out_diff, out_diff_pg,
+                                     static_cast<const unsigned char*>(local_region), rank, local_region ? n_ranks : 1,
+                                     sums, stream);
 }
 
 extern "C" int scb_population_fitness_peers(const void* local_region, int rank, int n_ranks, int n_groups,
@@ -374,7 +546,7 @@ extern "C" int scb_population_fitness_peers(const void* local_region, int rank, 
     if (n_individuals == 0) return SCB_OK;
     SCB_REQUIRE(local_region && lut && out_diff, "population_fitness_peers: null pointer");
     return launch_population_fitness(nullptr, n_groups, n_individuals, lut, active, out_diff, out_diff_pg,
-                                     static_cast<const unsigned char*>(local_region), rank, n_ranks, stream);
+                                     static_cast<const unsigned char*>(local_region), rank, n_ranks, no_sums(), stream);
 }
 
 extern "C" int scb_bitstring_fitness(const int64_t* task_diff, int64_t n_tasks, int64_t n_individuals,

@@ -188,11 +188,74 @@ class RuleCountsPlan:
                                                     self.parents.data_ptr(), self.plan.data_ptr(),
                                                     self.plan_bytes, _stream()), "scb_rule_counts_plan_build")
         self.counts = torch.empty((self.n_groups, 16), dtype=torch.int64, device=dev)
+        self.n_untargeted = int(self.n_rows - len(set(int(t) for t in target))) if target.size else self.n_rows
+        self.fused_supported = bool(self.n_groups) and bool(
+            L.scb_rule_sums_supported(self.n_rows, self.n_groups, self.n_untargeted))
 
-    def run(self, planes: BitPlanes, exchange=None):
+    def _flags(self, chained: bool) -> int:
+        return _lib.SCB_COUNTS_SCRATCH_CLEAN | (_lib.SCB_COUNTS_CHAINED if chained else 0)
+
+    def sums_run(self, planes: BitPlanes, exchange=None, chained: bool = False):
+        """First half of the fused GA step: ``scb_rule_sums_run`` -- one pass over the cells that leaves
+        the SUBSET SUMS of every group in the plan's scratch (and, with ``exchange``, pushes them to the
+        peers).  Must be followed by exactly one ``fitness_from_sums`` on this plan."""
+        torch = _torch()
+        if not self.fused_supported:
+            raise ValueError("more groups than the fused step holds (about 660: its fitness kernel keeps a copy "
+                             "of the sums in shared memory): use run() + population_fitness()")
+        if planes.n_rows != self.n_rows:
+            raise ValueError("plan was built for a different number of rows")
+        if exchange is not None and exchange.n_groups != self.n_groups:
+            raise ValueError("exchange was built for a different number of groups")
+        with torch.cuda.device(self.counts.device):
+            _lib.check(_lib.lib().scb_rule_sums_run(
+                planes.words.data_ptr(), planes.n_rows, planes.wpad, planes.n_cells, self.n_groups, self.n_untargeted,
+                self.plan.data_ptr(), self.scratch.data_ptr(), self.scratch_bytes, self._flags(chained),
+                exchange.peer_table.data_ptr() if exchange is not None else None,
+                exchange.rank if exchange is not None else 0, exchange.world_size if exchange is not None else 1,
+                _stream()), "scb_rule_sums_run")
+        self._sums_cells = planes.n_cells
+
+    def fitness_from_sums(self, lut, out=None, exchange=None, active=None, per_node: bool = False):
+        """Second half: ``scb_population_fitness_sums`` -- inverts the sums while it builds its tables,
+        evaluates the population and leaves the scratch cleared for the next pass."""
+        torch = _torch()
+        dev = self.counts.device
+        if isinstance(lut, torch.Tensor) and lut.dtype == torch.uint8 and lut.device == dev and lut.is_contiguous():
+            d_lut = lut
+        else:
+            d_lut = _dev(lut if isinstance(lut, torch.Tensor) else np.asarray(lut, dtype=np.uint8), torch.uint8, dev)
+        n_ind = int(d_lut.shape[0])
+        if int(d_lut.shape[1]) != self.n_groups:
+            raise ValueError("lut must be [P, G] with G == the plan's group count")
+        d_act = _dev(active, torch.uint8, dev) if active is not None else None
+        if out is None:
+            out = torch.empty(n_ind, dtype=torch.int64, device=dev)
+        out_pg = torch.empty((n_ind, self.n_groups), dtype=torch.int64, device=dev) if per_node else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().scb_population_fitness_sums(
+                self.plan.data_ptr(), self.scratch.data_ptr(), self.n_rows, self.n_groups, self._sums_cells,
+                exchange.region if exchange is not None else None,
+                exchange.rank if exchange is not None else 0, exchange.world_size if exchange is not None else 1,
+                n_ind, d_lut.data_ptr(), d_act.data_ptr() if d_act is not None else None, out.data_ptr(),
+                out_pg.data_ptr() if out_pg is not None else None, _stream()), "scb_population_fitness_sums")
+        return out, out_pg
+
+    def fitness_step(self, planes: BitPlanes, lut, out=None, exchange=None, active=None, per_node: bool = False,
+                     chained: bool = False):
+        """One GA-fitness step, fused: ``sums_run`` + ``fitness_from_sums`` -- two kernel launches and
+        nothing else; no ticket, no last-CTA finalize, no memset between or after them.  With
+        ``exchange`` the sums of the cell shards travel through the peers' exchange regions.
+        ``chained=True`` is the caller's word that the kernel enqueued before this call wrote neither the
+        bitplanes nor the plan (e.g. it is the previous ``fitness_step``): the pass then overlaps that
+        kernel's tail.  Same numbers as ``run`` + ``population_fitness``."""
+        self.sums_run(planes, exchange=exchange, chained=chained)
+        return self.fitness_from_sums(lut, out=out, exchange=exchange, active=active, per_node=per_node)
+
+    def run(self, planes: BitPlanes, exchange=None, chained: bool = False):
         """Enqueue the pass on the current stream; returns the (reused) int64 [G, 16] tensor.
         With ``exchange`` (``distributed.PeerExchange``) the kernel's last CTA also pushes the counts
-        to every peer's exchange region (``scb_rule_counts_run_push``)."""
+        to every peer's exchange region (``scb_rule_counts_run_push``).  ``chained``: see ``fitness_step``."""
         torch = _torch()
         if planes.n_rows != self.n_rows:
             raise ValueError("plan was built for a different number of rows")
@@ -203,14 +266,14 @@ class RuleCountsPlan:
                 _lib.check(_lib.lib().scb_rule_counts_run_push(
                     planes.words.data_ptr(), planes.n_rows, planes.wpad, planes.n_cells, self.n_groups,
                     self.plan.data_ptr(), self.scratch.data_ptr(), self.scratch_bytes,
-                    self.counts.data_ptr(), _lib.SCB_COUNTS_SCRATCH_CLEAN, exchange.peer_table.data_ptr(),
+                    self.counts.data_ptr(), self._flags(chained), exchange.peer_table.data_ptr(),
                     exchange.rank, exchange.world_size, _stream()), "scb_rule_counts_run_push")
             return self.counts
         with torch.cuda.device(self.counts.device):
             _lib.check(_lib.lib().scb_rule_counts_run(
                 planes.words.data_ptr(), planes.n_rows, planes.wpad, planes.n_cells, self.n_groups,
                 self.plan.data_ptr(), self.scratch.data_ptr(), self.scratch_bytes,
-                self.counts.data_ptr(), _lib.SCB_COUNTS_SCRATCH_CLEAN, _stream()), "scb_rule_counts_run")
+                self.counts.data_ptr(), self._flags(chained), _stream()), "scb_rule_counts_run")
         return self.counts
 
 

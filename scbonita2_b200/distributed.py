@@ -207,7 +207,13 @@ class PeerExchange:
         err = ctypes.c_int(0)
         _lib.check(_lib.lib().scb_peer_error(self.region, ctypes.byref(err)), "scb_peer_error")
         if err.value:
-            raise RuntimeError("peer exchange: a rank did not deliver its counts within 2 s")
+            raise RuntimeError("peer exchange: a rank did not deliver its counts in time; the results of the "
+                               "affected launches were poisoned (INT64_MIN)")
+
+    def set_timeout(self, milliseconds: int):
+        """How long a kernel waits for a peer's word before it gives up (0 = the default of 30 s)."""
+        from . import _lib
+        _lib.check(_lib.lib().scb_peer_set_timeout(self.region, int(milliseconds)), "scb_peer_set_timeout")
 
     def close(self):
         from . import _lib

@@ -386,3 +386,120 @@ def test_spearman_top3_matches_scipy_selection(cuda):
         rho, _ = spearmanr(dense[a].astype(float), dense[b].astype(float))
         assert abs(spearman.phi_from_table(*t) - rho) < 1e-12
         assert t.sum() == n_cells
+
+
+# ---- the fused GA step: scb_rule_sums_run + scb_population_fitness_sums ------------------------
+def _random_groups(rng, n_rows, n_groups, p_bound=0.6, targets=None):
+    parents = np.full((n_groups, 3), -1, dtype=np.int32)
+    for g in range(n_groups):
+        bound = rng.random(3) < p_bound
+        parents[g, bound] = rng.integers(0, n_rows, int(bound.sum()))
+    if targets is None:
+        targets = rng.integers(0, n_rows, n_groups)
+    return np.asarray(targets, dtype=np.int32), parents
+
+
+@pytest.mark.parametrize("n_rows,n_groups,n_cells,p_bound,seed", [
+    (5, 1, 33, 1.0, 0), (12, 12, 1000, 0.6, 1), (40, 40, 4097, 0.9, 2), (64, 200, 70_001, 0.7, 3),
+    (200, 200, 123_457, 0.66, 4), (300, 77, 9_999, 0.5, 5), (30, 600, 5_000, 0.4, 6), (255, 100, 31, 1.0, 7),
+    (17, 17, 2_000_003, 0.8, 8)])
+def test_fused_fitness_step_matches_counts_then_fitness(cuda, n_rows, n_groups, n_cells, p_bound, seed):
+    """Counting kernel in sums-only mode + Moebius inversion inside the fitness kernel against the counts
+    kernel + fitness kernel (itself checked against NumPy and the eval-per-cell oracle above): parent holes in any
+    pattern, several groups per target row, rows nobody targets, repeated passes on one plan."""
+    import torch
+    from scbonita2_b200 import device
+    rng = np.random.default_rng(100 + seed)
+    targets, parents = _random_groups(rng, n_rows, n_groups, p_bound)
+    planes_np = synth.random_planes(n_rows, n_cells, 50 + seed, density=rng.uniform(0.05, 0.9, n_rows))
+    planes = device.BitPlanes.from_packed(planes_np, n_cells)
+    plan = device.RuleCountsPlan(n_rows, targets, parents)
+    assert plan.fused_supported
+    lut = torch.from_numpy(rng.integers(0, 256, (37, n_groups), dtype=np.uint8)).cuda()
+    active = (rng.random((37, n_groups)) < 0.7).astype(np.uint8)
+    want, want_pg = device.population_fitness(plan.run(planes).clone(), lut, per_node=True)
+    want_act, _ = device.population_fitness(plan.counts, lut, active=active)
+    for rep in range(3):
+        got, got_pg = plan.fitness_step(planes, lut, per_node=(rep == 1), chained=(rep == 2))
+        assert torch.equal(got, want), rep
+        if got_pg is not None:
+            assert torch.equal(got_pg, want_pg)
+    got_act, _ = plan.fitness_step(planes, lut, active=active)
+    assert torch.equal(got_act, want_act)
+    # the scratch is clean again: the counts path still gives the same counts on the same plan
+    assert torch.equal(plan.run(planes), device.rule_counts(planes, targets, parents))
+
+
+def test_fused_step_refuses_what_it_cannot_hold(cuda):
+    from scbonita2_b200 import device
+    rng = np.random.default_rng(3)
+    targets, parents = _random_groups(rng, 50, 900)
+    plan = device.RuleCountsPlan(50, targets, parents)
+    assert not plan.fused_supported                   # the fitness kernel's shared-memory copy of the sums does not fit
+    planes = device.BitPlanes.from_packed(synth.random_planes(50, 100, 1), 100)
+    with pytest.raises(ValueError):
+        plan.fitness_step(planes, np.zeros((2, 900), dtype=np.uint8))
+    assert plan.run(planes).shape == (900, 16)       # the counts path takes any number of groups
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_fused_step_sums_through_the_peer_regions(cuda, world):
+    """Sharded cells on ONE device (logical ranks): every rank's sums kernel pushes its subset sums from
+    its last CTA, every rank's fitness kernel sums the slots and inverts: equal to the unsharded step."""
+    import torch
+    from scbonita2_b200 import device
+    from scbonita2_b200.distributed import PeerExchange, word_range
+    n_nodes, n_cells = 30, 50_021
+    specs, planes_np = synth.synthetic_dataset(n_nodes, n_cells, 41 + world, flip=0.1)
+    targets, parents = _groups(specs)
+    full = device.BitPlanes.from_packed(planes_np, n_cells)
+    rng = np.random.default_rng(5)
+    lut = torch.from_numpy(rng.integers(0, 256, (50, n_nodes), dtype=np.uint8)).cuda()
+    want, want_pg = device.population_fitness(device.rule_counts(full, targets, parents), lut, per_node=True)
+    group = PeerExchange.local_group(n_nodes, world)
+    plans = [device.RuleCountsPlan(n_nodes, targets, parents) for _ in range(world)]
+    shards = [full.word_slice(*word_range(n_cells, r, world)) for r in range(world)]
+    try:
+        for epoch in range(4):
+            for r in range(world):
+                plans[r].sums_run(shards[r], exchange=group[r], chained=(epoch > 1))
+            for r in range(world):
+                got, got_pg = plans[r].fitness_from_sums(lut, exchange=group[r], per_node=(epoch == 0))
+                assert torch.equal(got, want), (epoch, r)
+                if got_pg is not None:
+                    assert torch.equal(got_pg, want_pg)
+        for ex in group:
+            ex.check()
+    finally:
+        for ex in group:
+            ex.close()
+
+
+def test_peer_timeout_poisons_the_results(cuda):
+    """A rank whose peer never delivers must not leave plausible numbers behind: the kernel gives up
+    after the configured time, writes INT64_MIN everywhere and raises the region's error flag (which
+    check() reports once and clears)."""
+    import torch
+    from scbonita2_b200 import device
+    from scbonita2_b200.distributed import PeerExchange
+    rng = np.random.default_rng(9)
+    n_groups = 10
+    group = PeerExchange.local_group(n_groups, 2)
+    try:
+        for ex in group:
+            ex.set_timeout(50)
+        counts = torch.from_numpy(rng.integers(0, 1000, (n_groups, 16))).cuda()
+        lut = torch.from_numpy(rng.integers(0, 256, (5, n_groups), dtype=np.uint8)).cuda()
+        group[0].push(counts)                                  # rank 1 never pushes
+        got, got_pg = group[0].population_fitness(lut, per_node=True)
+        assert (got == torch.iinfo(torch.int64).min).all() and (got_pg == torch.iinfo(torch.int64).min).all()
+        with pytest.raises(RuntimeError):
+            group[0].check()
+        group[0].check()                                       # reported once
+        group[1].push(counts)                                  # the late rank arrives: the next read is whole again
+        want, _ = device.population_fitness(2 * counts, lut)
+        got, _ = group[0].population_fitness(lut)
+        assert torch.equal(got, want)
+    finally:
+        for ex in group:
+            ex.close()

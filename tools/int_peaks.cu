@@ -20,7 +20,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(1024, 2) pipe_kernel(uint32_t* out, long long* cycles, long long* nanos, uint32_t seed) {
+__global__ void __launch_bounds__(1024, 1) pipe_kernel(uint32_t* out, long long* cycles, long long* nanos, uint32_t seed) {
     uint32_t x[ILP], y = seed ^ threadIdx.x;
 #pragma unroll
     for (int i = 0; i < ILP; ++i) x[i] = seed * (i + 1) + threadIdx.x;
@@ -65,7 +65,7 @@ template <int MODE>
 static void run(const char* name, double inst_per_iter, int sms) {
     uint32_t* out;
     long long *cyc, *ns;
-    int blocks = sms * 2;
+    int blocks = sms;  // one 32-warp CTA per SM (8 warps x ILP 8 per scheduler): every CTA runs for the whole kernel
     cudaMalloc(&out, 4);
     cudaMalloc(&cyc, blocks * sizeof(long long));
     cudaMalloc(&ns, blocks * sizeof(long long));
@@ -90,8 +90,8 @@ static void run(const char* name, double inst_per_iter, int sms) {
     }
     mean /= blocks;
     mean_ns /= blocks;
-    // two 32-warp CTAs share an SM: warp-instructions per SM = 2 CTAs * 32 warps * ITERS * inst
-    double warp_inst_per_sm = 2.0 * 32.0 * ITERS * inst_per_iter;
+    // warp-instructions per SM = 32 warps * ITERS * inst
+    double warp_inst_per_sm = 32.0 * ITERS * inst_per_iter;
     double lane_ops = (double)blocks * 1024.0 * ITERS * inst_per_iter;
     const double sm_mhz = mean / mean_ns * 1e3;
     printf("{\"pipe\": \"%s\", \"warp_inst_per_clk_per_sm\": %.3f, \"lanes_per_clk_per_sm\": %.1f, \"sm_mhz_in_kernel\": %.0f, "
