@@ -168,3 +168,11 @@ def test_sweep_exact_on_a_hard_k50_like_case(cuda, monkeypatch, fast, sort):
     hard = cport.importance_raw_bitsliced(planes_np[:, :64], 2048, parents, luts, 50)
     assert hard[1][0] > 0 and hard[1][1:].max() > 0 and hard[2] > 0   # cells without a repeat, KeyError pairs
     _compare_with_bitsliced_oracle(planes_np, n_cells, parents, luts)
+
+
+def test_every_kernel_family_once(cuda):
+    """tools/sanitize_target.py -- the workload meant for compute-sanitizer (closed on this pool, see
+    profiles/r2_sanitizer_closed.txt) -- as a parity run: every kernel family at small sizes, each result
+    checked against NumPy / the C oracle."""
+    from tools import sanitize_target
+    sanitize_target.main()
