@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--sweep-steps", type=int, default=2, help="timed sweep repetitions (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fused-peers", action="store_true", help="N>1: exchange subset sums (scb_rule_sums_run) instead of counts")
     ap.add_argument("--unfused", action="store_true", help="GA step = scb_rule_counts_run + scb_population_fitness (round-1 kernels)")
     ap.add_argument("--no-e2e-dense", action="store_true", help="skip the dense-uint8 variant of the end-to-end step")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling block (same 1M cells split over the ranks)")
@@ -501,7 +502,10 @@ def run_ours(args):
         rot = [planes] + [device.BitPlanes(planes.words.clone(), planes.n_rows, planes.n_cells)
                           for _ in range(n_rot - 1)]
 
-        fused = plan.fused_supported and not args.unfused and (world == 1 or exchange is not None)
+        # one GPU: counting kernel in sums-only mode + fitness kernel that inverts (no ticket / last-CTA finalize).
+        # Sharded: the last CTA is needed for the push either way, and the counts format (two words per
+        # thread in the polling fitness kernel) measured faster at N=8 (28.9 vs 34.5 us per step): round-1 pair.
+        fused = plan.fused_supported and not args.unfused and (world == 1 or args.fused_peers)
 
         def fitness_step(k=0):
             # two kernel launches (+ one NCCL all-reduce in the --nccl variant); nothing else is enqueued

@@ -460,6 +460,17 @@ static int launch_population_fitness(const int64_t* counts, int n_groups, int64_
     int64_t blocks = (n_individuals + 31) / 32;  // 32 warps per CTA, one individual per warp and round
     int64_t cap = (int64_t)sm_count();
     if (blocks > cap) blocks = cap;
+    // sharded cells, experiment (SCB_FITNESS_PER_WARP=k): every CTA sums the slots of all ranks (n_ranks x
+    // 16 G words from L2) before it can start; fewer CTAs with k individuals per warp trade that traffic
+    // for a longer loop.  Measured with 8 logical ranks on one device (tools/time_peers.py): no gain at
+    // k = 2, slower from k = 4 on -- off by default.
+    if (region && n_ranks > 1) {
+        if (const char* e = getenv("SCB_FITNESS_PER_WARP")) {
+            const int per_warp = atoi(e) > 0 ? atoi(e) : 1;
+            const int64_t fewer = (n_individuals + 32 * per_warp - 1) / (32 * per_warp);
+            if (fewer < blocks) blocks = fewer < 1 ? 1 : fewer;
+        }
+    }
     // programmatic dependent launch: the kernel may start while its producer (scb_rule_counts in the
     // same stream) drains; it waits for it with griddepcontrol.wait before it reads the counts
     cudaLaunchConfig_t cfg = {};
