@@ -54,16 +54,44 @@ class PopulationFitness:
 
 
 class GeneticAlgorithm:
-    """Seeded GA over multi-rule individuals, fitness on the GPU (SURVEY §8-f next-1).
+    """Seeded GA over multi-rule individuals, fitness on the GPU (SURVEY 8-f next-1).
 
-    The GA only survives in the reference as Python-3.6 bytecode; what is restated here are its
-    recovered constants and shapes: 15 generations, start population 50, 25 parents /
-    25 children, crossover 0.1, mutation 0.9, bit-flip 0.5, a node's segment of the bitstring
-    holds 1..5 set bits, fitness = sum(differences) / sum(counts) + 0.002 * (#rules) * gen/max_gen,
-    minimised.  PARITY UNPINNED against the historic code (no runnable source); the fitness values
-    are pinned to ``calculate_error`` through the oracle identity, and the run is a pure function
-    of ``seed`` (NumPy ``default_rng``), which is what "selected rules under a fixed seed and
-    population trajectory" can mean for a reference that no longer ships its GA.
+    The GA only survives in the reference as Python-3.6 bytecode
+    (``code/__pycache__/updated_deap_class.cpython-36.pyc``); its disassembly is committed as
+    ``oracle/bytecode/updated_deap_class_py36.dis.txt`` (made by ``oracle/pyc36_dis.py``) and is what this
+    class follows -- source line numbers below are the ones recorded in that bytecode:
+
+    * generation loop (``genetic_algorithm``, 83-165): the start population is evaluated with
+      ``(current_gen, max_gen) = (0, generations)``; then for ``gen = 1 .. generations``: ``offspring =
+      __varOrAdaptive(population, ..., gen / generations, ...)``, every offspring is evaluated with
+      ``(gen, generations + 1)``, the last generation's offspring are the result, otherwise
+      ``population[:] = select(offspring, parent_population_size)`` -- survivors come from the OFFSPRING
+      only, there is no elitism;
+    * variation (``__varOrAdaptive``, 949-975): per child one uniform draw: ``< cx`` -> two-point
+      crossover on node boundaries of two sampled parents, the first child kept (``__cxTwoPointNode``,
+      978-1020); ``< cx + mut`` -> adaptive bit-flip mutation of a clone (``__mutFlipBitAdapt``);
+      otherwise a parent is copied;
+    * fitness (``fitness_calculation``, 892-946): ``sum(difference) / sum(count)`` over every selected
+      rule of every node, plus ``0.002 * (#selected rules) * current_gen / max_gen``; minimised
+      (``FitnessMin``, ONE weight of -1.0: ``make_toolbox`` 648-649 -- the per-node weight tuple built
+      just above it is never used);
+    * selection (``__selNSGA2`` 727-756 with ``__sortNondominatedAdapt`` / ``__dominated`` 834-854):
+      "dominates" compares ``mean(wvalues)``, i.e. the single fitness value, so the non-dominated fronts
+      are the groups of individuals with EQUAL fitness in ascending order: NSGA-II selection degenerates
+      to truncation by fitness.  What remains of it is the tie rule: fronts are taken whole, and the
+      front that crosses ``k`` is ordered by crowding distance -- with identical fitness values its
+      first and last member get ``inf`` and the rest ``0.0`` (``__assignCrowdingDist`` 857-890), so the
+      stable descending sort yields first, last, then the others in order.  ``_select`` does exactly that;
+    * start individuals (``__genBits``, 686-717): random bits, per node at most five and at least one
+      set bit.
+
+    The mutation operator is restated in simplified form (the node to rewrite is drawn with probability
+    proportional to its error, ``__selectMutNode`` 1118-1137; the reference additionally biases towards
+    nodes with many upstream candidates), and the reference's draws come from ``random`` / ``np.random``
+    streams that a NumPy ``default_rng`` cannot replay.  PARITY UNPINNED against the historic code (no
+    runnable source); the fitness values are pinned to ``calculate_error`` through the oracle identity,
+    and a run is a pure function of ``seed``.  Recovered constants: 15 generations, start
+    population 50, 25 parents, 25 children, crossover 0.1, mutation 0.9, bit-flip 0.5.
     """
 
     def __init__(self, nodes, planes: device.BitPlanes, seed: int = 0, generations: int = 15,
@@ -104,11 +132,33 @@ class GeneticAlgorithm:
         bits = self.rng.integers(0, 2, size=int(self.offsets[-1])).astype(np.uint8)
         return self._repair(bits)
 
-    def evaluate(self, pop, generation):
+    def evaluate(self, pop, generation, max_gen=None):
         diff, nsel = device.bitstring_fitness(self.task_diff, np.ascontiguousarray(pop))
         diff, nsel = diff.cpu().numpy(), nsel.cpu().numpy()
         raw = diff / (nsel.astype(np.int64) * self.n_cells)
-        return raw, raw + 0.002 * nsel * generation / self.generations
+        max_gen = self.generations if max_gen is None else max_gen
+        return raw, raw + 0.002 * nsel * generation / max_gen
+
+    @staticmethod
+    def _select(fitness, k):
+        """Indices of the ``k`` survivors (``__selNSGA2`` on a single objective, see the class notes):
+        groups of equal fitness, best first and whole; the group that crosses ``k`` contributes its first,
+        its last, then its other members in order."""
+        order = {}
+        for i, f in enumerate(fitness):
+            order.setdefault(float(f), []).append(i)
+        chosen = []
+        for value in sorted(order):
+            front = order[value]
+            if len(chosen) + len(front) <= k:
+                chosen.extend(front)
+                if len(chosen) == k:
+                    break
+                continue
+            ranked = [front[0], front[-1]] + front[1:-1] if len(front) > 1 else front
+            chosen.extend(ranked[:k - len(chosen)])
+            break
+        return chosen
 
     def _crossover(self, a, b):
         cut = np.sort(self.rng.choice(len(self.nodes) + 1, 2, replace=False))
@@ -129,24 +179,32 @@ class GeneticAlgorithm:
         return self._repair(bits)
 
     def run(self):
-        pop = np.stack([self._random_individual() for _ in range(self.population)])
-        for gen in range(self.generations):
-            raw, fit = self.evaluate(pop, gen)
-            order = np.lexsort((np.arange(len(fit)), fit))     # best first, ties by position
-            keep = pop[order[:self.n_parents]]
-            self.history.append({"generation": gen, "best": float(fit[order[0]]),
-                                 "mean": float(fit.mean()), "best_raw": float(raw[order[0]])})
+        population = np.stack([self._random_individual() for _ in range(self.population)])
+        raw, fit = self.evaluate(population, 0, self.generations)
+        self.history.append({"generation": 0, "best": float(fit.min()), "mean": float(fit.mean()),
+                             "best_raw": float(raw[int(np.argmin(fit))])})
+        for gen in range(1, self.generations + 1):
             kids = []
-            for _ in range(self.n_children):
-                i, j = self.rng.integers(0, len(keep), 2)
-                child = self._crossover(keep[i], keep[j]) if self.rng.random() < self.cx else keep[i].copy()
-                if self.rng.random() < self.mut:
-                    child = self._mutate(child)
+            for _ in range(self.n_children):            # __varOrAdaptive
+                op_choice = self.rng.random()
+                if op_choice < self.cx:
+                    i, j = self.rng.choice(len(population), 2, replace=False)
+                    child = self._crossover(population[i], population[j])
+                elif op_choice < self.cx + self.mut:
+                    child = self._mutate(population[self.rng.integers(0, len(population))].copy())
+                else:
+                    child = population[self.rng.integers(0, len(population))].copy()
                 kids.append(child)
-            pop = np.concatenate([keep, np.stack(kids)])
-        raw, fit = self.evaluate(pop, self.generations)
-        best = pop[int(np.lexsort((np.arange(len(fit)), fit))[0])]
-        self.population_bits = pop
+            offspring = np.stack(kids)
+            raw, fit = self.evaluate(offspring, gen, self.generations + 1)
+            self.history.append({"generation": gen, "best": float(fit.min()), "mean": float(fit.mean()),
+                                 "best_raw": float(raw[int(np.argmin(fit))])})
+            if gen == self.generations:
+                population = offspring
+                break
+            population = offspring[self._select(fit, self.n_parents)]
+        best = population[int(np.lexsort((np.arange(len(fit)), fit))[0])]
+        self.population_bits = population
         self.final_raw, self.final_fitness = raw, fit
         rules = []
         for n, node in enumerate(self.nodes):

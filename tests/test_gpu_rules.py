@@ -251,8 +251,9 @@ def test_rule_inference_constructor_golden(cuda, name, tmp_path, gpu_pruning):
 
 
 def test_genetic_algorithm_seeded_and_fitness_pinned(cuda):
-    """GA loop (next-1): deterministic under a seed, elitist, and its GPU fitness equals the oracle
-    formula sum(calculate_error)/sum(count) + 0.002 * #rules * gen/max_gen."""
+    """GA loop (next-1): deterministic under a seed, survivors drawn from the offspring only with the
+    NSGA-II tie rule of the disassembled reference (oracle/bytecode/), and its GPU fitness equals the
+    oracle formula sum(calculate_error)/sum(count) + 0.002 * #rules * gen/max_gen."""
     from scbonita2_b200 import device
     from scbonita2_b200.genetic_algorithm import GeneticAlgorithm
     specs, planes_np = synth.synthetic_dataset(8, 120, 71, flip=0.03, relax_steps=3)
@@ -265,14 +266,18 @@ def test_genetic_algorithm_seeded_and_fitness_pinned(cuda):
     (ga, res), (_, res2) = runs
     assert res["rules"] == res2["rules"] and res["history"] == res2["history"]
     assert (res["best_individual"] == res2["best_individual"]).all()
-    bests = [h["best_raw"] for h in res["history"]]
-    assert all(b2 <= b1 + 1e-15 for b1, b2 in zip(bests, bests[1:]))     # parents survive
-    # oracle check of three final individuals
+    assert [h["generation"] for h in res["history"]] == list(range(7)) and len(ga.population_bits) == 10
+    # selection: groups of equal fitness best first and whole; the group that crosses k gives its first,
+    # its last, then its other members (crowding distance inf, inf, 0, 0, ...)
+    assert GeneticAlgorithm._select([3.0, 1.0, 2.0, 1.0, 1.0, 5.0], 2) == [1, 4]
+    assert GeneticAlgorithm._select([3.0, 1.0, 2.0, 1.0, 1.0, 5.0], 4) == [1, 3, 4, 2]
+    assert GeneticAlgorithm._select([1, 1, 1, 1, 1], 3) == [0, 4, 1] and GeneticAlgorithm._select([2, 1], 5) == [1, 0]
+    # oracle check of three final individuals: the last generation is evaluated with (gen, generations + 1)
     logics = ga.logics
-    for p in (0, 7, 19):
+    for p in (0, 4, 9):
         bits = ga.population_bits[p]
         sel = [list(np.flatnonzero(bits[ga.offsets[n]:ga.offsets[n + 1]])) for n in range(8)]
-        raw, fit = ref_port.population_fitness(ga.nodes, logics, [sel], dense, ga.generations, ga.generations)
+        raw, fit = ref_port.population_fitness(ga.nodes, logics, [sel], dense, ga.generations, ga.generations + 1)
         assert ga.final_raw[p] == raw[0] and ga.final_fitness[p] == fit[0][0]
 
 
