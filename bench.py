@@ -714,9 +714,11 @@ def run_ours(args):
     k_ms = ga["counts_kernel_ms"]
     algo_bytes = args.nodes * n_words * 4 + args.nodes * 16 * 8
     traffic = None
-    traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(traffic_path) and args.nodes == 200 and args.cells == 1_000_000:
-        traffic = json.load(open(traffic_path))["rule_counts_kernel"]["dram_bytes"]   # ncu --set full capture
+    for name in ("r2_traffic.json", "r1_traffic.json"):       # ncu --set full capture of one launch on H1M
+        traffic_path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(traffic_path) and args.nodes == 200 and args.cells == 1_000_000:
+            traffic = json.load(open(traffic_path))["rule_counts_kernel"]["dram_bytes"]
+            break
     roofline_hbm = {"kernel": ga["kernel"], "bound": "hbm", "achieved": algo_bytes / (k_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": algo_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                     "traffic": traffic, "peak_source": hbm_src, "kernel_ms": k_ms, "algorithmic_bytes": algo_bytes}
