@@ -58,6 +58,17 @@ static inline int ensure_dynamic_smem(const void* kernel, size_t smem, SmemMarks
     return SCB_OK;
 }
 
+// Shared-memory carve-out at its maximum for a kernel that wants several large CTAs per SM (per device,
+// once per call site like ensure_dynamic_smem).
+static inline int ensure_max_carveout(const void* kernel, SmemMarks& marks) {
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && marks.mark[dev]) return SCB_OK;
+    SCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    if (dev >= 0 && dev < 64) marks.mark[dev] = 1;
+    return SCB_OK;
+}
+
 // lop3.b32 with a compile-time truth table: bit (a<<2|b<<1|c) of IMM
 template <int IMM>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {

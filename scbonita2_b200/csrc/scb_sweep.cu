@@ -1522,6 +1522,270 @@ sweep_kernel(const SweepArgs args) {
 }
 
 // ---------------------------------------------------------------------------------------
+// KO/KI on the plane words, two CTAs per SM (the default KO/KI pass when the recheck pass follows).
+//
+// Same work and the same results as sweep_kernel<64, MODE_KOKI> with the register ring -- a CTA is
+// (forced node, 32 words), slot 2l = KO and slot 2l + 1 = KI of word l, ring of 2: a lane whose new
+// state equals state_{t-1} or state_{t-2} has its first repeat there and is frozen at it, lanes still
+// open when the CTA stops go to the recheck list -- laid out for occupancy instead of for one fat CTA:
+//  * shared memory holds TWO state copies, not four: the copy a step writes holds state_{t-2}, and the
+//    owner of a (node, slot) word reads it just before it overwrites it -- nobody else touches that
+//    copy during the step.  102 KB for 200 nodes x 64 slots: two CTAs (32 warps) per SM, so the
+//    dependent LDS -> IMAD -> LOP3 chain of one warp is covered by seven others per scheduler
+//    instead of three;
+//  * the KO and the KI word of a (node, word) are neighbours: one 64-bit load / store serves both;
+//  * parent offsets are byte offsets (one add per parent), the forced node is an ordinary one-parent
+//    node whose parent is a constant row (KO slots 0, KI slots ~0): nothing about it in the loop;
+//  * nodes are dealt to the 16 warps evenly (N/16 or N/16 + 1 each);
+//  * no slow path: the deferral lists hold every cell (sweep_list_capacity), a lane the ring cannot
+//    settle is always handed on.
+// Scoring needs at most one more step: a lane frozen by this ring has period 1 or 2, so its states at
+// offsets 0, 1, 2 are s, step(s), s (align_attractors, importance_scores.py:325-340).
+// ---------------------------------------------------------------------------------------
+constexpr int kKkThreads = 512, kKkWarps = 16, kKkSlots = 64;
+constexpr int kKkRow = 2 * kKkSlots;  // words per node: [copy][slot]
+constexpr int kKkTabPad = 16;
+
+static size_t koki_plane_smem_bytes(int n_nodes) {
+    return (size_t)(n_nodes + 1) * kKkRow * 4 + (size_t)(n_nodes + kKkTabPad) * (sizeof(int4) + sizeof(LutMasks)) +
+           (size_t)3 * 2 * kKkSlots * 4;
+}
+
+// kKkCurRegs: state_{t-1} of the own nodes in registers (else re-read from the copy the step reads)
+template <int CH, bool kKkCurRegs>
+__global__ void __launch_bounds__(kKkThreads, 2)
+koki_plane_kernel(const SweepArgs args) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int N = args.n_nodes;
+    const int64_t wpad = args.wpad;
+    uint32_t* state = smem;                                                   // [N + 1][2][64], row N = forced values
+    int4* offs = reinterpret_cast<int4*>(smem + (size_t)(N + 1) * kKkRow);    // [N + pad] parent byte offsets, arity
+    LutMasks* masks = reinterpret_cast<LutMasks*>(offs + N + kKkTabPad);      // [N + pad] affine tables
+    uint32_t* votes = reinterpret_cast<uint32_t*>(masks + N + kKkTabPad);     // [3][2][64]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int base = N / kKkWarps, rem = N % kKkWarps;
+    const int cnt = base + (warp < rem ? 1 : 0);         // nodes of this warp (<= CH)
+    const int n0 = warp * base + min(warp, rem);
+    const int forced_node = (int)(blockIdx.x % (unsigned)N);
+    const int64_t word = (int64_t)(blockIdx.x / (unsigned)N) * 32 + lane;
+    const bool word_ok = word < wpad;
+    uint32_t cellmask = word_ok ? tail_mask(word, args.n_cells) : 0u;
+
+    // ---- tables (the forced node reads the constant row), constant row, vote words
+    for (int n = tid; n < N + kKkTabPad; n += kKkThreads) {
+        int4 o = make_int4(0, 0, 0, 0);
+        LutMasks mk = affine_table(0u, 0);
+        if (n < N) {
+            int arity;
+            const NodeEntry e = make_entry(args.net_parent, args.net_lut, n, &arity);
+            o = make_int4(e.pa * kKkRow * 4, e.pb * kKkRow * 4, e.pc * kKkRow * 4, arity);
+            mk = affine_table(e.lut, arity);
+            if (n == forced_node) {
+                o = make_int4(N * kKkRow * 4, N * kKkRow * 4, N * kKkRow * 4, 1);
+                mk = affine_table(0xF0u, 1);  // f = A
+            }
+        }
+        offs[n] = o;
+        masks[n] = mk;
+    }
+    if (tid < 2 * kKkSlots) state[(size_t)N * kKkRow + tid] = (tid & 1) ? 0xFFFFFFFFu : 0u;
+    for (int i = tid; i < 3 * 2 * kKkSlots; i += kKkThreads) votes[i] = 0u;
+    // cells whose unperturbed run needed the general scheme go straight to the cleanup list (see sweep_kernel)
+    {
+        const uint32_t hard = word_ok ? __ldg(args.np_hard + word) & cellmask : 0u;
+        if (hard && warp == 0) {
+            const unsigned int k = __popc(hard);
+            const unsigned int at0 = atomicAdd(&args.hard_count[forced_node], k);
+            int32_t* dst = args.hard_cells + (size_t)forced_node * args.hard_cap + at0;  // cap = n_cells: always room
+            for (uint32_t m = hard; m; m &= m - 1) *dst++ = (int32_t)(word * 32 + (__ffs(m) - 1));
+        }
+        cellmask &= ~hard;
+    }
+    // ---- data -> copy 1 (both slots of a word start from the same state)
+    uint2 cur[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        cur[i] = make_uint2(0u, 0u);
+        if (i < cnt) {
+            const uint32_t v = word_ok ? __ldg(args.planes + (size_t)(n0 + i) * wpad + word) : 0u;
+            cur[i] = make_uint2(v, v);
+            *reinterpret_cast<uint2*>(state + (size_t)(n0 + i) * kKkRow + kKkSlots + 2 * lane) = cur[i];
+        }
+    }
+    __syncthreads();
+
+    // ---- ring of 2
+    uint32_t frozen0 = ~cellmask, frozen1 = ~cellmask;
+    uint32_t lam0_0 = 0, lam1_0 = 0, lam0_1 = 0, lam1_1 = 0;  // lamB_h: bit B of lambda, slot h
+    int vset = 0;
+    unsigned int last_open = 0xFFFFFFFFu;
+    int stall = 0;
+    bool moved = false;
+    const int stop_open = args.stop_open, stop_stall = args.stop_stall;
+    const int t_fast = args.fast_steps > 0 ? min(args.steps, args.fast_steps) : min(args.steps, (int)args.counters[3]);
+    const char* tab_o = reinterpret_cast<const char*>(offs + n0);
+    const char* tab_m = reinterpret_cast<const char*>(masks + n0);
+
+    // value of the node with table entry (o, mk) for both slots, parents read at `srd` (copy, slot pair)
+    auto eval2 = [&](const int4 o, const char* mk, const char* srd) -> uint2 {
+        uint2 f;
+        if (o.w <= 1) {
+            const uint2 so = *reinterpret_cast<const uint2*>(mk);
+            const uint2 a = *reinterpret_cast<const uint2*>(srd + o.x);
+            f.x = affine(a.x, so.x, so.y);
+            f.y = affine(a.y, so.x, so.y);
+            return f;
+        }
+        const uint4 lo = *reinterpret_cast<const uint4*>(mk);
+        const uint2 a = *reinterpret_cast<const uint2*>(srd + o.x);
+        const uint2 b = *reinterpret_cast<const uint2*>(srd + o.y);
+        if (o.w == 2) {
+            f.x = lop3<0xCA>(a.x, affine(b.x, lo.z, lo.w), affine(b.x, lo.x, lo.y));
+            f.y = lop3<0xCA>(a.y, affine(b.y, lo.z, lo.w), affine(b.y, lo.x, lo.y));
+            return f;
+        }
+        const uint4 hi = *reinterpret_cast<const uint4*>(mk + 16);
+        const uint2 c = *reinterpret_cast<const uint2*>(srd + o.z);
+        f.x = lop3<0xCA>(a.x, lop3<0xCA>(b.x, affine(c.x, hi.z, hi.w), affine(c.x, hi.x, hi.y)),
+                         lop3<0xCA>(b.x, affine(c.x, lo.z, lo.w), affine(c.x, lo.x, lo.y)));
+        f.y = lop3<0xCA>(a.y, lop3<0xCA>(b.y, affine(c.y, hi.z, hi.w), affine(c.y, hi.x, hi.y)),
+                         lop3<0xCA>(b.y, affine(c.y, lo.z, lo.w), affine(c.y, lo.x, lo.y)));
+        return f;
+    };
+
+    // one step: reads copy RD (state_{t-1}), writes copy RD ^ 1 (which holds state_{t-2} of the own nodes)
+    auto step = [&](auto rd_tag, int t) -> bool {
+        constexpr int RD = decltype(rd_tag)::value, WR = RD ^ 1;
+        const char* srd = reinterpret_cast<const char*>(state + RD * kKkSlots + 2 * lane);
+        uint32_t* own_wr = state + (size_t)n0 * kKkRow + WR * kKkSlots + 2 * lane;
+        const uint32_t* own_rd = state + (size_t)n0 * kKkRow + RD * kKkSlots + 2 * lane;
+        uint32_t q1x = 0, q1y = 0, q2x = 0, q2y = 0;
+        int4 o_next = *reinterpret_cast<const int4*>(tab_o);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int4 o = o_next;
+            if (i + 1 < CH) o_next = *reinterpret_cast<const int4*>(tab_o + (i + 1) * 16);  // (tables are padded)
+            if (i < cnt) {
+                const uint2 old2 = *reinterpret_cast<const uint2*>(own_wr + i * kKkRow);
+                const uint2 c1 = kKkCurRegs ? cur[i] : *reinterpret_cast<const uint2*>(own_rd + i * kKkRow);
+                const uint2 f = eval2(o, tab_m + i * 32, srd);
+                q1x |= f.x ^ c1.x;
+                q1y |= f.y ^ c1.y;
+                q2x |= f.x ^ old2.x;
+                q2y |= f.y ^ old2.y;
+                uint2 w;
+                w.x = (f.x & ~frozen0) | (c1.x & frozen0);
+                w.y = (f.y & ~frozen1) | (c1.y & frozen1);
+                *reinterpret_cast<uint2*>(own_wr + i * kKkRow) = w;
+                if (kKkCurRegs) cur[i] = w;
+            }
+        }
+        uint32_t* v = votes + vset * 2 * kKkSlots;
+        if (q1x) atomicOr(v + 2 * lane, q1x);
+        if (q1y) atomicOr(v + 2 * lane + 1, q1y);
+        if (q2x) atomicOr(v + kKkSlots + 2 * lane, q2x);
+        if (q2y) atomicOr(v + kKkSlots + 2 * lane + 1, q2y);
+        __syncthreads();
+        const uint2 n1 = *reinterpret_cast<const uint2*>(v + 2 * lane);
+        const uint2 n2 = *reinterpret_cast<const uint2*>(v + kKkSlots + 2 * lane);
+        // state_{t-d} exists for t >= d only (the raw data state is never compared)
+        uint32_t open = ~frozen0;
+        uint32_t e1 = t >= 1 ? ~n1.x & open : 0u;
+        open &= ~e1;
+        uint32_t e2 = t >= 2 ? ~n2.x & open : 0u;
+        lam0_0 |= e1;
+        lam1_0 |= e2;
+        frozen0 |= e1 | e2;
+        open = ~frozen1;
+        e1 = t >= 1 ? ~n1.y & open : 0u;
+        open &= ~e1;
+        e2 = t >= 2 ? ~n2.y & open : 0u;
+        lam0_1 |= e1;
+        lam1_1 |= e2;
+        frozen1 |= e1 | e2;
+        // every warp holds the frozen masks of all 64 slots: the stop rule needs no barrier (ring2_registers)
+        const unsigned int n_open = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)(__popc(~frozen0) + __popc(~frozen1)));
+        if (n_open <= (unsigned int)stop_open) return true;
+        if (n_open < last_open) {
+            moved = last_open != 0xFFFFFFFFu;
+            last_open = n_open;
+            stall = 0;
+        } else if (moved && ++stall >= stop_stall) {
+            return true;
+        }
+        const int vclear = vset == 0 ? 2 : vset - 1;  // (t + 2) % 3: every reader is past the barrier of step t + 1 by then
+        if (tid < 2 * kKkSlots) votes[vclear * 2 * kKkSlots + tid] = 0u;
+        vset = vset == 2 ? 0 : vset + 1;
+        return false;
+    };
+    using FromOne = std::integral_constant<int, 1>;
+    using FromZero = std::integral_constant<int, 0>;
+    int xs = 1;  // copy that holds the final states
+    for (int t = 0; t < t_fast; t += 2) {
+        xs = 0;
+        if (step(FromOne{}, t)) break;
+        if (t + 1 >= t_fast) break;
+        xs = 1;
+        if (step(FromZero{}, t + 1)) break;
+    }
+    // (the closing barrier of the last step ordered every store of copy xs; nothing below writes the state)
+
+    // ---- lanes still open: KO and KI of a cell travel together to the recheck list
+    const uint32_t both = ~frozen0 | ~frozen1;
+    if (both && warp == 0) {
+        const unsigned int k = __popc(both);
+        const unsigned int at0 = atomicAdd(&args.out_count[forced_node], k);
+        int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + at0;  // cap = n_cells: always room
+        for (uint32_t m = both; m; m &= m - 1) *dst++ = (int32_t)(word * 32 + (__ffs(m) - 1));
+    }
+    cellmask &= ~both;
+
+    // ---- scoring: a cell counts only if its KO run AND its KI run repeat (and the normal one)
+    const uint32_t found_n = word_ok ? __ldg(args.np_found + word) : 0u;
+    uint32_t lamn_ge2 = 0u;
+    if (word_ok) {
+#pragma unroll
+        for (int b = 1; b < kLamPlanes; ++b) lamn_ge2 |= __ldg(args.np_lam + (size_t)b * wpad + word);
+    }
+    const uint32_t valid = cellmask & found_n;  // every lane left in cellmask is frozen in both slots
+    if (warp == 0) {
+        const uint32_t bad = __popc(cellmask & ~found_n);
+        if (bad) atomicAdd(args.out_keyerror, (unsigned long long)bad);
+    }
+    unsigned long long score = 0;
+    if (__any_sync(0xFFFFFFFFu, valid != 0)) {
+        const char* srd = reinterpret_cast<const char*>(state + xs * kKkSlots + 2 * lane);
+        const uint32_t* own = state + (size_t)n0 * kKkRow + xs * kKkSlots + 2 * lane;
+        const bool cyc = __any_sync(0xFFFFFFFFu, (valid & (lam1_0 | lam1_1 | lamn_ge2)) != 0);
+        const uint32_t act2_0 = valid & lam1_0 & lamn_ge2, act2_1 = valid & lam1_1 & lamn_ge2;
+        const bool any2 = __any_sync(0xFFFFFFFFu, (act2_0 | act2_1) != 0);
+        uint32_t sc = 0, sc1 = 0;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            if (i < cnt) {
+                const size_t at = (size_t)(n0 + i) * wpad + word;
+                const uint2 s = *reinterpret_cast<const uint2*>(own + i * kKkRow);
+                const uint32_t ref0 = word_ok ? __ldg(args.np_states + at) : 0u;
+                sc += __popc((s.x ^ ref0) & valid) + __popc((s.y ^ ref0) & valid);
+                if (cyc) {
+                    const uint2 f = eval2(*reinterpret_cast<const int4*>(tab_o + i * 16), tab_m + i * 32, srd);
+                    const uint32_t ref1 = word_ok ? __ldg(args.np_states + (size_t)N * wpad + at) : 0u;
+                    sc1 += __popc((f.x ^ ref1) & valid) + __popc((f.y ^ ref1) & valid);
+                    if (any2) {
+                        const uint32_t ref2 = word_ok ? __ldg(args.np_states + (size_t)2 * N * wpad + at) : 0u;
+                        sc1 += __popc((s.x ^ ref2) & act2_0) + __popc((s.y ^ ref2) & act2_1);
+                    }
+                }
+            }
+        }
+        score = cyc ? (unsigned long long)sc + sc1 : 2ull * sc;  // fixed point vs fixed point: offset 1 repeats offset 0
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
+    if (lane == 0 && score) atomicAdd(args.out_raw + forced_node, score);
+}
+
+// ---------------------------------------------------------------------------------------
 // trajectories: slot word = 32 selected cells; out[m][n][t] bytes
 // ---------------------------------------------------------------------------------------
 constexpr int kTrajSlots = 32;
@@ -1693,8 +1957,29 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
         return SCB_ERR_UNSUPPORTED;
     }
     dim3 grid_k((unsigned)n_koki);
-    sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(args);
-    SCB_LAUNCH_CHECK("sweep_kernel<koki>");
+    // the two-CTAs-per-SM kernel whenever the recheck pass follows and the nodes fit its register arrays
+    // (SCB_SWEEP_KOKI=old keeps sweep_kernel<SLOTS, MODE_KOKI>: experiments, tests of both paths)
+    const char* koki_env = getenv("SCB_SWEEP_KOKI");
+    const bool plane2 = SLOTS == 64 && two_level && args.n_nodes <= kKkWarps * 13 && !(koki_env && koki_env[0] == 'o') &&
+                        koki_plane_smem_bytes(args.n_nodes) <= kMaxDynSmem;
+    if (plane2) {
+        const char* cur_env = getenv("SCB_SWEEP_KK_CUR");  // experiments: 0 = state_{t-1} re-read from shared memory
+        const int cr = (cur_env && cur_env[0] == '0') ? 0 : 1;
+        const void* kk[2][3] = {{(const void*)koki_plane_kernel<4, false>, (const void*)koki_plane_kernel<8, false>, (const void*)koki_plane_kernel<13, false>},
+                                {(const void*)koki_plane_kernel<4, true>, (const void*)koki_plane_kernel<8, true>, (const void*)koki_plane_kernel<13, true>}};
+        static thread_local SmemMarks kk_marks[2][3];
+        static thread_local SmemMarks kk_carve[2][3];
+        const int v = args.n_nodes <= kKkWarps * 4 ? 0 : args.n_nodes <= kKkWarps * 8 ? 1 : 2;
+        const size_t kk_smem = koki_plane_smem_bytes(args.n_nodes);
+        if (int rc = ensure_dynamic_smem(kk[cr][v], kk_smem, kk_marks[cr][v])) return rc;
+        if (int rc = ensure_max_carveout(kk[cr][v], kk_carve[cr][v])) return rc;
+        void* kargs[1] = {(void*)&args};
+        SCB_CUDA(cudaLaunchKernel(kk[cr][v], grid_k, dim3(kKkThreads), kargs, kk_smem, stream));
+        SCB_LAUNCH_CHECK("koki_plane_kernel");
+    } else {
+        sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(args);
+        SCB_LAUNCH_CHECK("sweep_kernel<koki>");
+    }
     int per_sm = smem <= kMaxDynSmem / 2 ? 2 : 1;
     if (two_level) {
         // slow convergers, compacted: a persistent grid runs the full-length ring on list A

@@ -1,3 +1,5 @@
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_sweep.py tests/test_gpu_fullsize.py tests/test_gpu_entry_points.py -x -q -m gpu 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_sweep.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -3
+SCB_SWEEP_KOKI=old python tools/time_sweep.py | tail -1
 python tools/time_sweep.py | tail -1
+SCB_SWEEP_KK_CUR=0 python tools/time_sweep.py | tail -1
