@@ -1544,11 +1544,95 @@ sweep_kernel(const SweepArgs args) {
 // ---------------------------------------------------------------------------------------
 constexpr int kKkThreads = 512, kKkWarps = 16, kKkSlots = 64;
 constexpr int kKkRow = 2 * kKkSlots;  // words per node: [copy][slot]
+constexpr int kKkRowBytes = kKkRow * 4, kKkCopyBytes = kKkSlots * 4;
 constexpr int kKkTabPad = 16;
 
+// Table entry of a node, 16 bytes, read with broadcast loads (one wavefront for 8 bytes, two for 16):
+//   w0  parent rows A, B, C (bytes 0-2) and the number of bound parents (byte 3)
+//   w1  affine table pairs 0 and 1 as bytes S0, O0, S1, O1 (affine_table: S in {0, 1, -1}, O in {0, ~0})
+//   w2  pairs 2 and 3 (three-parent nodes only)
+// A byte becomes a register operand with one PRMT (sign extension for S, sign replication for O), so a
+// node costs one or two wavefronts of table traffic instead of four to six.
+struct __align__(16) KkEntry {
+    uint32_t w0, w1, w2, w3;
+};
+constexpr int kKkEntryBytes = (int)sizeof(KkEntry);  // 16
+__device__ __forceinline__ uint32_t kk_pack_pairs(const LutMasks& t, int first) {
+    return (t.m[first] & 0xFFu) | ((t.m[first + 1] & 0xFFu) << 8) | ((t.m[first + 2] & 0xFFu) << 16) | ((t.m[first + 3] & 0xFFu) << 24);
+}
+__device__ __forceinline__ KkEntry kk_make_entry(int pa, int pb, int pc, int arity, const LutMasks& t) {
+    KkEntry e;
+    e.w0 = (uint32_t)pa | ((uint32_t)pb << 8) | ((uint32_t)pc << 16) | ((uint32_t)arity << 24);
+    e.w1 = kk_pack_pairs(t, 0);
+    e.w2 = kk_pack_pairs(t, 4);
+    e.w3 = 0u;
+    return e;
+}
+// byte k of w as a multiplier (sign-extended) / as a full-word mask (its sign bit replicated): prmt.b32 with
+// bit 3 of a selector nibble set copies the sign of the selected byte (__byte_perm drops that bit)
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t kk_prmt(uint32_t w) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "n"(SEL));
+    return r;
+}
+template <int K>
+__device__ __forceinline__ uint32_t kk_s(uint32_t w) { return kk_prmt<0x8880u | (uint32_t)K | ((uint32_t)K << 4) | ((uint32_t)K << 8) | ((uint32_t)K << 12)>(w); }
+template <int K>
+__device__ __forceinline__ uint32_t kk_o(uint32_t w) { return kk_prmt<0x8888u | (uint32_t)K | ((uint32_t)K << 4) | ((uint32_t)K << 8) | ((uint32_t)K << 12)>(w); }
+// shared-space address of parent row K of entry word w0 for the slot pair behind `srd`
+template <int K>
+__device__ __forceinline__ uint32_t kk_parent(uint32_t w0, uint32_t srd) { return srd + kk_prmt<0x4440u | (uint32_t)K>(w0) * (uint32_t)kKkRowBytes; }
+
 static size_t koki_plane_smem_bytes(int n_nodes) {
-    return (size_t)(n_nodes + 1) * kKkRow * 4 + (size_t)(n_nodes + kKkTabPad) * (sizeof(int4) + sizeof(LutMasks)) +
-           (size_t)3 * 2 * kKkSlots * 4;
+    return (size_t)(n_nodes + 1) * kKkRowBytes + (size_t)(n_nodes + kKkTabPad) * sizeof(KkEntry) + (size_t)3 * 2 * kKkSlots * 4;
+}
+
+// shared-memory accesses by 32-bit shared-space address.  Loads and stores are volatile asm: they stay in the
+// order they are written, which is how a node's loads get issued together ahead of the previous node's store.
+__device__ __forceinline__ uint2 kk_lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void kk_sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// Value of a node for one slot pair: words w0, w1 of its table entry were fetched one node ahead, parents are
+// read at `srd` (copy, slot pair).  The branch on the number of parents is warp-uniform and does not wait
+// for a load; each arm starts by issuing all of its loads.
+__device__ __forceinline__ uint32_t kk_lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 kk_eval(const uint2 e, uint32_t entry, uint32_t srd) {
+    uint2 f;
+    if (e.x < (2u << 24)) {
+        const uint2 a = kk_lds64(kk_parent<0>(e.x, srd));
+        const uint32_t s = kk_s<0>(e.y), o = kk_o<1>(e.y);
+        f.x = affine(a.x, s, o);
+        f.y = affine(a.y, s, o);
+    } else if (e.x < (3u << 24)) {
+        const uint2 a = kk_lds64(kk_parent<0>(e.x, srd));
+        const uint2 b = kk_lds64(kk_parent<1>(e.x, srd));
+        const uint32_t s0 = kk_s<0>(e.y), o0 = kk_o<1>(e.y), s1 = kk_s<2>(e.y), o1 = kk_o<3>(e.y);
+        f.x = lop3<0xCA>(a.x, affine(b.x, s1, o1), affine(b.x, s0, o0));
+        f.y = lop3<0xCA>(a.y, affine(b.y, s1, o1), affine(b.y, s0, o0));
+    } else {
+        const uint2 a = kk_lds64(kk_parent<0>(e.x, srd));
+        const uint2 b = kk_lds64(kk_parent<1>(e.x, srd));
+        const uint2 c = kk_lds64(kk_parent<2>(e.x, srd));
+        const uint32_t hi = kk_lds32(entry + 8);
+        const uint32_t s0 = kk_s<0>(e.y), o0 = kk_o<1>(e.y), s1 = kk_s<2>(e.y), o1 = kk_o<3>(e.y);
+        const uint32_t s2 = kk_s<0>(hi), o2 = kk_o<1>(hi), s3 = kk_s<2>(hi), o3 = kk_o<3>(hi);
+        f.x = lop3<0xCA>(a.x, lop3<0xCA>(b.x, affine(c.x, s3, o3), affine(c.x, s2, o2)),
+                         lop3<0xCA>(b.x, affine(c.x, s1, o1), affine(c.x, s0, o0)));
+        f.y = lop3<0xCA>(a.y, lop3<0xCA>(b.y, affine(c.y, s3, o3), affine(c.y, s2, o2)),
+                         lop3<0xCA>(b.y, affine(c.y, s1, o1), affine(c.y, s0, o0)));
+    }
+    return f;
 }
 
 // kKkCurRegs: state_{t-1} of the own nodes in registers (else re-read from the copy the step reads)
@@ -1558,10 +1642,9 @@ koki_plane_kernel(const SweepArgs args) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = args.n_nodes;
     const int64_t wpad = args.wpad;
-    uint32_t* state = smem;                                                   // [N + 1][2][64], row N = forced values
-    int4* offs = reinterpret_cast<int4*>(smem + (size_t)(N + 1) * kKkRow);    // [N + pad] parent byte offsets, arity
-    LutMasks* masks = reinterpret_cast<LutMasks*>(offs + N + kKkTabPad);      // [N + pad] affine tables
-    uint32_t* votes = reinterpret_cast<uint32_t*>(masks + N + kKkTabPad);     // [3][2][64]
+    uint32_t* state = smem;                                                      // [N + 1][2][64], row N = forced values
+    KkEntry* table = reinterpret_cast<KkEntry*>(smem + (size_t)(N + 1) * kKkRow);  // [N + pad]
+    uint32_t* votes = reinterpret_cast<uint32_t*>(table + N + kKkTabPad);        // [3][2][64]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int base = N / kKkWarps, rem = N % kKkWarps;
     const int cnt = base + (warp < rem ? 1 : 0);         // nodes of this warp (<= CH)
@@ -1573,20 +1656,14 @@ koki_plane_kernel(const SweepArgs args) {
 
     // ---- tables (the forced node reads the constant row), constant row, vote words
     for (int n = tid; n < N + kKkTabPad; n += kKkThreads) {
-        int4 o = make_int4(0, 0, 0, 0);
-        LutMasks mk = affine_table(0u, 0);
+        KkEntry e = kk_make_entry(0, 0, 0, 0, affine_table(0u, 0));
         if (n < N) {
             int arity;
-            const NodeEntry e = make_entry(args.net_parent, args.net_lut, n, &arity);
-            o = make_int4(e.pa * kKkRow * 4, e.pb * kKkRow * 4, e.pc * kKkRow * 4, arity);
-            mk = affine_table(e.lut, arity);
-            if (n == forced_node) {
-                o = make_int4(N * kKkRow * 4, N * kKkRow * 4, N * kKkRow * 4, 1);
-                mk = affine_table(0xF0u, 1);  // f = A
-            }
+            const NodeEntry ne = make_entry(args.net_parent, args.net_lut, n, &arity);
+            e = kk_make_entry(ne.pa, ne.pb, ne.pc, arity, affine_table(ne.lut, arity));
+            if (n == forced_node) e = kk_make_entry(N, N, N, 1, affine_table(0xF0u, 1));  // f = A, A = the constant row
         }
-        offs[n] = o;
-        masks[n] = mk;
+        table[n] = e;
     }
     if (tid < 2 * kKkSlots) state[(size_t)N * kKkRow + tid] = (tid & 1) ? 0xFFFFFFFFu : 0u;
     for (int i = tid; i < 3 * 2 * kKkSlots; i += kKkThreads) votes[i] = 0u;
@@ -1601,6 +1678,10 @@ koki_plane_kernel(const SweepArgs args) {
         }
         cellmask &= ~hard;
     }
+    // shared-space addresses: (node n, copy k, slot pair of this lane) = s_lane + n * kKkRowBytes + k * kKkCopyBytes
+    const uint32_t s_lane = shared_addr(state) + lane * 8;
+    const uint32_t s_own = s_lane + n0 * kKkRowBytes;
+    const uint32_t s_tab = shared_addr(table) + n0 * kKkEntryBytes;
     // ---- data -> copy 1 (both slots of a word start from the same state)
     uint2 cur[CH];
 #pragma unroll
@@ -1609,7 +1690,7 @@ koki_plane_kernel(const SweepArgs args) {
         if (i < cnt) {
             const uint32_t v = word_ok ? __ldg(args.planes + (size_t)(n0 + i) * wpad + word) : 0u;
             cur[i] = make_uint2(v, v);
-            *reinterpret_cast<uint2*>(state + (size_t)(n0 + i) * kKkRow + kKkSlots + 2 * lane) = cur[i];
+            kk_sts64(s_own + i * kKkRowBytes + kKkCopyBytes, cur[i]);
         }
     }
     __syncthreads();
@@ -1621,54 +1702,24 @@ koki_plane_kernel(const SweepArgs args) {
     unsigned int last_open = 0xFFFFFFFFu;
     int stall = 0;
     bool moved = false;
-    const int stop_open = args.stop_open, stop_stall = args.stop_stall;
     const int t_fast = args.fast_steps > 0 ? min(args.steps, args.fast_steps) : min(args.steps, (int)args.counters[3]);
-    const char* tab_o = reinterpret_cast<const char*>(offs + n0);
-    const char* tab_m = reinterpret_cast<const char*>(masks + n0);
 
-    // value of the node with table entry (o, mk) for both slots, parents read at `srd` (copy, slot pair)
-    auto eval2 = [&](const int4 o, const char* mk, const char* srd) -> uint2 {
-        uint2 f;
-        if (o.w <= 1) {
-            const uint2 so = *reinterpret_cast<const uint2*>(mk);
-            const uint2 a = *reinterpret_cast<const uint2*>(srd + o.x);
-            f.x = affine(a.x, so.x, so.y);
-            f.y = affine(a.y, so.x, so.y);
-            return f;
-        }
-        const uint4 lo = *reinterpret_cast<const uint4*>(mk);
-        const uint2 a = *reinterpret_cast<const uint2*>(srd + o.x);
-        const uint2 b = *reinterpret_cast<const uint2*>(srd + o.y);
-        if (o.w == 2) {
-            f.x = lop3<0xCA>(a.x, affine(b.x, lo.z, lo.w), affine(b.x, lo.x, lo.y));
-            f.y = lop3<0xCA>(a.y, affine(b.y, lo.z, lo.w), affine(b.y, lo.x, lo.y));
-            return f;
-        }
-        const uint4 hi = *reinterpret_cast<const uint4*>(mk + 16);
-        const uint2 c = *reinterpret_cast<const uint2*>(srd + o.z);
-        f.x = lop3<0xCA>(a.x, lop3<0xCA>(b.x, affine(c.x, hi.z, hi.w), affine(c.x, hi.x, hi.y)),
-                         lop3<0xCA>(b.x, affine(c.x, lo.z, lo.w), affine(c.x, lo.x, lo.y)));
-        f.y = lop3<0xCA>(a.y, lop3<0xCA>(b.y, affine(c.y, hi.z, hi.w), affine(c.y, hi.x, hi.y)),
-                         lop3<0xCA>(b.y, affine(c.y, lo.z, lo.w), affine(c.y, lo.x, lo.y)));
-        return f;
-    };
-
-    // one step: reads copy RD (state_{t-1}), writes copy RD ^ 1 (which holds state_{t-2} of the own nodes)
+    // one step: reads copy RD (state_{t-1}), writes copy RD ^ 1 (which holds state_{t-2} of the own nodes).
+    // Per node: the table entry was fetched one node ahead; parents, table words, state_{t-2} (and state_{t-1})
+    // are requested together, then the value, the two compares, the freeze merge and the store.
     auto step = [&](auto rd_tag, int t) -> bool {
         constexpr int RD = decltype(rd_tag)::value, WR = RD ^ 1;
-        const char* srd = reinterpret_cast<const char*>(state + RD * kKkSlots + 2 * lane);
-        uint32_t* own_wr = state + (size_t)n0 * kKkRow + WR * kKkSlots + 2 * lane;
-        const uint32_t* own_rd = state + (size_t)n0 * kKkRow + RD * kKkSlots + 2 * lane;
+        const uint32_t srd = s_lane + RD * kKkCopyBytes;
         uint32_t q1x = 0, q1y = 0, q2x = 0, q2y = 0;
-        int4 o_next = *reinterpret_cast<const int4*>(tab_o);
+        uint2 e_next = kk_lds64(s_tab);
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-            const int4 o = o_next;
-            if (i + 1 < CH) o_next = *reinterpret_cast<const int4*>(tab_o + (i + 1) * 16);  // (tables are padded)
+            const uint2 e = e_next;
+            if (i + 1 < CH) e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);  // (the table is padded)
             if (i < cnt) {
-                const uint2 old2 = *reinterpret_cast<const uint2*>(own_wr + i * kKkRow);
-                const uint2 c1 = kKkCurRegs ? cur[i] : *reinterpret_cast<const uint2*>(own_rd + i * kKkRow);
-                const uint2 f = eval2(o, tab_m + i * 32, srd);
+                const uint2 old2 = kk_lds64(s_own + i * kKkRowBytes + WR * kKkCopyBytes);
+                const uint2 c1 = kKkCurRegs ? cur[i] : kk_lds64(s_own + i * kKkRowBytes + RD * kKkCopyBytes);
+                const uint2 f = kk_eval(e, s_tab + i * kKkEntryBytes, srd);
                 q1x |= f.x ^ c1.x;
                 q1y |= f.y ^ c1.y;
                 q2x |= f.x ^ old2.x;
@@ -1676,7 +1727,7 @@ koki_plane_kernel(const SweepArgs args) {
                 uint2 w;
                 w.x = (f.x & ~frozen0) | (c1.x & frozen0);
                 w.y = (f.y & ~frozen1) | (c1.y & frozen1);
-                *reinterpret_cast<uint2*>(own_wr + i * kKkRow) = w;
+                kk_sts64(s_own + i * kKkRowBytes + WR * kKkCopyBytes, w);
                 if (kKkCurRegs) cur[i] = w;
             }
         }
@@ -1705,12 +1756,12 @@ koki_plane_kernel(const SweepArgs args) {
         frozen1 |= e1 | e2;
         // every warp holds the frozen masks of all 64 slots: the stop rule needs no barrier (ring2_registers)
         const unsigned int n_open = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)(__popc(~frozen0) + __popc(~frozen1)));
-        if (n_open <= (unsigned int)stop_open) return true;
+        if (n_open <= (unsigned int)args.stop_open) return true;
         if (n_open < last_open) {
             moved = last_open != 0xFFFFFFFFu;
             last_open = n_open;
             stall = 0;
-        } else if (moved && ++stall >= stop_stall) {
+        } else if (moved && ++stall >= args.stop_stall) {
             return true;
         }
         const int vclear = vset == 0 ? 2 : vset - 1;  // (t + 2) % 3: every reader is past the barrier of step t + 1 by then
@@ -1754,8 +1805,7 @@ koki_plane_kernel(const SweepArgs args) {
     }
     unsigned long long score = 0;
     if (__any_sync(0xFFFFFFFFu, valid != 0)) {
-        const char* srd = reinterpret_cast<const char*>(state + xs * kKkSlots + 2 * lane);
-        const uint32_t* own = state + (size_t)n0 * kKkRow + xs * kKkSlots + 2 * lane;
+        const uint32_t srd = s_lane + xs * kKkCopyBytes;
         const bool cyc = __any_sync(0xFFFFFFFFu, (valid & (lam1_0 | lam1_1 | lamn_ge2)) != 0);
         const uint32_t act2_0 = valid & lam1_0 & lamn_ge2, act2_1 = valid & lam1_1 & lamn_ge2;
         const bool any2 = __any_sync(0xFFFFFFFFu, (act2_0 | act2_1) != 0);
@@ -1764,11 +1814,11 @@ koki_plane_kernel(const SweepArgs args) {
         for (int i = 0; i < CH; ++i) {
             if (i < cnt) {
                 const size_t at = (size_t)(n0 + i) * wpad + word;
-                const uint2 s = *reinterpret_cast<const uint2*>(own + i * kKkRow);
+                const uint2 s = kk_lds64(s_own + i * kKkRowBytes + xs * kKkCopyBytes);
                 const uint32_t ref0 = word_ok ? __ldg(args.np_states + at) : 0u;
                 sc += __popc((s.x ^ ref0) & valid) + __popc((s.y ^ ref0) & valid);
                 if (cyc) {
-                    const uint2 f = eval2(*reinterpret_cast<const int4*>(tab_o + i * 16), tab_m + i * 32, srd);
+                    const uint2 f = kk_eval(kk_lds64(s_tab + i * kKkEntryBytes), s_tab + i * kKkEntryBytes, srd);
                     const uint32_t ref1 = word_ok ? __ldg(args.np_states + (size_t)N * wpad + at) : 0u;
                     sc1 += __popc((f.x ^ ref1) & valid) + __popc((f.y ^ ref1) & valid);
                     if (any2) {
