@@ -1584,8 +1584,12 @@ __device__ __forceinline__ uint32_t kk_o(uint32_t w) { return kk_prmt<0x8888u | 
 template <int K>
 __device__ __forceinline__ uint32_t kk_parent(uint32_t w0, uint32_t srd) { return srd + kk_prmt<0x4440u | (uint32_t)K>(w0) * (uint32_t)kKkRowBytes; }
 
+// nodes per warp: the node rows are padded with do-nothing nodes to a multiple of the warp count, so every warp
+// owns exactly the same number and the unrolled loop has no "does this node exist" test
+static inline int koki_plane_cnt(int n_nodes) { return (n_nodes + kKkWarps - 1) / kKkWarps; }
 static size_t koki_plane_smem_bytes(int n_nodes) {
-    return (size_t)(n_nodes + 1) * kKkRowBytes + (size_t)(n_nodes + kKkTabPad) * sizeof(KkEntry) + (size_t)3 * 2 * kKkSlots * 4;
+    const int n_pad = koki_plane_cnt(n_nodes) * kKkWarps;
+    return (size_t)(n_pad + 1) * kKkRowBytes + (size_t)(n_pad + kKkTabPad) * sizeof(KkEntry) + (size_t)3 * 2 * kKkSlots * 4;
 }
 
 // shared-memory accesses by 32-bit shared-space address.  Loads and stores are volatile asm: they stay in the
@@ -1635,37 +1639,35 @@ __device__ __forceinline__ uint2 kk_eval(const uint2 e, uint32_t entry, uint32_t
     return f;
 }
 
-// kKkCurRegs: state_{t-1} of the own nodes in registers (else re-read from the copy the step reads)
-template <int CH, bool kKkCurRegs>
+template <int CNT>  // nodes per warp
 __global__ void __launch_bounds__(kKkThreads, 2)
 koki_plane_kernel(const SweepArgs args) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = args.n_nodes;
+    constexpr int NP = CNT * kKkWarps;  // node rows incl. the padding; row NP = forced values
     const int64_t wpad = args.wpad;
-    uint32_t* state = smem;                                                      // [N + 1][2][64], row N = forced values
-    KkEntry* table = reinterpret_cast<KkEntry*>(smem + (size_t)(N + 1) * kKkRow);  // [N + pad]
-    uint32_t* votes = reinterpret_cast<uint32_t*>(table + N + kKkTabPad);        // [3][2][64]
+    uint32_t* state = smem;                                                       // [NP + 1][2][64]
+    KkEntry* table = reinterpret_cast<KkEntry*>(smem + (size_t)(NP + 1) * kKkRow);  // [NP + pad]
+    uint32_t* votes = reinterpret_cast<uint32_t*>(table + NP + kKkTabPad);        // [3][2][64]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int base = N / kKkWarps, rem = N % kKkWarps;
-    const int cnt = base + (warp < rem ? 1 : 0);         // nodes of this warp (<= CH)
-    const int n0 = warp * base + min(warp, rem);
+    const int n0 = warp * CNT;
     const int forced_node = (int)(blockIdx.x % (unsigned)N);
     const int64_t word = (int64_t)(blockIdx.x / (unsigned)N) * 32 + lane;
     const bool word_ok = word < wpad;
     uint32_t cellmask = word_ok ? tail_mask(word, args.n_cells) : 0u;
 
-    // ---- tables (the forced node reads the constant row), constant row, vote words
-    for (int n = tid; n < N + kKkTabPad; n += kKkThreads) {
-        KkEntry e = kk_make_entry(0, 0, 0, 0, affine_table(0u, 0));
+    // ---- tables (the forced node reads the constant row; a padding node is constant 0), constant row, vote words
+    for (int n = tid; n < NP + kKkTabPad; n += kKkThreads) {
+        KkEntry e = kk_make_entry(n < NP ? n : 0, 0, 0, 0, affine_table(0u, 0));
         if (n < N) {
             int arity;
             const NodeEntry ne = make_entry(args.net_parent, args.net_lut, n, &arity);
             e = kk_make_entry(ne.pa, ne.pb, ne.pc, arity, affine_table(ne.lut, arity));
-            if (n == forced_node) e = kk_make_entry(N, N, N, 1, affine_table(0xF0u, 1));  // f = A, A = the constant row
+            if (n == forced_node) e = kk_make_entry(NP, NP, NP, 1, affine_table(0xF0u, 1));  // f = A, A = the constant row
         }
         table[n] = e;
     }
-    if (tid < 2 * kKkSlots) state[(size_t)N * kKkRow + tid] = (tid & 1) ? 0xFFFFFFFFu : 0u;
+    if (tid < 2 * kKkSlots) state[(size_t)NP * kKkRow + tid] = (tid & 1) ? 0xFFFFFFFFu : 0u;
     for (int i = tid; i < 3 * 2 * kKkSlots; i += kKkThreads) votes[i] = 0u;
     // cells whose unperturbed run needed the general scheme go straight to the cleanup list (see sweep_kernel)
     {
@@ -1682,16 +1684,13 @@ koki_plane_kernel(const SweepArgs args) {
     const uint32_t s_lane = shared_addr(state) + lane * 8;
     const uint32_t s_own = s_lane + n0 * kKkRowBytes;
     const uint32_t s_tab = shared_addr(table) + n0 * kKkEntryBytes;
-    // ---- data -> copy 1 (both slots of a word start from the same state)
-    uint2 cur[CH];
+    // ---- data -> copy 1 (both slots of a word start from the same state); padding rows: zero in both copies
 #pragma unroll
-    for (int i = 0; i < CH; ++i) {
-        cur[i] = make_uint2(0u, 0u);
-        if (i < cnt) {
-            const uint32_t v = word_ok ? __ldg(args.planes + (size_t)(n0 + i) * wpad + word) : 0u;
-            cur[i] = make_uint2(v, v);
-            kk_sts64(s_own + i * kKkRowBytes + kKkCopyBytes, cur[i]);
-        }
+    for (int i = 0; i < CNT; ++i) {
+        const bool real = n0 + i < N;
+        const uint32_t v = (real && word_ok) ? __ldg(args.planes + (size_t)(n0 + i) * wpad + word) : 0u;
+        kk_sts64(s_own + i * kKkRowBytes + kKkCopyBytes, make_uint2(v, v));
+        if (!real) kk_sts64(s_own + i * kKkRowBytes, make_uint2(0u, 0u));
     }
     __syncthreads();
 
@@ -1705,31 +1704,28 @@ koki_plane_kernel(const SweepArgs args) {
     const int t_fast = args.fast_steps > 0 ? min(args.steps, args.fast_steps) : min(args.steps, (int)args.counters[3]);
 
     // one step: reads copy RD (state_{t-1}), writes copy RD ^ 1 (which holds state_{t-2} of the own nodes).
-    // Per node: the table entry was fetched one node ahead; parents, table words, state_{t-2} (and state_{t-1})
-    // are requested together, then the value, the two compares, the freeze merge and the store.
+    // Per node: the table entry was fetched one node ahead; parents, state_{t-2} and state_{t-1} of the node are
+    // requested together, then the value, the two compares, the freeze merge and the store.
     auto step = [&](auto rd_tag, int t) -> bool {
         constexpr int RD = decltype(rd_tag)::value, WR = RD ^ 1;
         const uint32_t srd = s_lane + RD * kKkCopyBytes;
         uint32_t q1x = 0, q1y = 0, q2x = 0, q2y = 0;
         uint2 e_next = kk_lds64(s_tab);
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
+        for (int i = 0; i < CNT; ++i) {
             const uint2 e = e_next;
-            if (i + 1 < CH) e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);  // (the table is padded)
-            if (i < cnt) {
-                const uint2 old2 = kk_lds64(s_own + i * kKkRowBytes + WR * kKkCopyBytes);
-                const uint2 c1 = kKkCurRegs ? cur[i] : kk_lds64(s_own + i * kKkRowBytes + RD * kKkCopyBytes);
-                const uint2 f = kk_eval(e, s_tab + i * kKkEntryBytes, srd);
-                q1x |= f.x ^ c1.x;
-                q1y |= f.y ^ c1.y;
-                q2x |= f.x ^ old2.x;
-                q2y |= f.y ^ old2.y;
-                uint2 w;
-                w.x = (f.x & ~frozen0) | (c1.x & frozen0);
-                w.y = (f.y & ~frozen1) | (c1.y & frozen1);
-                kk_sts64(s_own + i * kKkRowBytes + WR * kKkCopyBytes, w);
-                if (kKkCurRegs) cur[i] = w;
-            }
+            if (i + 1 < CNT) e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
+            const uint2 old2 = kk_lds64(s_own + i * kKkRowBytes + WR * kKkCopyBytes);
+            const uint2 c1 = kk_lds64(s_own + i * kKkRowBytes + RD * kKkCopyBytes);
+            const uint2 f = kk_eval(e, s_tab + i * kKkEntryBytes, srd);
+            q1x |= f.x ^ c1.x;
+            q1y |= f.y ^ c1.y;
+            q2x |= f.x ^ old2.x;
+            q2y |= f.y ^ old2.y;
+            uint2 w;
+            w.x = (f.x & ~frozen0) | (c1.x & frozen0);
+            w.y = (f.y & ~frozen1) | (c1.y & frozen1);
+            kk_sts64(s_own + i * kKkRowBytes + WR * kKkCopyBytes, w);
         }
         uint32_t* v = votes + vset * 2 * kKkSlots;
         if (q1x) atomicOr(v + 2 * lane, q1x);
@@ -1811,8 +1807,8 @@ koki_plane_kernel(const SweepArgs args) {
         const bool any2 = __any_sync(0xFFFFFFFFu, (act2_0 | act2_1) != 0);
         uint32_t sc = 0, sc1 = 0;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            if (i < cnt) {
+        for (int i = 0; i < CNT; ++i) {
+            if (n0 + i < N) {
                 const size_t at = (size_t)(n0 + i) * wpad + word;
                 const uint2 s = kk_lds64(s_own + i * kKkRowBytes + xs * kKkCopyBytes);
                 const uint32_t ref0 = word_ok ? __ldg(args.np_states + at) : 0u;
@@ -2013,18 +2009,20 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
     const bool plane2 = SLOTS == 64 && two_level && args.n_nodes <= kKkWarps * 13 && !(koki_env && koki_env[0] == 'o') &&
                         koki_plane_smem_bytes(args.n_nodes) <= kMaxDynSmem;
     if (plane2) {
-        const char* cur_env = getenv("SCB_SWEEP_KK_CUR");  // experiments: 0 = state_{t-1} re-read from shared memory
-        const int cr = (cur_env && cur_env[0] == '0') ? 0 : 1;
-        const void* kk[2][3] = {{(const void*)koki_plane_kernel<4, false>, (const void*)koki_plane_kernel<8, false>, (const void*)koki_plane_kernel<13, false>},
-                                {(const void*)koki_plane_kernel<4, true>, (const void*)koki_plane_kernel<8, true>, (const void*)koki_plane_kernel<13, true>}};
-        static thread_local SmemMarks kk_marks[2][3];
-        static thread_local SmemMarks kk_carve[2][3];
-        const int v = args.n_nodes <= kKkWarps * 4 ? 0 : args.n_nodes <= kKkWarps * 8 ? 1 : 2;
+        static const void* const kk[13] = {
+            (const void*)koki_plane_kernel<1>, (const void*)koki_plane_kernel<2>, (const void*)koki_plane_kernel<3>,
+            (const void*)koki_plane_kernel<4>, (const void*)koki_plane_kernel<5>, (const void*)koki_plane_kernel<6>,
+            (const void*)koki_plane_kernel<7>, (const void*)koki_plane_kernel<8>, (const void*)koki_plane_kernel<9>,
+            (const void*)koki_plane_kernel<10>, (const void*)koki_plane_kernel<11>, (const void*)koki_plane_kernel<12>,
+            (const void*)koki_plane_kernel<13>};
+        static thread_local SmemMarks kk_marks[13];
+        static thread_local SmemMarks kk_carve[13];
+        const int v = koki_plane_cnt(args.n_nodes) - 1;
         const size_t kk_smem = koki_plane_smem_bytes(args.n_nodes);
-        if (int rc = ensure_dynamic_smem(kk[cr][v], kk_smem, kk_marks[cr][v])) return rc;
-        if (int rc = ensure_max_carveout(kk[cr][v], kk_carve[cr][v])) return rc;
+        if (int rc = ensure_dynamic_smem(kk[v], kk_smem, kk_marks[v])) return rc;
+        if (int rc = ensure_max_carveout(kk[v], kk_carve[v])) return rc;
         void* kargs[1] = {(void*)&args};
-        SCB_CUDA(cudaLaunchKernel(kk[cr][v], grid_k, dim3(kKkThreads), kargs, kk_smem, stream));
+        SCB_CUDA(cudaLaunchKernel(kk[v], grid_k, dim3(kKkThreads), kargs, kk_smem, stream));
         SCB_LAUNCH_CHECK("koki_plane_kernel");
     } else {
         sweep_kernel<SLOTS, MODE_KOKI><<<grid_k, kSweepThreads, smem, stream>>>(args);
