@@ -236,6 +236,39 @@ def test_sweep_general_tables_and_parent_holes_vs_c_oracle(cuda, monkeypatch, n_
         assert (raw.cpu().numpy() == w_raw).all()
 
 
+@pytest.mark.parametrize("n_nodes,koki", [(5, "plane"), (16, "plane"), (17, "plane"), (40, "plane"), (49, "plane"),
+                                          (70, "plane"), (96, "plane"), (111, "plane"), (113, "plane"), (140, "plane"),
+                                          (160, "plane"), (176, "plane"), (177, "plane"), (193, "plane"), (208, "plane"),
+                                          (70, "old"), (177, "old"), (200, "old")])
+def test_sweep_koki_kernels_vs_c_oracle(cuda, monkeypatch, n_nodes, koki):
+    """The KO/KI pass on the plane words has two implementations: ``koki_plane_kernel<CNT>`` (two CTAs per SM,
+    CNT = ceil(N / 16) nodes per warp, node rows padded to 16 * CNT: every CNT from 1 to 13 is hit here, with
+    and without padding rows) and ``sweep_kernel<64, MODE_KOKI>`` (``SCB_SWEEP_KOKI=old``).  Both must give
+    the cell-by-cell oracle's integers on mixed dynamics (fixed points, period 2, longer cycles, no repeat)."""
+    from oracle import cport
+    from scbonita2_b200 import device
+    rng = np.random.default_rng(n_nodes)
+    n_cells, steps = 1300, 50
+    parents = np.full((n_nodes, 3), -1, dtype=np.int32)
+    for n in range(n_nodes):
+        bound = rng.random(3) < 0.6
+        parents[n, bound] = rng.integers(0, n_nodes, int(bound.sum()))
+    luts = np.where(rng.random(n_nodes) < 0.6, rng.choice([0xF0, 0xCC, 0xAA, 0x80, 0xFE, 0xE8, 0x0F, 0x33], n_nodes),
+                    rng.integers(0, 256, n_nodes)).astype(np.uint8)
+    planes_np = synth.random_planes(n_nodes, n_cells, 11 + n_nodes, density=0.4)
+    monkeypatch.delenv("SCB_SWEEP_FAST_STEPS", raising=False)
+    if koki == "old":
+        monkeypatch.setenv("SCB_SWEEP_KOKI", "old")
+    else:
+        monkeypatch.delenv("SCB_SWEEP_KOKI", raising=False)
+    raw, missing, keyerr = device.ko_ki_sweep(device.BitPlanes.from_packed(planes_np, n_cells), parents, luts, steps)
+    w_raw, w_missing, w_key = cport.importance_raw(synth.planes_to_dense(planes_np, n_cells), parents, luts, steps)
+    assert int(keyerr.item()) == w_key
+    assert (missing.cpu().numpy() == w_missing).all()
+    if w_key == 0:
+        assert (raw.cpu().numpy() == w_raw).all()
+
+
 def test_trajectories_with_parent_holes_vs_c_oracle(cuda):
     """Parent slots bound in any pattern and arbitrary tables through scb_trajectories_forced."""
     from oracle import cport
