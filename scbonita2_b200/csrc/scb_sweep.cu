@@ -1581,8 +1581,8 @@ __device__ __forceinline__ uint32_t kk_s(uint32_t w) { return kk_prmt<0x8880u | 
 template <int K>
 __device__ __forceinline__ uint32_t kk_o(uint32_t w) { return kk_prmt<0x8888u | (uint32_t)K | ((uint32_t)K << 4) | ((uint32_t)K << 8) | ((uint32_t)K << 12)>(w); }
 // shared-space address of parent row K of entry word w0 for the slot pair behind `srd`
-template <int K>
-__device__ __forceinline__ uint32_t kk_parent(uint32_t w0, uint32_t srd) { return srd + kk_prmt<0x4440u | (uint32_t)K>(w0) * (uint32_t)kKkRowBytes; }
+template <int K, int ROWB>
+__device__ __forceinline__ uint32_t kk_parent(uint32_t w0, uint32_t srd) { return srd + kk_prmt<0x4440u | (uint32_t)K>(w0) * (uint32_t)ROWB; }
 
 // nodes per warp: the node rows are padded with do-nothing nodes to a multiple of the warp count, so every warp
 // owns exactly the same number and the unrolled loop has no "does this node exist" test
@@ -1611,23 +1611,24 @@ __device__ __forceinline__ uint32_t kk_lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+template <int ROWB = kKkRowBytes>  // bytes between the rows of two nodes
 __device__ __forceinline__ uint2 kk_eval(const uint2 e, uint32_t entry, uint32_t srd) {
     uint2 f;
     if (e.x < (2u << 24)) {
-        const uint2 a = kk_lds64(kk_parent<0>(e.x, srd));
+        const uint2 a = kk_lds64(kk_parent<0, ROWB>(e.x, srd));
         const uint32_t s = kk_s<0>(e.y), o = kk_o<1>(e.y);
         f.x = affine(a.x, s, o);
         f.y = affine(a.y, s, o);
     } else if (e.x < (3u << 24)) {
-        const uint2 a = kk_lds64(kk_parent<0>(e.x, srd));
-        const uint2 b = kk_lds64(kk_parent<1>(e.x, srd));
+        const uint2 a = kk_lds64(kk_parent<0, ROWB>(e.x, srd));
+        const uint2 b = kk_lds64(kk_parent<1, ROWB>(e.x, srd));
         const uint32_t s0 = kk_s<0>(e.y), o0 = kk_o<1>(e.y), s1 = kk_s<2>(e.y), o1 = kk_o<3>(e.y);
         f.x = lop3<0xCA>(a.x, affine(b.x, s1, o1), affine(b.x, s0, o0));
         f.y = lop3<0xCA>(a.y, affine(b.y, s1, o1), affine(b.y, s0, o0));
     } else {
-        const uint2 a = kk_lds64(kk_parent<0>(e.x, srd));
-        const uint2 b = kk_lds64(kk_parent<1>(e.x, srd));
-        const uint2 c = kk_lds64(kk_parent<2>(e.x, srd));
+        const uint2 a = kk_lds64(kk_parent<0, ROWB>(e.x, srd));
+        const uint2 b = kk_lds64(kk_parent<1, ROWB>(e.x, srd));
+        const uint2 c = kk_lds64(kk_parent<2, ROWB>(e.x, srd));
         const uint32_t hi = kk_lds32(entry + 8);
         const uint32_t s0 = kk_s<0>(e.y), o0 = kk_o<1>(e.y), s1 = kk_s<2>(e.y), o1 = kk_o<3>(e.y);
         const uint32_t s2 = kk_s<0>(hi), o2 = kk_o<1>(hi), s3 = kk_s<2>(hi), o3 = kk_o<3>(hi);
@@ -1829,6 +1830,425 @@ koki_plane_kernel(const SweepArgs args) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
     if (lane == 0 && score) atomicAdd(args.out_raw + forced_node, score);
+}
+
+// ---------------------------------------------------------------------------------------
+// Cleanup pass (compacted cells, the general scheme), written like koki_plane_kernel.
+//
+// Same work and the same results as sweep_kernel<64, MODE_CLEANUP> with brent_registers / replay_registers:
+// a batch is 1024 deferred cells of one forced node gathered into 32 virtual words, slot 2v = KO and 2v + 1 = KI
+// of virtual word v; Brent checkpoints give lambda, two replays from the data (P runs lambda_cell steps ahead
+// of Q under per-cell stall masks) give mu and leave Q frozen at state_mu; scoring steps the frozen states
+// along the stored normal-run states.  What changed is the machinery: 768 threads (24 warps, six per
+// scheduler instead of four; 80 registers), nodes dealt evenly (N / 24 or N / 24 + 1 per warp, the kernel is
+// instantiated per N / 24 so only the last position carries a test), 64-bit KO/KI pairs, 16-byte packed table
+// entries fetched one node ahead, the forced node as a constant row, parents by shared-space address -- and
+// every warp holds the masks of all 64 slots (a lane is a virtual word, all warps read the same votes), so
+// "is any lane left" is a warp vote instead of a barrier reduction: ONE barrier per step in every phase.
+// The cells are gathered once per batch (a pristine copy of the data stays in state copy 2 while the Brent
+// phase runs in copies 0 / 1), lambda / cyc / fixed-point planes are kept by warp 0 in shared memory during
+// the Brent phase (registers there hold the previous state and the checkpoint of the own nodes).
+// ---------------------------------------------------------------------------------------
+constexpr int kKcThreads = 768, kKcWarps = kKcThreads / 32;
+constexpr int kKcRowBytes = 4 * kKkSlots * 4, kKcCopyBytes = kKkSlots * 4;  // [node][4 copies][64 slots]
+constexpr int kKcBatchCells = 32 * 32;
+
+static size_t koki_cleanup_smem_bytes(int n_nodes) {
+    return (size_t)(n_nodes + 1) * kKcRowBytes + (size_t)(n_nodes + kKkTabPad) * sizeof(KkEntry) + (size_t)3 * 2 * kKkSlots * 4 +
+           (size_t)8 * kKkSlots * 4 + (size_t)kKcBatchCells * 4 + (size_t)(1 + kLamPlanes) * 32 * 4 + (size_t)(n_nodes + 1) * 4;
+}
+
+template <int BASE, typename F>
+__device__ __forceinline__ void kc_for_own(bool extra, F&& f) {
+#pragma unroll
+    for (int i = 0; i < BASE; ++i) f(i);
+    if (extra) f(BASE);
+}
+
+template <int BASE>  // N / 24: every warp owns BASE nodes, the first N % 24 warps one more
+__global__ void __launch_bounds__(kKcThreads, 1)
+koki_cleanup_kernel(const SweepArgs args) {
+    constexpr int MODE = MODE_CLEANUP;  // (trace macros)
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int N = args.n_nodes;
+    const int steps = args.steps;
+    uint32_t* state = smem;                                                         // [N + 1][4][64], row N = forced values
+    KkEntry* table = reinterpret_cast<KkEntry*>(smem + (size_t)(N + 1) * 4 * kKkSlots);  // [N + pad]
+    uint32_t* votes = reinterpret_cast<uint32_t*>(table + N + kKkTabPad);           // [3][2][64]
+    uint32_t* res = votes + 3 * 2 * kKkSlots;                                       // [8][64]: lambda planes, cyc, fixed point
+    int* cellidx = reinterpret_cast<int*>(res + 8 * kKkSlots);                      // [32][32]
+    uint32_t* nrm = reinterpret_cast<uint32_t*>(cellidx + kKcBatchCells);           // [1 + kLamPlanes][32]
+    int* pre = reinterpret_cast<int*>(nrm + (1 + kLamPlanes) * 32);                 // [N + 1]
+    __shared__ int s_node;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef SCB_TRACE
+    long long trace_t_ = clock64();
+#endif
+    const int rem = N - BASE * kKcWarps;  // 0 <= rem < 24 by the choice of BASE
+    const bool extra = warp < rem;
+    const int n0 = warp * BASE + min(warp, rem);
+    const int cnt = BASE + (extra ? 1 : 0);
+
+    for (int n = tid; n < N + kKkTabPad; n += kKcThreads) {
+        KkEntry e = kk_make_entry(0, 0, 0, 0, affine_table(0u, 0));
+        if (n < N) {
+            int arity;
+            const NodeEntry ne = make_entry(args.net_parent, args.net_lut, n, &arity);
+            e = kk_make_entry(ne.pa, ne.pb, ne.pc, arity, affine_table(ne.lut, arity));
+        }
+        table[n] = e;
+    }
+    if (tid < 4 * kKkSlots) state[(size_t)N * 4 * kKkSlots + tid] = (tid & 1) ? 0xFFFFFFFFu : 0u;
+    if (tid == 0) {
+        int acc = 0;
+        for (int k = 0; k < N; ++k) {
+            pre[k] = acc;
+            int64_t c = args.in_count[k];
+            if (c > args.in_cap) c = args.in_cap;
+            acc += (int)((c + kKcBatchCells - 1) / kKcBatchCells);
+        }
+        pre[N] = acc;
+    }
+    __syncthreads();
+    const int total_batches = pre[N];
+    const uint32_t s_lane = shared_addr(state) + lane * 8;
+    const uint32_t s_own = s_lane + n0 * kKcRowBytes;
+    const uint32_t s_tab = shared_addr(table) + n0 * kKkEntryBytes;
+    int prev_forced = -1;
+
+    // copy k of every node, both slots, from the cell-major records of the batch's cells (`src_t`), through the
+    // staging copy kstage: one warp per virtual word, lane = cell, 128-bit loads fetch its record, every record
+    // word goes through a 32 x 32 warp transpose (lane b gets node 32j + b) and is parked at a pair position
+    // rotated by the node index (the lanes of a warp hold different nodes, whose rows start on the same bank);
+    // after a barrier every thread moves the pairs of its own nodes into place -- in copy k and, if k2 >= 0, in k2.
+    auto gather = [&](const uint32_t* __restrict__ src_t, int k, int k2, int kstage) {
+        const int nwp = args.nwp;
+        for (int v0 = warp; v0 < 32; v0 += 2 * kKcWarps) {
+            const int v1 = v0 + kKcWarps;
+            const int c0 = cellidx[v0 * 32 + lane];
+            const int c1 = v1 < 32 ? cellidx[v1 * 32 + lane] : -1;
+            for (int j4 = 0; j4 < nwp; j4 += 4) {
+                uint4 x0 = make_uint4(0u, 0u, 0u, 0u), x1 = x0;
+                if (c0 >= 0) x0 = __ldg(reinterpret_cast<const uint4*>(src_t + (size_t)c0 * nwp + j4));
+                if (c1 >= 0) x1 = __ldg(reinterpret_cast<const uint4*>(src_t + (size_t)c1 * nwp + j4));
+                const uint32_t xw[2][4] = {{x0.x, x0.y, x0.z, x0.w}, {x1.x, x1.y, x1.z, x1.w}};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int v = h ? v1 : v0;
+                    if (v >= 32) break;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int nb = (j4 + q) * 32;
+                        if (nb < N) {
+                            const uint32_t mine = warp_transpose32(xw[h][q], lane);
+                            const int n = nb + lane;
+                            if (n < N)
+                                *reinterpret_cast<uint2*>(state + ((size_t)n * 4 + kstage) * kKkSlots + 2 * ((v + n) & 31)) = make_uint2(mine, mine);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        kc_for_own<BASE>(extra, [&](int i) {
+            const uint2 x = kk_lds64(shared_addr(state) + (uint32_t)(n0 + i) * kKcRowBytes + kstage * kKcCopyBytes + 8 * ((lane + n0 + i) & 31));
+            kk_sts64(s_own + i * kKcRowBytes + k * kKcCopyBytes, x);
+            if (k2 >= 0) kk_sts64(s_own + i * kKcRowBytes + k2 * kKcCopyBytes, x);
+        });
+    };
+
+    for (int batch = blockIdx.x; batch < total_batches; batch += gridDim.x) {
+        // ------------------------------------------------------------ the batch: node, cells, table patch
+        if (tid == 0) {
+            int lo = 0, hi = N;  // largest k with pre[k] <= batch
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pre[mid] <= batch) lo = mid; else hi = mid;
+            }
+            s_node = lo;
+        }
+        __syncthreads();
+        const int forced_node = s_node;
+        int64_t n_in = args.in_count[forced_node];
+        if (n_in > args.in_cap) n_in = args.in_cap;
+        const int64_t batch_first = (int64_t)(batch - pre[forced_node]) * kKcBatchCells;
+        for (int i = tid; i < kKcBatchCells; i += kKcThreads)
+            cellidx[i] = batch_first + i < n_in ? args.in_cells[(size_t)forced_node * args.in_cap + batch_first + i] : -1;
+        if (forced_node != prev_forced && tid == 0) {
+            if (prev_forced >= 0) {
+                int arity;
+                const NodeEntry ne = make_entry(args.net_parent, args.net_lut, prev_forced, &arity);
+                table[prev_forced] = kk_make_entry(ne.pa, ne.pb, ne.pc, arity, affine_table(ne.lut, arity));
+            }
+            table[forced_node] = kk_make_entry(N, N, N, 1, affine_table(0xF0u, 1));  // f = A, A = the constant row
+        }
+        prev_forced = forced_node;
+        for (int i = tid; i < 3 * 2 * kKkSlots + 8 * kKkSlots; i += kKcThreads) votes[i] = 0u;  // votes and res
+        const int64_t left = n_in - (batch_first + (int64_t)lane * 32);
+        const uint32_t cellmask = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << (int)left) - 1u : 0u);
+        __syncthreads();
+        SCB_SWEEP_PHASE(0);
+
+        // ------------------------------------------------------------ Brent phase: copies 0 / 1, data kept in copy 2
+        gather(args.planes_t, 0, 2, 3);
+        uint2 cur[BASE + 1], chk[BASE + 1];
+        kc_for_own<BASE>(extra, [&](int i) {
+            cur[i] = kk_lds64(s_own + i * kKcRowBytes);
+            chk[i] = make_uint2(0u, 0u);
+        });
+        __syncthreads();
+        uint32_t resolved0 = ~cellmask, resolved1 = ~cellmask;
+        int chk_time = -1;
+        int vset = 0;
+        const int t1_max = 2 * steps - 1;  // checkpoints at t = 2^k - 1 < steps - 1 and a last one at steps - 1 (see sweep_kernel)
+        auto brent_step = [&](auto rd_tag, int t) -> bool {
+            constexpr int RD = decltype(rd_tag)::value, WR = RD ^ 1;
+            const uint32_t srd = s_lane + RD * kKcCopyBytes;
+            uint32_t qpx = 0, qpy = 0, qcx = 0, qcy = 0;
+            uint2 e_next = kk_lds64(s_tab);
+            kc_for_own<BASE>(extra, [&](int i) {
+                const uint2 e = e_next;
+                e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);  // (the table is padded)
+                const uint2 f = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, srd);
+                qpx |= f.x ^ cur[i].x;
+                qpy |= f.y ^ cur[i].y;
+                qcx |= f.x ^ chk[i].x;
+                qcy |= f.y ^ chk[i].y;
+                kk_sts64(s_own + i * kKcRowBytes + WR * kKcCopyBytes, f);
+                cur[i] = f;
+            });
+            uint32_t* v = votes + vset * 2 * kKkSlots;
+            if (qpx) atomicOr(v + 2 * lane, qpx);
+            if (qpy) atomicOr(v + 2 * lane + 1, qpy);
+            if (chk_time >= 0) {
+                if (qcx) atomicOr(v + kKkSlots + 2 * lane, qcx);
+                if (qcy) atomicOr(v + kKkSlots + 2 * lane + 1, qcy);
+            }
+            __syncthreads();
+            const uint2 np = *reinterpret_cast<const uint2*>(v + 2 * lane);
+            const uint2 nc = *reinterpret_cast<const uint2*>(v + kKkSlots + 2 * lane);
+            const int l = t - chk_time;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t& resolved = h ? resolved1 : resolved0;
+                const uint32_t neq_prev = h ? np.y : np.x, neq_chk = h ? nc.y : nc.x;
+                uint32_t* r = res + 2 * lane + h;  // plane b of this slot: r[b * 64]
+                if (t >= 1) {
+                    const uint32_t newly = ~neq_prev & ~resolved;
+                    resolved |= newly;
+                    if (warp == 0 && newly) {
+                        r[0] |= newly;  // lambda = 1
+                        if (t <= steps - 1) r[7 * kKkSlots] |= newly;  // reached a fixed point inside the window
+                    }
+                }
+                if (chk_time >= 0) {
+                    const uint32_t newly = ~neq_chk & ~resolved;
+                    resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
+                    if (warp == 0 && newly && l <= steps - 1) {
+#pragma unroll
+                        for (int b = 0; b < kLamPlanes; ++b)
+                            if ((l >> b) & 1) r[b * kKkSlots] |= newly;
+                        r[6 * kKkSlots] |= newly;  // a period found through a checkpoint
+                    }
+                }
+            }
+            if ((((t + 1) & t) == 0 && t < steps - 1) || t == steps - 1) {
+                kc_for_own<BASE>(extra, [&](int i) { chk[i] = cur[i]; });
+                chk_time = t;
+            }
+            const int vclear = vset == 0 ? 2 : vset - 1;
+            if (tid < 2 * kKkSlots) votes[vclear * 2 * kKkSlots + tid] = 0u;
+            vset = vset == 2 ? 0 : vset + 1;
+            return __all_sync(0xFFFFFFFFu, (resolved0 & resolved1) == 0xFFFFFFFFu);
+        };
+        using C0 = std::integral_constant<int, 0>;
+        using C1 = std::integral_constant<int, 1>;
+        int last = 0;  // copy that holds the last state
+        for (int t = 0; t < t1_max; t += 2) {
+            last = 1;
+            if (brent_step(C0{}, t)) break;
+            if (t + 1 >= t1_max) break;
+            last = 0;
+            if (brent_step(C1{}, t + 1)) break;
+        }
+        __syncthreads();  // res is complete (warp 0), every vote word has been read
+        uint32_t lam0[kLamPlanes], lam1[kLamPlanes];
+#pragma unroll
+        for (int b = 0; b < kLamPlanes; ++b) {
+            const uint2 x = *reinterpret_cast<const uint2*>(res + b * kKkSlots + 2 * lane);
+            lam0[b] = x.x;
+            lam1[b] = x.y;
+        }
+        const uint2 cyc = *reinterpret_cast<const uint2*>(res + 6 * kKkSlots + 2 * lane);
+        const uint2 fpt = *reinterpret_cast<const uint2*>(res + 7 * kKkSlots + 2 * lane);
+        uint32_t found0, found1;
+        int xs, xn;  // copy frozen at state_mu for found lanes / its scratch partner
+        if (!__any_sync(0xFFFFFFFFu, (cyc.x | cyc.y) != 0)) {
+            found0 = fpt.x;  // every settled lane sits on its fixed point already
+            found1 = fpt.y;
+            xs = last;
+            xn = last ^ 1;
+        } else {
+            // ------------------------------------------------------------ replay: P in copies 0 / 1, Q in copies 2 / 3
+            for (int i = tid; i < 3 * 2 * kKkSlots; i += kKcThreads) votes[i] = 0u;
+            uint2 pq[BASE + 1];  // own nodes: P during the advance, Q afterwards
+            kc_for_own<BASE>(extra, [&](int i) {
+                pq[i] = kk_lds64(s_own + i * kKcRowBytes + 2 * kKcCopyBytes);
+                kk_sts64(s_own + i * kKcRowBytes, pq[i]);
+            });
+            __syncthreads();
+            const uint32_t has0 = planes_ge(lam0, 1) & cellmask, has1 = planes_ge(lam1, 1) & cellmask;
+            int pc = 0;
+            for (int s = 0; s < steps; ++s) {
+                const uint32_t adv0 = planes_gt(lam0, s) & has0, adv1 = planes_gt(lam1, s) & has1;  // lanes that still owe P a step
+                if (!__any_sync(0xFFFFFFFFu, (adv0 | adv1) != 0)) break;
+                const uint32_t srd = s_lane + pc * kKcCopyBytes;
+                uint2 e_next = kk_lds64(s_tab);
+                kc_for_own<BASE>(extra, [&](int i) {
+                    const uint2 e = e_next;
+                    e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
+                    const uint2 f = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, srd);
+                    pq[i].x = (f.x & adv0) | (pq[i].x & ~adv0);
+                    pq[i].y = (f.y & adv1) | (pq[i].y & ~adv1);
+                    kk_sts64(s_own + i * kKcRowBytes + (pc ^ 1) * kKcCopyBytes, pq[i]);
+                });
+                __syncthreads();
+                pc ^= 1;
+            }
+            kc_for_own<BASE>(extra, [&](int i) { pq[i] = kk_lds64(s_own + i * kKcRowBytes + 2 * kKcCopyBytes); });
+            int qc = 2;
+            uint32_t done0 = ~has0, done1 = ~has1;
+            found0 = found1 = 0u;
+            vset = 0;
+            for (int j = 0; j <= steps - 2; ++j) {
+                uint32_t neq0 = 0, neq1 = 0;
+                const uint32_t prd = s_lane + pc * kKcCopyBytes, qrd = s_lane + qc * kKcCopyBytes;
+                uint2 e_next = kk_lds64(s_tab);
+                kc_for_own<BASE>(extra, [&](int i) {
+                    const uint2 e = e_next;
+                    e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
+                    const uint2 fp = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, prd);
+                    const uint2 fq = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, qrd);
+                    neq0 |= fp.x ^ fq.x;
+                    neq1 |= fp.y ^ fq.y;
+                    pq[i].x = (pq[i].x & done0) | (fq.x & ~done0);
+                    pq[i].y = (pq[i].y & done1) | (fq.y & ~done1);
+                    kk_sts64(s_own + i * kKcRowBytes + (pc ^ 1) * kKcCopyBytes, fp);
+                    kk_sts64(s_own + i * kKcRowBytes + (qc ^ 1) * kKcCopyBytes, pq[i]);
+                });
+                uint32_t* v = votes + vset * 2 * kKkSlots;
+                if (neq0) atomicOr(v + 2 * lane, neq0);
+                if (neq1) atomicOr(v + 2 * lane + 1, neq1);
+                __syncthreads();
+                const uint2 nq = *reinterpret_cast<const uint2*>(v + 2 * lane);
+                // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
+                uint32_t newly = ~nq.x & ~done0;
+                found0 |= newly & ~planes_gt(lam0, steps - 1 - j);
+                done0 |= newly;
+                newly = ~nq.y & ~done1;
+                found1 |= newly & ~planes_gt(lam1, steps - 1 - j);
+                done1 |= newly;
+                const int vclear = vset == 0 ? 2 : vset - 1;
+                if (tid < kKkSlots) votes[vclear * 2 * kKkSlots + tid] = 0u;
+                vset = vset == 2 ? 0 : vset + 1;
+                pc ^= 1;
+                qc ^= 1;
+                if (__all_sync(0xFFFFFFFFu, (done0 & done1) == 0xFFFFFFFFu)) break;
+            }
+            xs = qc;
+            xn = qc ^ 1;
+        }
+        found0 &= cellmask;
+        found1 &= cellmask;
+        SCB_SWEEP_PHASE(4);
+
+        // ------------------------------------------------------------ outputs
+        // normal-run info of the batch's cells: one 4-byte record per cell (bits 0..5 lambda, bit 6 found)
+        for (int v = warp; v < 32; v += kKcWarps) {
+            const int c = cellidx[v * 32 + lane];
+            const uint32_t rec = c >= 0 ? __ldg(args.np_info_t + c) : 0u;
+#pragma unroll
+            for (int b = 0; b <= kLamPlanes; ++b) {
+                const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (rec >> b) & 1u);
+                if (lane == 0) nrm[(b == kLamPlanes ? 0 : 1 + b) * 32 + v] = bits;
+            }
+        }
+        __syncthreads();
+        const uint32_t found_n = nrm[lane];
+        uint32_t lamn[kLamPlanes];
+#pragma unroll
+        for (int b = 0; b < kLamPlanes; ++b) lamn[b] = nrm[(1 + b) * 32 + lane];
+        // a cell counts only if its KO run AND its KI run repeat (and the normal one)
+        const uint32_t valid = found0 & found1 & found_n;
+        if (warp == 0) {
+            const uint32_t m0 = __popc(~found0 & cellmask), m1 = __popc(~found1 & cellmask);
+            if (m0) atomicAdd(args.out_missing + 1 + 2 * forced_node, (unsigned long long)m0);
+            if (m1) atomicAdd(args.out_missing + 2 + 2 * forced_node, (unsigned long long)m1);
+            const uint32_t bad = __popc(found0 & found1 & ~found_n);
+            if (bad) atomicAdd(args.out_keyerror, (unsigned long long)bad);
+        }
+        unsigned long long score = 0;
+        if (__any_sync(0xFFFFFFFFu, valid != 0)) {
+            // offset 0: the frozen states against the normal run's state_mu, gathered into the pair of copies
+            // that xs / xn do not use
+            gather(args.np_states_t, xs ^ 2, -1, xn ^ 2);
+            const uint32_t ge2_0 = planes_ge(lam0, 2), ge2_1 = planes_ge(lam1, 2), gen2 = planes_ge(lamn, 2);
+            const uint32_t both2_0 = valid & ge2_0 & gen2, both2_1 = valid & ge2_1 & gen2;
+            uint32_t sc = 0, sc_both2 = 0;
+            kc_for_own<BASE>(extra, [&](int i) {
+                if (n0 + i < N) {
+                    const uint32_t ref = kk_lds64(s_own + i * kKcRowBytes + (xs ^ 2) * kKcCopyBytes).x;
+                    const uint2 s = kk_lds64(s_own + i * kKcRowBytes + xs * kKcCopyBytes);
+                    const uint32_t x0 = (s.x ^ ref) & valid, x1 = (s.y ^ ref) & valid;
+                    sc += __popc(x0) + __popc(x1);
+                    sc_both2 += __popc(x0 & both2_0) + __popc(x1 & both2_1);
+                }
+            });
+            score = sc;
+            if (!__any_sync(0xFFFFFFFFu, (valid & (ge2_0 | ge2_1 | gen2)) != 0)) {
+                score *= 2;  // every counted cell: fixed point vs fixed point, offset 1 repeats offset 0
+            } else {
+                // offsets 1..min(lambda_x, lambda_n): step, and compare the new state while it is made.  With no
+                // period above 2 in the batch, offset 2 is offset 0 again for the period-2 pairs: one step suffices.
+                const bool short_cycles = !__any_sync(0xFFFFFFFFu, (valid & (planes_ge(lam0, 3) | planes_ge(lam1, 3) | planes_ge(lamn, 3))) != 0);
+                __syncthreads();  // (offset 0 read the reference copy; the next gather parks words in its partner)
+                for (int t = 1; t < steps; ++t) {
+                    if (short_cycles && t == 2) {
+                        score += sc_both2;
+                        break;
+                    }
+                    const uint32_t gn = planes_ge(lamn, t);
+                    const uint32_t act0 = valid & planes_ge(lam0, t) & gn, act1 = valid & planes_ge(lam1, t) & gn;
+                    if (!__any_sync(0xFFFFFFFFu, (act0 | act1) != 0)) break;
+                    gather(args.np_states_t + (size_t)t * args.wpad * 32 * args.nwp, xs ^ 2, -1, xn ^ 2);
+                    const uint32_t srd = s_lane + xs * kKcCopyBytes;
+                    uint32_t sct = 0;
+                    uint2 e_next = kk_lds64(s_tab);
+                    kc_for_own<BASE>(extra, [&](int i) {
+                        const uint2 e = e_next;
+                        e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
+                        const uint2 f = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, srd);
+                        const uint32_t ref = kk_lds64(s_own + i * kKcRowBytes + (xs ^ 2) * kKcCopyBytes).x;
+                        kk_sts64(s_own + i * kKcRowBytes + xn * kKcCopyBytes, f);
+                        sct += __popc((f.x ^ ref) & act0) + __popc((f.y ^ ref) & act1);
+                    });
+                    score += sct;
+                    __syncthreads();
+                    const int tmp = xs;
+                    xs = xn;
+                    xn = tmp;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
+        if (lane == 0 && score) atomicAdd(args.out_raw + forced_node, score);
+        SCB_SWEEP_PHASE(5);
+#ifdef SCB_TRACE
+        if (tid == 0) atomicAdd(&g_sweep_phase[MODE][15], 1ull);
+#endif
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2047,8 +2467,24 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
     args.out_cells = nullptr;
     args.out_cap = 0;
     args.out_count = nullptr;
-    sweep_kernel<SLOTS, MODE_CLEANUP><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
-    SCB_LAUNCH_CHECK("sweep_kernel<cleanup>");
+    // the 768-thread kernel whenever the nodes fit (SCB_SWEEP_CLEANUP=old keeps sweep_kernel<SLOTS, MODE_CLEANUP>)
+    const char* cl_env = getenv("SCB_SWEEP_CLEANUP");
+    const int cl_base = args.n_nodes / kKcWarps;
+    if (SLOTS == 64 && cl_base <= 8 && !(cl_env && cl_env[0] == 'o') && koki_cleanup_smem_bytes(args.n_nodes) <= kMaxDynSmem) {
+        static const void* const kc[9] = {
+            (const void*)koki_cleanup_kernel<0>, (const void*)koki_cleanup_kernel<1>, (const void*)koki_cleanup_kernel<2>,
+            (const void*)koki_cleanup_kernel<3>, (const void*)koki_cleanup_kernel<4>, (const void*)koki_cleanup_kernel<5>,
+            (const void*)koki_cleanup_kernel<6>, (const void*)koki_cleanup_kernel<7>, (const void*)koki_cleanup_kernel<8>};
+        static thread_local SmemMarks kc_marks[9];
+        const size_t kc_smem = koki_cleanup_smem_bytes(args.n_nodes);
+        if (int rc = ensure_dynamic_smem(kc[cl_base], kc_smem, kc_marks[cl_base])) return rc;
+        void* kargs[1] = {(void*)&args};
+        SCB_CUDA(cudaLaunchKernel(kc[cl_base], dim3((unsigned)sm_count()), dim3(kKcThreads), kargs, kc_smem, stream));
+        SCB_LAUNCH_CHECK("koki_cleanup_kernel");
+    } else {
+        sweep_kernel<SLOTS, MODE_CLEANUP><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
+        SCB_LAUNCH_CHECK("sweep_kernel<cleanup>");
+    }
     return SCB_OK;
 }
 
