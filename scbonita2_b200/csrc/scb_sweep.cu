@@ -1852,9 +1852,10 @@ koki_plane_kernel(const SweepArgs args) {
 constexpr int kKcThreads = 768, kKcWarps = kKcThreads / 32;
 constexpr int kKcRowBytes = 4 * kKkSlots * 4, kKcCopyBytes = kKkSlots * 4;  // [node][4 copies][64 slots]
 constexpr int kKcBatchCells = 32 * 32;
+constexpr int kKcVoteWords = 3 * 4 * kKkSlots;  // three sets of up to four vote words per slot
 
 static size_t koki_cleanup_smem_bytes(int n_nodes) {
-    return (size_t)(n_nodes + 1) * kKcRowBytes + (size_t)(n_nodes + kKkTabPad) * sizeof(KkEntry) + (size_t)3 * 2 * kKkSlots * 4 +
+    return (size_t)(n_nodes + 1) * kKcRowBytes + (size_t)(n_nodes + kKkTabPad) * sizeof(KkEntry) + (size_t)kKcVoteWords * 4 +
            (size_t)8 * kKkSlots * 4 + (size_t)kKcBatchCells * 4 + (size_t)(1 + kLamPlanes) * 32 * 4 + (size_t)(n_nodes + 1) * 4;
 }
 
@@ -1865,17 +1866,23 @@ __device__ __forceinline__ void kc_for_own(bool extra, F&& f) {
     if (extra) f(BASE);
 }
 
-template <int BASE>  // N / 24: every warp owns BASE nodes, the first N % 24 warps one more
+// BASE = N / 24: every warp owns BASE nodes, the first N % 24 warps one more.
+// RECHECK: the compacted recheck pass instead -- ring of 4 for all `steps` steps on the cells the KO/KI pass left
+// open (a lane whose new state equals state_{t-d}, smallest d <= 4, has its first repeat at (t-d, t) and is frozen
+// there; lanes still open -- longer cycles, no repeat -- go to the cleanup list): state_{t-1} and state_{t-2} of the
+// own nodes in registers, state_{t-3} and state_{t-4} read from the copies they live in (the oldest one is the copy
+// being overwritten), four vote words per slot.
+template <int BASE, bool RECHECK>
 __global__ void __launch_bounds__(kKcThreads, 1)
-koki_cleanup_kernel(const SweepArgs args) {
-    constexpr int MODE = MODE_CLEANUP;  // (trace macros)
+koki_compact_kernel(const SweepArgs args) {
+    constexpr int MODE = RECHECK ? MODE_RECHECK : MODE_CLEANUP;  // (trace macros)
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = args.n_nodes;
     const int steps = args.steps;
     uint32_t* state = smem;                                                         // [N + 1][4][64], row N = forced values
     KkEntry* table = reinterpret_cast<KkEntry*>(smem + (size_t)(N + 1) * 4 * kKkSlots);  // [N + pad]
-    uint32_t* votes = reinterpret_cast<uint32_t*>(table + N + kKkTabPad);           // [3][2][64]
-    uint32_t* res = votes + 3 * 2 * kKkSlots;                                       // [8][64]: lambda planes, cyc, fixed point
+    uint32_t* votes = reinterpret_cast<uint32_t*>(table + N + kKkTabPad);           // [3][2][64], recheck [3][4][64]
+    uint32_t* res = votes + kKcVoteWords;                                       // [8][64]: lambda planes, cyc, fixed point
     int* cellidx = reinterpret_cast<int*>(res + 8 * kKkSlots);                      // [32][32]
     uint32_t* nrm = reinterpret_cast<uint32_t*>(cellidx + kKcBatchCells);           // [1 + kLamPlanes][32]
     int* pre = reinterpret_cast<int*>(nrm + (1 + kLamPlanes) * 32);                 // [N + 1]
@@ -1983,180 +1990,308 @@ koki_cleanup_kernel(const SweepArgs args) {
             table[forced_node] = kk_make_entry(N, N, N, 1, affine_table(0xF0u, 1));  // f = A, A = the constant row
         }
         prev_forced = forced_node;
-        for (int i = tid; i < 3 * 2 * kKkSlots + 8 * kKkSlots; i += kKcThreads) votes[i] = 0u;  // votes and res
+        for (int i = tid; i < kKcVoteWords + 8 * kKkSlots; i += kKcThreads) votes[i] = 0u;  // votes and res
         const int64_t left = n_in - (batch_first + (int64_t)lane * 32);
-        const uint32_t cellmask = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << (int)left) - 1u : 0u);
+        uint32_t cellmask = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << (int)left) - 1u : 0u);
         __syncthreads();
         SCB_SWEEP_PHASE(0);
 
-        // ------------------------------------------------------------ Brent phase: copies 0 / 1, data kept in copy 2
-        gather(args.planes_t, 0, 2, 3);
-        uint2 cur[BASE + 1], chk[BASE + 1];
-        kc_for_own<BASE>(extra, [&](int i) {
-            cur[i] = kk_lds64(s_own + i * kKcRowBytes);
-            chk[i] = make_uint2(0u, 0u);
-        });
-        __syncthreads();
-        uint32_t resolved0 = ~cellmask, resolved1 = ~cellmask;
-        int chk_time = -1;
-        int vset = 0;
-        const int t1_max = 2 * steps - 1;  // checkpoints at t = 2^k - 1 < steps - 1 and a last one at steps - 1 (see sweep_kernel)
-        auto brent_step = [&](auto rd_tag, int t) -> bool {
-            constexpr int RD = decltype(rd_tag)::value, WR = RD ^ 1;
-            const uint32_t srd = s_lane + RD * kKcCopyBytes;
-            uint32_t qpx = 0, qpy = 0, qcx = 0, qcy = 0;
-            uint2 e_next = kk_lds64(s_tab);
-            kc_for_own<BASE>(extra, [&](int i) {
-                const uint2 e = e_next;
-                e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);  // (the table is padded)
-                const uint2 f = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, srd);
-                qpx |= f.x ^ cur[i].x;
-                qpy |= f.y ^ cur[i].y;
-                qcx |= f.x ^ chk[i].x;
-                qcy |= f.y ^ chk[i].y;
-                kk_sts64(s_own + i * kKcRowBytes + WR * kKcCopyBytes, f);
-                cur[i] = f;
-            });
-            uint32_t* v = votes + vset * 2 * kKkSlots;
-            if (qpx) atomicOr(v + 2 * lane, qpx);
-            if (qpy) atomicOr(v + 2 * lane + 1, qpy);
-            if (chk_time >= 0) {
-                if (qcx) atomicOr(v + kKkSlots + 2 * lane, qcx);
-                if (qcy) atomicOr(v + kKkSlots + 2 * lane + 1, qcy);
-            }
-            __syncthreads();
-            const uint2 np = *reinterpret_cast<const uint2*>(v + 2 * lane);
-            const uint2 nc = *reinterpret_cast<const uint2*>(v + kKkSlots + 2 * lane);
-            const int l = t - chk_time;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t& resolved = h ? resolved1 : resolved0;
-                const uint32_t neq_prev = h ? np.y : np.x, neq_chk = h ? nc.y : nc.x;
-                uint32_t* r = res + 2 * lane + h;  // plane b of this slot: r[b * 64]
-                if (t >= 1) {
-                    const uint32_t newly = ~neq_prev & ~resolved;
-                    resolved |= newly;
-                    if (warp == 0 && newly) {
-                        r[0] |= newly;  // lambda = 1
-                        if (t <= steps - 1) r[7 * kKkSlots] |= newly;  // reached a fixed point inside the window
-                    }
-                }
-                if (chk_time >= 0) {
-                    const uint32_t newly = ~neq_chk & ~resolved;
-                    resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
-                    if (warp == 0 && newly && l <= steps - 1) {
-#pragma unroll
-                        for (int b = 0; b < kLamPlanes; ++b)
-                            if ((l >> b) & 1) r[b * kKkSlots] |= newly;
-                        r[6 * kKkSlots] |= newly;  // a period found through a checkpoint
-                    }
-                }
-            }
-            if ((((t + 1) & t) == 0 && t < steps - 1) || t == steps - 1) {
-                kc_for_own<BASE>(extra, [&](int i) { chk[i] = cur[i]; });
-                chk_time = t;
-            }
-            const int vclear = vset == 0 ? 2 : vset - 1;
-            if (tid < 2 * kKkSlots) votes[vclear * 2 * kKkSlots + tid] = 0u;
-            vset = vset == 2 ? 0 : vset + 1;
-            return __all_sync(0xFFFFFFFFu, (resolved0 & resolved1) == 0xFFFFFFFFu);
-        };
-        using C0 = std::integral_constant<int, 0>;
-        using C1 = std::integral_constant<int, 1>;
-        int last = 0;  // copy that holds the last state
-        for (int t = 0; t < t1_max; t += 2) {
-            last = 1;
-            if (brent_step(C0{}, t)) break;
-            if (t + 1 >= t1_max) break;
-            last = 0;
-            if (brent_step(C1{}, t + 1)) break;
-        }
-        __syncthreads();  // res is complete (warp 0), every vote word has been read
-        uint32_t lam0[kLamPlanes], lam1[kLamPlanes];
-#pragma unroll
-        for (int b = 0; b < kLamPlanes; ++b) {
-            const uint2 x = *reinterpret_cast<const uint2*>(res + b * kKkSlots + 2 * lane);
-            lam0[b] = x.x;
-            lam1[b] = x.y;
-        }
-        const uint2 cyc = *reinterpret_cast<const uint2*>(res + 6 * kKkSlots + 2 * lane);
-        const uint2 fpt = *reinterpret_cast<const uint2*>(res + 7 * kKkSlots + 2 * lane);
+        uint32_t lam0[kLamPlanes], lam1[kLamPlanes];  // cycle length of every lane, bit-sliced
         uint32_t found0, found1;
         int xs, xn;  // copy frozen at state_mu for found lanes / its scratch partner
-        if (!__any_sync(0xFFFFFFFFu, (cyc.x | cyc.y) != 0)) {
-            found0 = fpt.x;  // every settled lane sits on its fixed point already
-            found1 = fpt.y;
-            xs = last;
-            xn = last ^ 1;
-        } else {
-            // ------------------------------------------------------------ replay: P in copies 0 / 1, Q in copies 2 / 3
-            for (int i = tid; i < 3 * 2 * kKkSlots; i += kKcThreads) votes[i] = 0u;
-            uint2 pq[BASE + 1];  // own nodes: P during the advance, Q afterwards
+        if constexpr (RECHECK) {
+            // ------------------------------------------------------------ ring of 4 (data into copy 3)
+            gather(args.planes_t, 3, -1, 0);
+            uint2 ra[BASE + 1], rb[BASE + 1];  // state_{t-1} / state_{t-2} of the own nodes, roles alternate
             kc_for_own<BASE>(extra, [&](int i) {
-                pq[i] = kk_lds64(s_own + i * kKcRowBytes + 2 * kKcCopyBytes);
-                kk_sts64(s_own + i * kKcRowBytes, pq[i]);
+                ra[i] = kk_lds64(s_own + i * kKcRowBytes + 3 * kKcCopyBytes);
+                rb[i] = make_uint2(0u, 0u);
             });
             __syncthreads();
-            const uint32_t has0 = planes_ge(lam0, 1) & cellmask, has1 = planes_ge(lam1, 1) & cellmask;
-            int pc = 0;
-            for (int s = 0; s < steps; ++s) {
-                const uint32_t adv0 = planes_gt(lam0, s) & has0, adv1 = planes_gt(lam1, s) & has1;  // lanes that still owe P a step
-                if (!__any_sync(0xFFFFFFFFu, (adv0 | adv1) != 0)) break;
-                const uint32_t srd = s_lane + pc * kKcCopyBytes;
+            uint32_t frozen0 = ~cellmask, frozen1 = ~cellmask;
+#pragma unroll
+            for (int b = 0; b < kLamPlanes; ++b) lam0[b] = lam1[b] = 0u;
+            unsigned int last_open = 0xFFFFFFFFu;
+            int stall = 0, vset = 0;
+            bool moved = false;
+            // step t writes copy KD = t & 3 (it holds state_{t-4}) and reads copy KD + 3 (state_{t-1}); cur / prv are
+            // state_{t-1} / state_{t-2} of the own nodes, prv receives state_t.  Returns true when the ring is done.
+            auto ring_step = [&](auto kd_tag, uint2 (&cur)[BASE + 1], uint2 (&prv)[BASE + 1], int t) -> bool {
+                constexpr int KD = decltype(kd_tag)::value, KS = (KD + 3) & 3, K3 = (KD + 1) & 3;
+                const uint32_t srd = s_lane + KS * kKcCopyBytes;
+                uint32_t q1x = 0, q1y = 0, q2x = 0, q2y = 0, q3x = 0, q3y = 0, q4x = 0, q4y = 0;
                 uint2 e_next = kk_lds64(s_tab);
                 kc_for_own<BASE>(extra, [&](int i) {
                     const uint2 e = e_next;
-                    e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
+                    e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);  // (the table is padded)
+                    const uint2 o3 = kk_lds64(s_own + i * kKcRowBytes + K3 * kKcCopyBytes);
+                    const uint2 o4 = kk_lds64(s_own + i * kKcRowBytes + KD * kKcCopyBytes);
                     const uint2 f = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, srd);
-                    pq[i].x = (f.x & adv0) | (pq[i].x & ~adv0);
-                    pq[i].y = (f.y & adv1) | (pq[i].y & ~adv1);
-                    kk_sts64(s_own + i * kKcRowBytes + (pc ^ 1) * kKcCopyBytes, pq[i]);
+                    q1x |= f.x ^ cur[i].x;
+                    q1y |= f.y ^ cur[i].y;
+                    q2x |= f.x ^ prv[i].x;
+                    q2y |= f.y ^ prv[i].y;
+                    q3x |= f.x ^ o3.x;
+                    q3y |= f.y ^ o3.y;
+                    q4x |= f.x ^ o4.x;
+                    q4y |= f.y ^ o4.y;
+                    uint2 w;
+                    w.x = (f.x & ~frozen0) | (cur[i].x & frozen0);
+                    w.y = (f.y & ~frozen1) | (cur[i].y & frozen1);
+                    kk_sts64(s_own + i * kKcRowBytes + KD * kKcCopyBytes, w);
+                    prv[i] = w;
                 });
+                uint32_t* v = votes + vset * 4 * kKkSlots;  // [d - 1][slot]; only open lanes matter
+                q1x &= ~frozen0; q2x &= ~frozen0; q3x &= ~frozen0; q4x &= ~frozen0;
+                q1y &= ~frozen1; q2y &= ~frozen1; q3y &= ~frozen1; q4y &= ~frozen1;
+                if (q1x) atomicOr(v + 2 * lane, q1x);
+                if (q1y) atomicOr(v + 2 * lane + 1, q1y);
+                if (q2x) atomicOr(v + kKkSlots + 2 * lane, q2x);
+                if (q2y) atomicOr(v + kKkSlots + 2 * lane + 1, q2y);
+                if (q3x) atomicOr(v + 2 * kKkSlots + 2 * lane, q3x);
+                if (q3y) atomicOr(v + 2 * kKkSlots + 2 * lane + 1, q3y);
+                if (q4x) atomicOr(v + 3 * kKkSlots + 2 * lane, q4x);
+                if (q4y) atomicOr(v + 3 * kKkSlots + 2 * lane + 1, q4y);
                 __syncthreads();
-                pc ^= 1;
+                const uint2 n1 = *reinterpret_cast<const uint2*>(v + 2 * lane);
+                const uint2 n2 = *reinterpret_cast<const uint2*>(v + kKkSlots + 2 * lane);
+                const uint2 n3 = *reinterpret_cast<const uint2*>(v + 2 * kKkSlots + 2 * lane);
+                const uint2 n4 = *reinterpret_cast<const uint2*>(v + 3 * kKkSlots + 2 * lane);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t& frozen = h ? frozen1 : frozen0;
+                    uint32_t(&lam)[kLamPlanes] = h ? lam1 : lam0;
+                    // state_{t-d} exists for t >= d only (the raw data state is never compared)
+                    uint32_t open = ~frozen;
+                    const uint32_t e1 = t >= 1 ? ~(h ? n1.y : n1.x) & open : 0u;
+                    open &= ~e1;
+                    const uint32_t e2 = t >= 2 ? ~(h ? n2.y : n2.x) & open : 0u;
+                    open &= ~e2;
+                    const uint32_t e3 = t >= 3 ? ~(h ? n3.y : n3.x) & open : 0u;
+                    open &= ~e3;
+                    const uint32_t e4 = t >= 4 ? ~(h ? n4.y : n4.x) & open : 0u;
+                    lam[0] |= e1 | e3;
+                    lam[1] |= e2 | e3;
+                    lam[2] |= e4;
+                    frozen |= e1 | e2 | e3 | e4;
+                }
+                // set t % 3 is written in step t and read after its barrier; set (t + 2) % 3 is cleared here, after
+                // the barrier of step t (its readers finished before it) and written in step t + 2
+                const int vclear = vset == 0 ? 2 : vset - 1;
+                if (tid < 4 * kKkSlots) votes[vclear * 4 * kKkSlots + tid] = 0u;
+                vset = vset == 2 ? 0 : vset + 1;
+                // stop when nothing is open, or once lanes had started to settle and none did for a while (what is left
+                // are cycles the ring cannot see)
+                const unsigned int n_open = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)(__popc(~frozen0) + __popc(~frozen1)));
+                if (n_open == 0) return true;
+                if (n_open < last_open) {
+                    moved = last_open != 0xFFFFFFFFu;
+                    last_open = n_open;
+                    stall = 0;
+                } else if (moved && ++stall >= args.ring_stall) {
+                    return true;
+                }
+                return false;
+            };
+            using K0 = std::integral_constant<int, 0>;
+            using K1 = std::integral_constant<int, 1>;
+            using K2 = std::integral_constant<int, 2>;
+            using K3 = std::integral_constant<int, 3>;
+            xs = 3;
+            for (int t = 0; t < steps; t += 4) {
+                xs = 0;
+                if (ring_step(K0{}, ra, rb, t)) break;
+                if (t + 1 >= steps) break;
+                xs = 1;
+                if (ring_step(K1{}, rb, ra, t + 1)) break;
+                if (t + 2 >= steps) break;
+                xs = 2;
+                if (ring_step(K2{}, ra, rb, t + 2)) break;
+                if (t + 3 >= steps) break;
+                xs = 3;
+                if (ring_step(K3{}, rb, ra, t + 3)) break;
             }
-            kc_for_own<BASE>(extra, [&](int i) { pq[i] = kk_lds64(s_own + i * kKcRowBytes + 2 * kKcCopyBytes); });
-            int qc = 2;
-            uint32_t done0 = ~has0, done1 = ~has1;
-            found0 = found1 = 0u;
-            vset = 0;
-            for (int j = 0; j <= steps - 2; ++j) {
-                uint32_t neq0 = 0, neq1 = 0;
-                const uint32_t prd = s_lane + pc * kKcCopyBytes, qrd = s_lane + qc * kKcCopyBytes;
+            xn = (xs + 1) & 3;
+            SCB_SWEEP_PHASE(2);
+            // lanes still open: KO and KI of a cell travel together to the cleanup list
+            const uint32_t both = ~frozen0 | ~frozen1;
+            if (both && warp == 0) {
+                const unsigned int k = __popc(both);
+                const unsigned int at0 = atomicAdd(&args.out_count[forced_node], k);
+                int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + at0;  // cap = n_cells: always room
+                for (uint32_t m = both; m; m &= m - 1) *dst++ = cellidx[lane * 32 + (__ffs(m) - 1)];
+            }
+            cellmask &= ~both;
+            found0 = frozen0;
+            found1 = frozen1;
+        }
+        if constexpr (!RECHECK) {
+            // ------------------------------------------------------------ Brent phase: copies 0 / 1, data kept in copy 2
+            gather(args.planes_t, 0, 2, 3);
+            uint2 cur[BASE + 1], chk[BASE + 1];
+            kc_for_own<BASE>(extra, [&](int i) {
+                cur[i] = kk_lds64(s_own + i * kKcRowBytes);
+                chk[i] = make_uint2(0u, 0u);
+            });
+            __syncthreads();
+            uint32_t resolved0 = ~cellmask, resolved1 = ~cellmask;
+            int chk_time = -1;
+            int vset = 0;
+            const int t1_max = 2 * steps - 1;  // checkpoints at t = 2^k - 1 < steps - 1 and a last one at steps - 1 (see sweep_kernel)
+            auto brent_step = [&](auto rd_tag, int t) -> bool {
+                constexpr int RD = decltype(rd_tag)::value, WR = RD ^ 1;
+                const uint32_t srd = s_lane + RD * kKcCopyBytes;
+                uint32_t qpx = 0, qpy = 0, qcx = 0, qcy = 0;
                 uint2 e_next = kk_lds64(s_tab);
                 kc_for_own<BASE>(extra, [&](int i) {
                     const uint2 e = e_next;
-                    e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
-                    const uint2 fp = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, prd);
-                    const uint2 fq = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, qrd);
-                    neq0 |= fp.x ^ fq.x;
-                    neq1 |= fp.y ^ fq.y;
-                    pq[i].x = (pq[i].x & done0) | (fq.x & ~done0);
-                    pq[i].y = (pq[i].y & done1) | (fq.y & ~done1);
-                    kk_sts64(s_own + i * kKcRowBytes + (pc ^ 1) * kKcCopyBytes, fp);
-                    kk_sts64(s_own + i * kKcRowBytes + (qc ^ 1) * kKcCopyBytes, pq[i]);
+                    e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);  // (the table is padded)
+                    const uint2 f = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, srd);
+                    qpx |= f.x ^ cur[i].x;
+                    qpy |= f.y ^ cur[i].y;
+                    qcx |= f.x ^ chk[i].x;
+                    qcy |= f.y ^ chk[i].y;
+                    kk_sts64(s_own + i * kKcRowBytes + WR * kKcCopyBytes, f);
+                    cur[i] = f;
                 });
                 uint32_t* v = votes + vset * 2 * kKkSlots;
-                if (neq0) atomicOr(v + 2 * lane, neq0);
-                if (neq1) atomicOr(v + 2 * lane + 1, neq1);
+                if (qpx) atomicOr(v + 2 * lane, qpx);
+                if (qpy) atomicOr(v + 2 * lane + 1, qpy);
+                if (chk_time >= 0) {
+                    if (qcx) atomicOr(v + kKkSlots + 2 * lane, qcx);
+                    if (qcy) atomicOr(v + kKkSlots + 2 * lane + 1, qcy);
+                }
                 __syncthreads();
-                const uint2 nq = *reinterpret_cast<const uint2*>(v + 2 * lane);
-                // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
-                uint32_t newly = ~nq.x & ~done0;
-                found0 |= newly & ~planes_gt(lam0, steps - 1 - j);
-                done0 |= newly;
-                newly = ~nq.y & ~done1;
-                found1 |= newly & ~planes_gt(lam1, steps - 1 - j);
-                done1 |= newly;
+                const uint2 np = *reinterpret_cast<const uint2*>(v + 2 * lane);
+                const uint2 nc = *reinterpret_cast<const uint2*>(v + kKkSlots + 2 * lane);
+                const int l = t - chk_time;
+    #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t& resolved = h ? resolved1 : resolved0;
+                    const uint32_t neq_prev = h ? np.y : np.x, neq_chk = h ? nc.y : nc.x;
+                    uint32_t* r = res + 2 * lane + h;  // plane b of this slot: r[b * 64]
+                    if (t >= 1) {
+                        const uint32_t newly = ~neq_prev & ~resolved;
+                        resolved |= newly;
+                        if (warp == 0 && newly) {
+                            r[0] |= newly;  // lambda = 1
+                            if (t <= steps - 1) r[7 * kKkSlots] |= newly;  // reached a fixed point inside the window
+                        }
+                    }
+                    if (chk_time >= 0) {
+                        const uint32_t newly = ~neq_chk & ~resolved;
+                        resolved |= newly;  // l >= steps: such a cell can never repeat inside the window
+                        if (warp == 0 && newly && l <= steps - 1) {
+    #pragma unroll
+                            for (int b = 0; b < kLamPlanes; ++b)
+                                if ((l >> b) & 1) r[b * kKkSlots] |= newly;
+                            r[6 * kKkSlots] |= newly;  // a period found through a checkpoint
+                        }
+                    }
+                }
+                if ((((t + 1) & t) == 0 && t < steps - 1) || t == steps - 1) {
+                    kc_for_own<BASE>(extra, [&](int i) { chk[i] = cur[i]; });
+                    chk_time = t;
+                }
                 const int vclear = vset == 0 ? 2 : vset - 1;
-                if (tid < kKkSlots) votes[vclear * 2 * kKkSlots + tid] = 0u;
+                if (tid < 2 * kKkSlots) votes[vclear * 2 * kKkSlots + tid] = 0u;
                 vset = vset == 2 ? 0 : vset + 1;
-                pc ^= 1;
-                qc ^= 1;
-                if (__all_sync(0xFFFFFFFFu, (done0 & done1) == 0xFFFFFFFFu)) break;
+                return __all_sync(0xFFFFFFFFu, (resolved0 & resolved1) == 0xFFFFFFFFu);
+            };
+            using C0 = std::integral_constant<int, 0>;
+            using C1 = std::integral_constant<int, 1>;
+            int last = 0;  // copy that holds the last state
+            for (int t = 0; t < t1_max; t += 2) {
+                last = 1;
+                if (brent_step(C0{}, t)) break;
+                if (t + 1 >= t1_max) break;
+                last = 0;
+                if (brent_step(C1{}, t + 1)) break;
             }
-            xs = qc;
-            xn = qc ^ 1;
+            __syncthreads();  // res is complete (warp 0), every vote word has been read
+    #pragma unroll
+            for (int b = 0; b < kLamPlanes; ++b) {
+                const uint2 x = *reinterpret_cast<const uint2*>(res + b * kKkSlots + 2 * lane);
+                lam0[b] = x.x;
+                lam1[b] = x.y;
+            }
+            const uint2 cyc = *reinterpret_cast<const uint2*>(res + 6 * kKkSlots + 2 * lane);
+            const uint2 fpt = *reinterpret_cast<const uint2*>(res + 7 * kKkSlots + 2 * lane);
+            if (!__any_sync(0xFFFFFFFFu, (cyc.x | cyc.y) != 0)) {
+                found0 = fpt.x;  // every settled lane sits on its fixed point already
+                found1 = fpt.y;
+                xs = last;
+                xn = last ^ 1;
+            } else {
+                // ------------------------------------------------------------ replay: P in copies 0 / 1, Q in copies 2 / 3
+                for (int i = tid; i < 3 * 2 * kKkSlots; i += kKcThreads) votes[i] = 0u;
+                uint2 pq[BASE + 1];  // own nodes: P during the advance, Q afterwards
+                kc_for_own<BASE>(extra, [&](int i) {
+                    pq[i] = kk_lds64(s_own + i * kKcRowBytes + 2 * kKcCopyBytes);
+                    kk_sts64(s_own + i * kKcRowBytes, pq[i]);
+                });
+                __syncthreads();
+                const uint32_t has0 = planes_ge(lam0, 1) & cellmask, has1 = planes_ge(lam1, 1) & cellmask;
+                int pc = 0;
+                for (int s = 0; s < steps; ++s) {
+                    const uint32_t adv0 = planes_gt(lam0, s) & has0, adv1 = planes_gt(lam1, s) & has1;  // lanes that still owe P a step
+                    if (!__any_sync(0xFFFFFFFFu, (adv0 | adv1) != 0)) break;
+                    const uint32_t srd = s_lane + pc * kKcCopyBytes;
+                    uint2 e_next = kk_lds64(s_tab);
+                    kc_for_own<BASE>(extra, [&](int i) {
+                        const uint2 e = e_next;
+                        e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
+                        const uint2 f = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, srd);
+                        pq[i].x = (f.x & adv0) | (pq[i].x & ~adv0);
+                        pq[i].y = (f.y & adv1) | (pq[i].y & ~adv1);
+                        kk_sts64(s_own + i * kKcRowBytes + (pc ^ 1) * kKcCopyBytes, pq[i]);
+                    });
+                    __syncthreads();
+                    pc ^= 1;
+                }
+                kc_for_own<BASE>(extra, [&](int i) { pq[i] = kk_lds64(s_own + i * kKcRowBytes + 2 * kKcCopyBytes); });
+                int qc = 2;
+                uint32_t done0 = ~has0, done1 = ~has1;
+                found0 = found1 = 0u;
+                vset = 0;
+                for (int j = 0; j <= steps - 2; ++j) {
+                    uint32_t neq0 = 0, neq1 = 0;
+                    const uint32_t prd = s_lane + pc * kKcCopyBytes, qrd = s_lane + qc * kKcCopyBytes;
+                    uint2 e_next = kk_lds64(s_tab);
+                    kc_for_own<BASE>(extra, [&](int i) {
+                        const uint2 e = e_next;
+                        e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
+                        const uint2 fp = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, prd);
+                        const uint2 fq = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, qrd);
+                        neq0 |= fp.x ^ fq.x;
+                        neq1 |= fp.y ^ fq.y;
+                        pq[i].x = (pq[i].x & done0) | (fq.x & ~done0);
+                        pq[i].y = (pq[i].y & done1) | (fq.y & ~done1);
+                        kk_sts64(s_own + i * kKcRowBytes + (pc ^ 1) * kKcCopyBytes, fp);
+                        kk_sts64(s_own + i * kKcRowBytes + (qc ^ 1) * kKcCopyBytes, pq[i]);
+                    });
+                    uint32_t* v = votes + vset * 2 * kKkSlots;
+                    if (neq0) atomicOr(v + 2 * lane, neq0);
+                    if (neq1) atomicOr(v + 2 * lane + 1, neq1);
+                    __syncthreads();
+                    const uint2 nq = *reinterpret_cast<const uint2*>(v + 2 * lane);
+                    // first repeat is (j, j + lambda); it only exists if j + lambda <= steps - 1
+                    uint32_t newly = ~nq.x & ~done0;
+                    found0 |= newly & ~planes_gt(lam0, steps - 1 - j);
+                    done0 |= newly;
+                    newly = ~nq.y & ~done1;
+                    found1 |= newly & ~planes_gt(lam1, steps - 1 - j);
+                    done1 |= newly;
+                    const int vclear = vset == 0 ? 2 : vset - 1;
+                    if (tid < kKkSlots) votes[vclear * 2 * kKkSlots + tid] = 0u;
+                    vset = vset == 2 ? 0 : vset + 1;
+                    pc ^= 1;
+                    qc ^= 1;
+                    if (__all_sync(0xFFFFFFFFu, (done0 & done1) == 0xFFFFFFFFu)) break;
+                }
+                xs = qc;
+                xn = qc ^ 1;
+            }
         }
         found0 &= cellmask;
         found1 &= cellmask;
@@ -2457,8 +2592,23 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
         args.out_cells = lists.cells_b;
         args.out_cap = lists.cap_b;
         args.out_count = lists.count_b;
-        sweep_kernel<SLOTS, MODE_RECHECK><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
-        SCB_LAUNCH_CHECK("sweep_kernel<recheck>");
+        const char* rc_env = getenv("SCB_SWEEP_RECHECK");  // =old keeps sweep_kernel<SLOTS, MODE_RECHECK>
+        const int rc_base = args.n_nodes / kKcWarps;
+        if (SLOTS == 64 && rc_base <= 8 && !(rc_env && rc_env[0] == 'o') && koki_cleanup_smem_bytes(args.n_nodes) <= kMaxDynSmem) {
+            static const void* const kr[9] = {
+                (const void*)koki_compact_kernel<0, true>, (const void*)koki_compact_kernel<1, true>, (const void*)koki_compact_kernel<2, true>,
+                (const void*)koki_compact_kernel<3, true>, (const void*)koki_compact_kernel<4, true>, (const void*)koki_compact_kernel<5, true>,
+                (const void*)koki_compact_kernel<6, true>, (const void*)koki_compact_kernel<7, true>, (const void*)koki_compact_kernel<8, true>};
+            static thread_local SmemMarks kr_marks[9];
+            const size_t kr_smem = koki_cleanup_smem_bytes(args.n_nodes);
+            if (int rc = ensure_dynamic_smem(kr[rc_base], kr_smem, kr_marks[rc_base])) return rc;
+            void* kargs[1] = {(void*)&args};
+            SCB_CUDA(cudaLaunchKernel(kr[rc_base], dim3((unsigned)sm_count()), dim3(kKcThreads), kargs, kr_smem, stream));
+            SCB_LAUNCH_CHECK("koki_compact_kernel<recheck>");
+        } else {
+            sweep_kernel<SLOTS, MODE_RECHECK><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
+            SCB_LAUNCH_CHECK("sweep_kernel<recheck>");
+        }
     }
     // stragglers, compacted: the general slow path on list B
     args.in_cells = lists.cells_b;
@@ -2472,15 +2622,15 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
     const int cl_base = args.n_nodes / kKcWarps;
     if (SLOTS == 64 && cl_base <= 8 && !(cl_env && cl_env[0] == 'o') && koki_cleanup_smem_bytes(args.n_nodes) <= kMaxDynSmem) {
         static const void* const kc[9] = {
-            (const void*)koki_cleanup_kernel<0>, (const void*)koki_cleanup_kernel<1>, (const void*)koki_cleanup_kernel<2>,
-            (const void*)koki_cleanup_kernel<3>, (const void*)koki_cleanup_kernel<4>, (const void*)koki_cleanup_kernel<5>,
-            (const void*)koki_cleanup_kernel<6>, (const void*)koki_cleanup_kernel<7>, (const void*)koki_cleanup_kernel<8>};
+            (const void*)koki_compact_kernel<0, false>, (const void*)koki_compact_kernel<1, false>, (const void*)koki_compact_kernel<2, false>,
+            (const void*)koki_compact_kernel<3, false>, (const void*)koki_compact_kernel<4, false>, (const void*)koki_compact_kernel<5, false>,
+            (const void*)koki_compact_kernel<6, false>, (const void*)koki_compact_kernel<7, false>, (const void*)koki_compact_kernel<8, false>};
         static thread_local SmemMarks kc_marks[9];
         const size_t kc_smem = koki_cleanup_smem_bytes(args.n_nodes);
         if (int rc = ensure_dynamic_smem(kc[cl_base], kc_smem, kc_marks[cl_base])) return rc;
         void* kargs[1] = {(void*)&args};
         SCB_CUDA(cudaLaunchKernel(kc[cl_base], dim3((unsigned)sm_count()), dim3(kKcThreads), kargs, kc_smem, stream));
-        SCB_LAUNCH_CHECK("koki_cleanup_kernel");
+        SCB_LAUNCH_CHECK("koki_compact_kernel<cleanup>");
     } else {
         sweep_kernel<SLOTS, MODE_CLEANUP><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
         SCB_LAUNCH_CHECK("sweep_kernel<cleanup>");
