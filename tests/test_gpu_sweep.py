@@ -239,7 +239,9 @@ def test_sweep_general_tables_and_parent_holes_vs_c_oracle(cuda, monkeypatch, n_
 @pytest.mark.parametrize("n_nodes,koki", [(5, "plane"), (16, "plane"), (17, "plane"), (40, "plane"), (49, "plane"),
                                           (70, "plane"), (96, "plane"), (111, "plane"), (113, "plane"), (140, "plane"),
                                           (160, "plane"), (176, "plane"), (177, "plane"), (193, "plane"), (208, "plane"),
-                                          (70, "old"), (177, "old"), (200, "old")])
+                                          (70, "old"), (177, "old"), (200, "old"),
+                                          (23, "old-compact"), (24, "old-compact"), (100, "old-compact"), (200, "old-compact"),
+                                          (209, "auto"), (216, "auto")])
 def test_sweep_koki_kernels_vs_c_oracle(cuda, monkeypatch, n_nodes, koki):
     """The KO/KI pass on the plane words has two implementations: ``koki_plane_kernel<CNT>`` (two CTAs per SM,
     CNT = ceil(N / 16) nodes per warp, node rows padded to 16 * CNT: every CNT from 1 to 13 is hit here, with
@@ -257,10 +259,13 @@ def test_sweep_koki_kernels_vs_c_oracle(cuda, monkeypatch, n_nodes, koki):
                     rng.integers(0, 256, n_nodes)).astype(np.uint8)
     planes_np = synth.random_planes(n_nodes, n_cells, 11 + n_nodes, density=0.4)
     monkeypatch.delenv("SCB_SWEEP_FAST_STEPS", raising=False)
+    for var in ("SCB_SWEEP_KOKI", "SCB_SWEEP_RECHECK", "SCB_SWEEP_CLEANUP"):
+        monkeypatch.delenv(var, raising=False)
     if koki == "old":
         monkeypatch.setenv("SCB_SWEEP_KOKI", "old")
-    else:
-        monkeypatch.delenv("SCB_SWEEP_KOKI", raising=False)
+    if koki == "old-compact":   # sweep_kernel<64, MODE_RECHECK / MODE_CLEANUP> instead of koki_compact_kernel
+        monkeypatch.setenv("SCB_SWEEP_RECHECK", "old")
+        monkeypatch.setenv("SCB_SWEEP_CLEANUP", "old")
     raw, missing, keyerr = device.ko_ki_sweep(device.BitPlanes.from_packed(planes_np, n_cells), parents, luts, steps)
     w_raw, w_missing, w_key = cport.importance_raw(synth.planes_to_dense(planes_np, n_cells), parents, luts, steps)
     assert int(keyerr.item()) == w_key
