@@ -791,6 +791,9 @@ def run_ours(args):
                           f"copy k % {ga['n_rot']} of the bitplanes ({ga['n_rot']} x {ga['plane_bytes'] / 1e6:.1f} MB > 2 x 126 MB L2)",
                 "wall_s_timed_region": ga["wall"], "fitness_checksum": ga["checksum"],
                 "launch": "one cuda graph of K steps" if ga["graph"] else "eager",
+                "overlap": "programmatic dependent launch both ways: the counting kernel of step k+1 claims its tiles "
+                           "dynamically and runs on the SMs the fitness kernel of step k (three individuals per warp: "
+                           "43 CTAs) leaves free; its flush waits for that kernel to complete",
                 "ms_per_step_eager": ga["eager_ms"], "ms_per_step_isolated_l2_flushed": ga["isolated_ms"]}),
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_pipe": roofline_pipe,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_dense": e2e_dense, "sweep": sweep, "strong": strong,

@@ -433,6 +433,7 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     __syncthreads();
     SCB_TRACE_AT(1, tid == 0);
 
+    unsigned int claim_done = 0u;  // producer lane: how many CTAs had claimed their last tile before this one
     if (warp == kConsumerWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
@@ -445,7 +446,21 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
             const int in_flight = n_stages < kInFlight ? n_stages : kInFlight;  // never waits on a re-armed stage
             int land_stage = 0, seq = 0;
             uint32_t land_phase = 0;
-            for (int64_t tile = blockIdx.x;; tile += gridDim.x, ++seq) {
+            // Tiles are CLAIMED, not strided: the kernel may start on a few SMs while the kernel before it in the
+            // stream (the previous pass's fitness kernel, programmatic dependent launch) still holds the others;
+            // a CTA that starts early then simply takes more tiles.  cta_ticket[1] is the claim counter (zero on
+            // entry; the last CTA to leave the claiming loop zeroes it, see below); the next claim is issued one
+            // tile ahead so its round trip to L2 hides behind the copy being set up.
+            // The first two tiles of a CTA are its own (no round trip before the first copies, and the burst of first
+            // claims -- every CTA at once, on one address -- has two tiles' time to return); claims start at 2 * gridDim.x
+            // and run three tiles ahead.
+            unsigned int* claim = cta_ticket + 1;
+            const int64_t claim_base = 2 * (int64_t)gridDim.x;
+            int64_t tile = blockIdx.x;
+            int64_t q1 = tile + gridDim.x;
+            int64_t q2 = claim_base + (int64_t)atomicAdd(claim, 1u);
+            int64_t q3 = claim_base + (int64_t)atomicAdd(claim, 1u);  // (the pipeline fill wants in_flight tiles at once)
+            for (;; tile = q1, q1 = q2, q2 = q3, q3 = q3 < n_tiles ? claim_base + (int64_t)atomicAdd(claim, 1u) : q3, ++seq) {
                 if (seq >= in_flight) {
                     mbar_wait(&full[land_stage], land_phase);
                     if (++land_stage == n_stages) {
@@ -479,6 +494,11 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
                     phase ^= 1;
                 }
             }
+            // this CTA has claimed its last tile; the last CTA to say so zeroes the claim counter for the next
+            // launch (which cannot start before this grid has completed: it is at best a programmatic
+            // dependent of the kernel AFTER this one)
+            // (the answer is looked at after the flush below: the round trip hides behind it)
+            claim_done = atomicAdd(cta_ticket + 2, 1u);
         }
         __syncwarp();
     } else {
@@ -589,6 +609,10 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     if (!kDirectRed)
         for (int i = tid; i < n_acc; i += blockDim.x)
             if (cta_acc[i]) atomicAdd(acc + i, (unsigned long long)cta_acc[i]);
+    if (warp == kConsumerWarps && lane == 0 && claim_done == gridDim.x - 1) {
+        cta_ticket[1] = 0u;
+        cta_ticket[2] = 0u;
+    }
     // sums_only on one GPU: that is all -- the consumer (the fitness kernel) is ordered behind this grid by
     // the stream, inverts the sums itself and zeroes the accumulators: no ticket, no last CTA
     if (sums_only && !peer_regions) return;

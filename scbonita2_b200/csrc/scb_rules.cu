@@ -86,7 +86,9 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
                           const uint8_t* __restrict__ lut, const uint8_t* __restrict__ active,
                           int64_t* __restrict__ out_diff, int64_t* __restrict__ out_diff_pg,
                           const unsigned char* region /*peer exchange region or NULL*/, int rank, int n_ranks,
-                          const SumsInput sums /*sums.mode != 0: subset sums instead of counts (scb_rule_sums_run)*/) {
+                          const SumsInput sums /*sums.mode != 0: subset sums instead of counts (scb_rule_sums_run)*/,
+                          int lut_off /*> 0: byte offset of the staged truth tables in shared memory*/,
+                          int chunk /*individuals per CTA (contiguous) when the tables are staged*/) {
     extern __shared__ __align__(16) long long s_tab[];  // base[G] | delta[8][G] (int64) | lo/hi[32][G] (int32)
     long long* base = s_tab;
     long long* delta = s_tab + n_groups;
@@ -94,6 +96,24 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // Staged truth tables: the CTA owns `chunk` consecutive individuals and copies their rows into shared memory
+    // BEFORE it waits for the kernel ahead of it (which never writes them) -- the copy hides behind that kernel's
+    // tail, and the population loop below reads bytes from shared memory instead of waiting one L2 round trip
+    // per individual.  That keeps the kernel short with FEW CTAs (four or more individuals per warp), which is
+    // what lets the next pass's counting kernel start beside it on the SMs it leaves free.
+    const int64_t c0 = (int64_t)blockIdx.x * chunk;
+    const int64_t c1 = c0 + chunk < n_ind ? c0 + chunk : n_ind;
+    uint8_t* s_lut = reinterpret_cast<uint8_t*>(s_tab) + lut_off;
+    if (lut_off > 0 && c0 < c1) {
+        const uint8_t* src = lut + (size_t)c0 * n_groups;
+        const int64_t n_bytes = (c1 - c0) * n_groups;
+        if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)n_bytes) & 15) == 0) {
+            for (int64_t i = threadIdx.x; i < n_bytes / 16; i += blockDim.x)
+                reinterpret_cast<uint4*>(s_lut)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        } else {
+            for (int64_t i = threadIdx.x; i < n_bytes; i += blockDim.x) s_lut[i] = __ldg(src + i);
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the producers' writes are visible from here on
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // Sharded cells: the counts are the sum of every rank's slot in the local exchange region, tagged
@@ -118,7 +138,7 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     constexpr int kMaxRounds = 8;  // register-prefetched rows: up to 256 groups
     const bool fast = n_groups <= 32 * kMaxRounds && !active && !out_diff_pg;
     uint32_t tab[kMaxRounds];
-    if (fast && warp0 < n_ind) {
+    if (fast && lut_off == 0 && warp0 < n_ind) {
 #pragma unroll
         for (int j = 0; j < kMaxRounds; ++j) {
             const int g = lane + 32 * j;
@@ -322,6 +342,29 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
         }
         __syncthreads();
     }
+    if (lut_off > 0) {
+        // staged tables (launch_population_fitness only stages when the fast conditions hold)
+        for (int64_t p = c0 + (threadIdx.x >> 5); p < c1; p += blockDim.x >> 5) {
+            const uint8_t* row = s_lut + (size_t)(p - c0) * n_groups;
+            long long total = 0;
+            for (int g = lane; g < n_groups; g += 32) {
+                const uint32_t table = row[g];
+                long long d = base[g];
+                if (wide) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if ((table >> k) & 1u) d += delta[k * n_groups + g];
+                } else {
+                    d += nib[(table & 15u) * n_groups + g] + nib[(16u + (table >> 4)) * n_groups + g];
+                }
+                total += d;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, off);
+            if (lane == 0) out_diff[p] = poisoned ? (long long)0x8000000000000000ull : total;
+        }
+        return;
+    }
     for (int64_t p = warp0; p < n_ind; p += n_warps) {
         long long total = 0;
         if (fast && !wide) {
@@ -455,22 +498,25 @@ static int launch_population_fitness(const int64_t* counts, int n_groups, int64_
         set_error("population_fitness: %d groups exceed the shared-memory table (max %d)", n_groups, (int)(200 * 1024 / 200));
         return SCB_ERR_UNSUPPORTED;
     }
-    static thread_local SmemMarks marks;
-    if (int rc = ensure_dynamic_smem((const void*)population_fitness_kernel, smem, marks)) return rc;
-    int64_t blocks = (n_individuals + 31) / 32;  // 32 warps per CTA, one individual per warp and round
+    // 32 warps per CTA and, by default, three individuals per warp: the kernel is dominated by its set-up (every
+    // CTA builds the tables), so fewer CTAs cost little time and leave SMs to the kernel that follows -- in the GA
+    // step the next pass's counting kernel, a programmatic dependent that claims its tiles dynamically.
+    // SCB_FITNESS_PER_WARP=k overrides (experiments).
+    int per_warp = 3;  // measured on H1M, population 4096: 22.8 / 19.6 / 18.0 / 18.8 / 20.1 us per step for 1 / 2 / 3 / 4 / 5
+    if (const char* e = getenv("SCB_FITNESS_PER_WARP")) per_warp = atoi(e) > 0 ? atoi(e) : 1;
+    int64_t blocks = (n_individuals + 32 * per_warp - 1) / (32 * per_warp);
     int64_t cap = (int64_t)sm_count();
     if (blocks > cap) blocks = cap;
-    // sharded cells, experiment (SCB_FITNESS_PER_WARP=k): every CTA sums the slots of all ranks (n_ranks x
-    // 16 G words from L2) before it can start; fewer CTAs with k individuals per warp trade that traffic
-    // for a longer loop.  Measured with 8 logical ranks on one device (tools/time_peers.py): no gain at
-    // k = 2, slower from k = 4 on -- off by default.
-    if (region && n_ranks > 1) {
-        if (const char* e = getenv("SCB_FITNESS_PER_WARP")) {
-            const int per_warp = atoi(e) > 0 ? atoi(e) : 1;
-            const int64_t fewer = (n_individuals + 32 * per_warp - 1) / (32 * per_warp);
-            if (fewer < blocks) blocks = fewer < 1 ? 1 : fewer;
-        }
+    if (blocks < 1) blocks = 1;
+    // staged truth tables (see the kernel): `chunk` consecutive individuals per CTA, rows in shared memory
+    const int64_t chunk = (n_individuals + blocks - 1) / blocks;
+    int lut_off = 0;
+    if (n_groups <= 256 && !active && !out_diff_pg && chunk * n_groups <= 64 * 1024 && !getenv("SCB_FITNESS_NO_STAGE")) {
+        lut_off = (int)((smem + 15) & ~(size_t)15);
+        smem = (size_t)lut_off + (size_t)((chunk * n_groups + 15) & ~(int64_t)15);
     }
+    static thread_local SmemMarks marks;
+    if (int rc = ensure_dynamic_smem((const void*)population_fitness_kernel, smem, marks)) return rc;
     // programmatic dependent launch: the kernel may start while its producer (scb_rule_counts in the
     // same stream) drains; it waits for it with griddepcontrol.wait before it reads the counts
     cudaLaunchConfig_t cfg = {};
@@ -502,7 +548,7 @@ static int launch_population_fitness(const int64_t* counts, int n_groups, int64_
     cfg.attrs = attr;
     cfg.numAttrs = n_attr;
     SCB_CUDA(cudaLaunchKernelEx(&cfg, population_fitness_kernel, counts, n_groups, n_individuals, lut, active,
-                                out_diff, out_diff_pg, region, rank, n_ranks, sums));
+                                out_diff, out_diff_pg, region, rank, n_ranks, sums, lut_off, (int)chunk));
     return SCB_OK;
 }
 

@@ -1,6 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2f.json 2> gpurun_out/bench_r2f.err; tail -2 gpurun_out/bench_r2f.err
-CELLS=131072 ITERS=1 ncu --set full --clock-control none --import-source on -k regex:koki_compact -c 2 -o gpurun_out/prof_kc python tools/time_sweep.py > gpurun_out/ncu_kc.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_sweep_launches_c.csv python tools/time_sweep.py > gpurun_out/ncu_kk_l3.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/k50_launches_c.csv python tools/run_k50.py > gpurun_out/ncu_k50_l3.log 2>&1
+run() { python bench.py --steps 40 --warmup 5 --sweep-steps 0 --no-cpu-baseline --no-e2e --no-e2e-dense 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('   step %.2f us  counts alone %.2f us  checksum %d' % (d['ms_per_step']*1e3, d['roofline']['kernel_ms']*1e3, d['config']['fitness_checksum']))"; }
+for st in 3 4 5 6; do echo "stages=$st"; SCB_COUNTS_STAGES=$st run; done

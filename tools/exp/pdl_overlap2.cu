@@ -41,20 +41,24 @@ static void launch(K k, int grid, int block, size_t smem, int us, cudaStream_t s
     cudaLaunchKernelEx(&cfg, k, us, sink);
 }
 template <int RA, int RB>
-static void run(cudaStream_t s, int blockB, int gridB) {
+static void run(cudaStream_t s, int blockB, int gridB, int blockA = 800, size_t smemA = 0, size_t smemB = 0) {
     const int ta = 13, tb = 20, K = 20;
     cudaFuncAttributes fa, fb;
+    cudaFuncSetAttribute(kA<RA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(kB<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(kA<RA>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(kB<RB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncGetAttributes(&fa, kA<RA>); cudaFuncGetAttributes(&fb, kB<RB>);
-    auto body = [&]() { for (int k = 0; k < K; ++k) { launch(kA<RA>, 148, 800, 0, ta, s); launch(kB<RB>, gridB, blockB, 0, tb, s); } };
+    auto body = [&]() { for (int k = 0; k < K; ++k) { launch(kA<RA>, 148, blockA, smemA, ta, s); launch(kB<RB>, gridB, blockB, smemB, tb, s); } };
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms = 0;
     body(); cudaStreamSynchronize(s);
     cudaEventRecord(e0, s); body(); cudaEventRecord(e1, s); cudaStreamSynchronize(s);
     cudaEventElapsedTime(&ms, e0, e1);
-    printf("A 800 thr x %d regs, B %d thr x %d regs, gridB=%d: %.1f us per pair (ta=%d tb=%d) err=%s\n", fa.numRegs, blockB, fb.numRegs, gridB, ms * 1e3 / K, ta, tb, cudaGetErrorString(cudaGetLastError()));
+    printf("A %d thr x %d regs %zu KB, B %d thr x %d regs %zu KB, gridB=%d: %.1f us per pair (ta=%d tb=%d) err=%s\n", blockA, fa.numRegs, smemA / 1024, blockB, fb.numRegs, smemB / 1024, gridB, ms * 1e3 / K, ta, tb, cudaGetErrorString(cudaGetLastError()));
 }
 int main() {
     cudaStream_t s; cudaStreamCreate(&s);
-    run<4, 4>(s, 1024, 128); run<60, 50>(s, 1024, 8); run<60, 50>(s, 1024, 128); run<60, 50>(s, 256, 128); run<60, 50>(s, 128, 128); run<40, 50>(s, 256, 128);
+    run<60, 50>(s, 256, 148, 544, 142 * 1024, 63 * 1024); run<60, 50>(s, 256, 148, 544, 0, 0); run<60, 50>(s, 1024, 128, 544, 142 * 1024, 63 * 1024); run<60, 50>(s, 384, 148, 672, 142 * 1024, 63 * 1024); run<60, 50>(s, 256, 148, 672, 142 * 1024, 63 * 1024); run<60, 50>(s, 256, 148, 672, 150 * 1024, 40 * 1024);
     return 0;
 }
