@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
-run() { python bench.py --steps 40 --warmup 5 --sweep-steps 0 --no-cpu-baseline --no-e2e --no-e2e-dense 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('   step %.2f us  counts alone %.2f us  checksum %d' % (d['ms_per_step']*1e3, d['roofline']['kernel_ms']*1e3, d['config']['fitness_checksum']))"; }
-for st in 3 4 5 6; do echo "stages=$st"; SCB_COUNTS_STAGES=$st run; done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r2g_n8.json 2> gpurun_out/bench_r2g_n8.err; tail -2 gpurun_out/bench_r2g_n8.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 tools/run_k50.py > gpurun_out/k50_r2g_n8.json 2> gpurun_out/k50_r2g_n8.err; tail -1 gpurun_out/k50_r2g_n8.json
