@@ -407,6 +407,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    numa_bound = device.bind_host_to_device()   # pinned host buffers on the GPU's own NUMA node
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -640,7 +641,8 @@ def run_ours(args):
                 assert int(out.sum()) == ga["checksum"], "host-buffer path disagrees with the device path"
             return {"value": units_per_step / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_step": int(in_bytes + lut_view.nbytes + targets.nbytes + parents.nbytes),
-                    "d2h_bytes_per_step": int(args.population * 8), "path": path}
+                    "d2h_bytes_per_step": int(args.population * 8), "path": path,
+                    "host_numa_bound_to_gpu": bool(numa_bound)}
 
         e2e = time_e2e(lambda: ws.load_planes(packed_view, args.cells), packed_view.nbytes,
                        "scb_host_load_planes (packed uint32 cell bitplanes, the layout the Python mirrors keep) + "

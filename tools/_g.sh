@@ -1,3 +1,12 @@
 cd $GRAFT_REPO_ROOT
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r2g_n8.json 2> gpurun_out/bench_r2g_n8.err; tail -2 gpurun_out/bench_r2g_n8.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 tools/run_k50.py > gpurun_out/k50_r2g_n8.json 2> gpurun_out/k50_r2g_n8.err; tail -1 gpurun_out/k50_r2g_n8.json
+nvidia-smi topo -m 2>/dev/null | head -6; lscpu | grep -i "numa\|socket" | head -6
+python - <<'PY'
+import os, sys
+sys.path.insert(0, '.')
+import torch
+from scbonita2_b200 import device
+print('affinity before', len(os.sched_getaffinity(0)))
+print('bound', device.bind_host_to_device(), 'affinity after', len(os.sched_getaffinity(0)), sorted(os.sched_getaffinity(0))[:4])
+PY
+python tools/time_e2e.py
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --sweep-steps 1 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('e2e', d['e2e']['ms_per_step'], d['e2e'].get('host_numa_bound_to_gpu'), 'dense', d['e2e_dense']['ms_per_step'], 'step', d['ms_per_step'], 'sweep e2e', d['sweep']['e2e']['seconds'])"
