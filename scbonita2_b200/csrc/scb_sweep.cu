@@ -151,10 +151,24 @@ struct SweepArgs {
     // lanes have started to settle and none did for `stop_stall` steps; open lanes go to the next pass
     int stop_open, stop_stall;
     int ring_stall;                 // the same stall rule in the shared-memory ring of the KO/KI and recheck passes
+    // Single runs (koki_plane_kernel, koki_compact_kernel<.., SINGLES>): a cell with ONE open run is deferred as that
+    // run alone -- entry = cell | which << 30 (which: 0 = KO, 1 = KI) -- in the same per-node arrays as the pairs,
+    // filled from the BACK (entry j of node n at cells[n * cap + cap - 1 - j]): a cell is in at most one of the two.
+    // The run that did settle is scored at once as if its partner will repeat; if the partner turns out not to, the
+    // settled run goes to the retract list and a last pass subtracts its contribution again.
+    int singles;                    // plane pass: defer single runs (else every open cell travels as a pair)
+    const unsigned int* in_count1;  // [N] single runs in the `in` arrays
+    unsigned int* out_count1;       // [N] single runs appended to the `out` arrays
+    int32_t* rt_cells;              // [N][rt_cap] retract list (filled from the back like the singles)
+    int64_t rt_cap;
+    unsigned int* rt_count;         // [N]
+    int negate;                     // compacted singles pass: subtract the scores (the retract pass), nothing else
     unsigned long long* out_raw;
     unsigned long long* out_missing;
     unsigned long long* out_keyerror;
 };
+constexpr int kWhichShift = 30;
+constexpr int32_t kCellMask = (1 << kWhichShift) - 1;
 
 // 32 x 32 bit transpose across a warp: lane i passes row i (bit j = element (i, j)) and receives
 // column i (bit j = element (j, i)).  Five exchange steps: at distance d the lanes i and i^d swap the
@@ -1778,15 +1792,27 @@ koki_plane_kernel(const SweepArgs args) {
     }
     // (the closing barrier of the last step ordered every store of copy xs; nothing below writes the state)
 
-    // ---- lanes still open: KO and KI of a cell travel together to the recheck list
-    const uint32_t both = ~frozen0 | ~frozen1;
-    if (both && warp == 0) {
-        const unsigned int k = __popc(both);
-        const unsigned int at0 = atomicAdd(&args.out_count[forced_node], k);
-        int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + at0;  // cap = n_cells: always room
-        for (uint32_t m = both; m; m &= m - 1) *dst++ = (int32_t)(word * 32 + (__ffs(m) - 1));
+    // ---- lanes still open go to the recheck list: a cell with both runs open as a pair, a cell with one run open
+    // as that run alone (args.singles), its settled partner being scored here as if the open run will repeat
+    const uint32_t open0 = ~frozen0, open1 = ~frozen1;
+    const uint32_t pairs = args.singles ? (open0 & open1) : (open0 | open1);
+    const uint32_t single0 = args.singles ? (open0 & ~open1) : 0u, single1 = args.singles ? (open1 & ~open0) : 0u;
+    if (warp == 0) {
+        if (pairs) {
+            const unsigned int k = __popc(pairs);
+            const unsigned int at0 = atomicAdd(&args.out_count[forced_node], k);
+            int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + at0;  // cap = n_cells: always room
+            for (uint32_t m = pairs; m; m &= m - 1) *dst++ = (int32_t)(word * 32 + (__ffs(m) - 1));
+        }
+        if (single0 | single1) {
+            const unsigned int k = __popc(single0) + __popc(single1);
+            const unsigned int at0 = atomicAdd(&args.out_count1[forced_node], k);
+            int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + (args.out_cap - 1 - at0);  // from the back
+            for (uint32_t m = single0; m; m &= m - 1) *dst-- = (int32_t)(word * 32 + (__ffs(m) - 1));
+            for (uint32_t m = single1; m; m &= m - 1) *dst-- = (int32_t)(word * 32 + (__ffs(m) - 1)) | (1 << kWhichShift);
+        }
     }
-    cellmask &= ~both;
+    const uint32_t cm0 = cellmask & ~pairs & ~single0, cm1 = cellmask & ~pairs & ~single1;  // lanes scored here, per slot
 
     // ---- scoring: a cell counts only if its KO run AND its KI run repeat (and the normal one)
     const uint32_t found_n = word_ok ? __ldg(args.np_found + word) : 0u;
@@ -1795,16 +1821,17 @@ koki_plane_kernel(const SweepArgs args) {
 #pragma unroll
         for (int b = 1; b < kLamPlanes; ++b) lamn_ge2 |= __ldg(args.np_lam + (size_t)b * wpad + word);
     }
-    const uint32_t valid = cellmask & found_n;  // every lane left in cellmask is frozen in both slots
+    const uint32_t valid0 = cm0 & found_n, valid1 = cm1 & found_n;  // every lane left in cm0 / cm1 is frozen in that slot
+    const uint32_t valid = valid0 | valid1;
     if (warp == 0) {
-        const uint32_t bad = __popc(cellmask & ~found_n);
+        const uint32_t bad = __popc(cm0 & cm1 & ~found_n);  // (a single run's cell is judged where that run settles)
         if (bad) atomicAdd(args.out_keyerror, (unsigned long long)bad);
     }
     unsigned long long score = 0;
     if (__any_sync(0xFFFFFFFFu, valid != 0)) {
         const uint32_t srd = s_lane + xs * kKkCopyBytes;
-        const bool cyc = __any_sync(0xFFFFFFFFu, (valid & (lam1_0 | lam1_1 | lamn_ge2)) != 0);
-        const uint32_t act2_0 = valid & lam1_0 & lamn_ge2, act2_1 = valid & lam1_1 & lamn_ge2;
+        const bool cyc = __any_sync(0xFFFFFFFFu, ((valid0 & (lam1_0 | lamn_ge2)) | (valid1 & (lam1_1 | lamn_ge2))) != 0);
+        const uint32_t act2_0 = valid0 & lam1_0 & lamn_ge2, act2_1 = valid1 & lam1_1 & lamn_ge2;
         const bool any2 = __any_sync(0xFFFFFFFFu, (act2_0 | act2_1) != 0);
         uint32_t sc = 0, sc1 = 0;
 #pragma unroll
@@ -1813,11 +1840,11 @@ koki_plane_kernel(const SweepArgs args) {
                 const size_t at = (size_t)(n0 + i) * wpad + word;
                 const uint2 s = kk_lds64(s_own + i * kKkRowBytes + xs * kKkCopyBytes);
                 const uint32_t ref0 = word_ok ? __ldg(args.np_states + at) : 0u;
-                sc += __popc((s.x ^ ref0) & valid) + __popc((s.y ^ ref0) & valid);
+                sc += __popc((s.x ^ ref0) & valid0) + __popc((s.y ^ ref0) & valid1);
                 if (cyc) {
                     const uint2 f = kk_eval(kk_lds64(s_tab + i * kKkEntryBytes), s_tab + i * kKkEntryBytes, srd);
                     const uint32_t ref1 = word_ok ? __ldg(args.np_states + (size_t)N * wpad + at) : 0u;
-                    sc1 += __popc((f.x ^ ref1) & valid) + __popc((f.y ^ ref1) & valid);
+                    sc1 += __popc((f.x ^ ref1) & valid0) + __popc((f.y ^ ref1) & valid1);
                     if (any2) {
                         const uint32_t ref2 = word_ok ? __ldg(args.np_states + (size_t)2 * N * wpad + at) : 0u;
                         sc1 += __popc((s.x ^ ref2) & act2_0) + __popc((s.y ^ ref2) & act2_1);
@@ -1856,7 +1883,8 @@ constexpr int kKcVoteWords = 3 * 4 * kKkSlots;  // three sets of up to four vote
 
 static size_t koki_cleanup_smem_bytes(int n_nodes) {
     return (size_t)(n_nodes + 1) * kKcRowBytes + (size_t)(n_nodes + kKkTabPad) * sizeof(KkEntry) + (size_t)kKcVoteWords * 4 +
-           (size_t)8 * kKkSlots * 4 + (size_t)kKcBatchCells * 4 + (size_t)(1 + kLamPlanes) * 32 * 4 + (size_t)(n_nodes + 1) * 4;
+           (size_t)8 * kKkSlots * 4 + (size_t)2 * kKcBatchCells * 4 + (size_t)(1 + kLamPlanes) * 64 * 4 + 64 * 4 +
+           (size_t)(n_nodes + 1) * 4;
 }
 
 template <int BASE, typename F>
@@ -1872,9 +1900,15 @@ __device__ __forceinline__ void kc_for_own(bool extra, F&& f) {
 // there; lanes still open -- longer cycles, no repeat -- go to the cleanup list): state_{t-1} and state_{t-2} of the
 // own nodes in registers, state_{t-3} and state_{t-4} read from the copies they live in (the oldest one is the copy
 // being overwritten), four vote words per slot.
-template <int BASE, bool RECHECK>
+// SINGLES: the batch is 2 048 single runs (SweepArgs::singles) instead of 1 024 KO/KI pairs: 64 virtual words, the
+// two slots of a lane are two unrelated words, the constant row holds per slot which of its runs are knock-ins, a
+// run is scored as if its partner (scored where it settled) repeats, and a run without a repeat sends that partner
+// to the retract list.  args.negate (with RECHECK): the retract pass -- scores are subtracted, nothing else is written.
+template <int BASE, bool RECHECK, bool SINGLES>
 __global__ void __launch_bounds__(kKcThreads, 1)
 koki_compact_kernel(const SweepArgs args) {
+    constexpr int NV = SINGLES ? 64 : 32;     // virtual words per batch
+    constexpr int kBatch = NV * 32;           // list entries per batch
     constexpr int MODE = RECHECK ? MODE_RECHECK : MODE_CLEANUP;  // (trace macros)
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = args.n_nodes;
@@ -1883,9 +1917,10 @@ koki_compact_kernel(const SweepArgs args) {
     KkEntry* table = reinterpret_cast<KkEntry*>(smem + (size_t)(N + 1) * 4 * kKkSlots);  // [N + pad]
     uint32_t* votes = reinterpret_cast<uint32_t*>(table + N + kKkTabPad);           // [3][2][64], recheck [3][4][64]
     uint32_t* res = votes + kKcVoteWords;                                       // [8][64]: lambda planes, cyc, fixed point
-    int* cellidx = reinterpret_cast<int*>(res + 8 * kKkSlots);                      // [32][32]
-    uint32_t* nrm = reinterpret_cast<uint32_t*>(cellidx + kKcBatchCells);           // [1 + kLamPlanes][32]
-    int* pre = reinterpret_cast<int*>(nrm + (1 + kLamPlanes) * 32);                 // [N + 1]
+    int* cellidx = reinterpret_cast<int*>(res + 8 * kKkSlots);                      // [NV][32] list entries (-1: none)
+    uint32_t* nrm = reinterpret_cast<uint32_t*>(cellidx + 2 * kKcBatchCells);       // [1 + kLamPlanes][NV]
+    uint32_t* kim = nrm + (1 + kLamPlanes) * 64;                                    // [64] singles: knock-in lanes of every slot
+    int* pre = reinterpret_cast<int*>(kim + 64);                                    // [N + 1]
     __shared__ int s_node;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef SCB_TRACE
@@ -1910,9 +1945,9 @@ koki_compact_kernel(const SweepArgs args) {
         int acc = 0;
         for (int k = 0; k < N; ++k) {
             pre[k] = acc;
-            int64_t c = args.in_count[k];
+            int64_t c = SINGLES ? args.in_count1[k] : args.in_count[k];
             if (c > args.in_cap) c = args.in_cap;
-            acc += (int)((c + kKcBatchCells - 1) / kKcBatchCells);
+            acc += (int)((c + kBatch - 1) / kBatch);
         }
         pre[N] = acc;
     }
@@ -1930,10 +1965,11 @@ koki_compact_kernel(const SweepArgs args) {
     // after a barrier every thread moves the pairs of its own nodes into place -- in copy k and, if k2 >= 0, in k2.
     auto gather = [&](const uint32_t* __restrict__ src_t, int k, int k2, int kstage) {
         const int nwp = args.nwp;
-        for (int v0 = warp; v0 < 32; v0 += 2 * kKcWarps) {
+        for (int v0 = warp; v0 < NV; v0 += 2 * kKcWarps) {
             const int v1 = v0 + kKcWarps;
-            const int c0 = cellidx[v0 * 32 + lane];
-            const int c1 = v1 < 32 ? cellidx[v1 * 32 + lane] : -1;
+            const int e0 = cellidx[v0 * 32 + lane];
+            const int e1 = v1 < NV ? cellidx[v1 * 32 + lane] : -1;
+            const int c0 = e0 >= 0 ? (e0 & kCellMask) : -1, c1 = e1 >= 0 ? (e1 & kCellMask) : -1;
             for (int j4 = 0; j4 < nwp; j4 += 4) {
                 uint4 x0 = make_uint4(0u, 0u, 0u, 0u), x1 = x0;
                 if (c0 >= 0) x0 = __ldg(reinterpret_cast<const uint4*>(src_t + (size_t)c0 * nwp + j4));
@@ -1942,15 +1978,17 @@ koki_compact_kernel(const SweepArgs args) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int v = h ? v1 : v0;
-                    if (v >= 32) break;
+                    if (v >= NV) break;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int nb = (j4 + q) * 32;
                         if (nb < N) {
                             const uint32_t mine = warp_transpose32(xw[h][q], lane);
                             const int n = nb + lane;
-                            if (n < N)
-                                *reinterpret_cast<uint2*>(state + ((size_t)n * 4 + kstage) * kKkSlots + 2 * ((v + n) & 31)) = make_uint2(mine, mine);
+                            if (n < N) {
+                                if (SINGLES) state[((size_t)n * 4 + kstage) * kKkSlots + ((v + n) & 63)] = mine;
+                                else *reinterpret_cast<uint2*>(state + ((size_t)n * 4 + kstage) * kKkSlots + 2 * ((v + n) & 31)) = make_uint2(mine, mine);
+                            }
                         }
                     }
                 }
@@ -1958,7 +1996,14 @@ koki_compact_kernel(const SweepArgs args) {
         }
         __syncthreads();
         kc_for_own<BASE>(extra, [&](int i) {
-            const uint2 x = kk_lds64(shared_addr(state) + (uint32_t)(n0 + i) * kKcRowBytes + kstage * kKcCopyBytes + 8 * ((lane + n0 + i) & 31));
+            uint2 x;
+            const uint32_t row = shared_addr(state) + (uint32_t)(n0 + i) * kKcRowBytes + kstage * kKcCopyBytes;
+            if (SINGLES) {
+                x.x = kk_lds32(row + 4 * ((2 * lane + n0 + i) & 63));
+                x.y = kk_lds32(row + 4 * ((2 * lane + 1 + n0 + i) & 63));
+            } else {
+                x = kk_lds64(row + 8 * ((lane + n0 + i) & 31));
+            }
             kk_sts64(s_own + i * kKcRowBytes + k * kKcCopyBytes, x);
             if (k2 >= 0) kk_sts64(s_own + i * kKcRowBytes + k2 * kKcCopyBytes, x);
         });
@@ -1976,11 +2021,13 @@ koki_compact_kernel(const SweepArgs args) {
         }
         __syncthreads();
         const int forced_node = s_node;
-        int64_t n_in = args.in_count[forced_node];
+        int64_t n_in = SINGLES ? args.in_count1[forced_node] : args.in_count[forced_node];
         if (n_in > args.in_cap) n_in = args.in_cap;
-        const int64_t batch_first = (int64_t)(batch - pre[forced_node]) * kKcBatchCells;
-        for (int i = tid; i < kKcBatchCells; i += kKcThreads)
-            cellidx[i] = batch_first + i < n_in ? args.in_cells[(size_t)forced_node * args.in_cap + batch_first + i] : -1;
+        const int64_t batch_first = (int64_t)(batch - pre[forced_node]) * kBatch;
+        for (int i = tid; i < kBatch; i += kKcThreads) {
+            const int64_t j = batch_first + i;  // (single runs are listed from the back of the node's array)
+            cellidx[i] = j < n_in ? args.in_cells[(size_t)forced_node * args.in_cap + (SINGLES ? args.in_cap - 1 - j : j)] : -1;
+        }
         if (forced_node != prev_forced && tid == 0) {
             if (prev_forced >= 0) {
                 int arity;
@@ -1991,9 +2038,26 @@ koki_compact_kernel(const SweepArgs args) {
         }
         prev_forced = forced_node;
         for (int i = tid; i < kKcVoteWords + 8 * kKkSlots; i += kKcThreads) votes[i] = 0u;  // votes and res
-        const int64_t left = n_in - (batch_first + (int64_t)lane * 32);
-        uint32_t cellmask = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << (int)left) - 1u : 0u);
+        // lanes in use, per slot: a pair batch has the same cells in both slots of a lane
+        auto lanes_of = [&](int v) -> uint32_t {
+            const int64_t left = n_in - (batch_first + (int64_t)v * 32);
+            return left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << (int)left) - 1u : 0u);
+        };
+        uint32_t cm0 = lanes_of(SINGLES ? 2 * lane : lane), cm1 = SINGLES ? lanes_of(2 * lane + 1) : cm0;
         __syncthreads();
+        uint32_t kim0 = 0u, kim1 = 0u;  // singles: the knock-in runs of my two slots
+        if constexpr (SINGLES) {
+            for (int v = warp; v < NV; v += kKcWarps) {
+                const int e = cellidx[v * 32 + lane];
+                const uint32_t bits = __ballot_sync(0xFFFFFFFFu, e >= 0 && ((e >> kWhichShift) & 1));
+                if (lane == 0) kim[v] = bits;
+            }
+            __syncthreads();
+            if (tid < 4 * kKkSlots) state[(size_t)N * 4 * kKkSlots + tid] = kim[tid & 63];  // the constant row, all four copies
+            kim0 = kim[2 * lane];
+            kim1 = kim[2 * lane + 1];
+            __syncthreads();
+        }
         SCB_SWEEP_PHASE(0);
 
         uint32_t lam0[kLamPlanes], lam1[kLamPlanes];  // cycle length of every lane, bit-sliced
@@ -2008,7 +2072,7 @@ koki_compact_kernel(const SweepArgs args) {
                 rb[i] = make_uint2(0u, 0u);
             });
             __syncthreads();
-            uint32_t frozen0 = ~cellmask, frozen1 = ~cellmask;
+            uint32_t frozen0 = ~cm0, frozen1 = ~cm1;
 #pragma unroll
             for (int b = 0; b < kLamPlanes; ++b) lam0[b] = lam1[b] = 0u;
             unsigned int last_open = 0xFFFFFFFFu;
@@ -2088,8 +2152,8 @@ koki_compact_kernel(const SweepArgs args) {
                     moved = last_open != 0xFFFFFFFFu;
                     last_open = n_open;
                     stall = 0;
-                } else if (moved && ++stall >= args.ring_stall) {
-                    return true;
+                } else if (moved && ++stall >= args.ring_stall && !args.negate) {
+                    return true;  // (the retract pass runs on: every one of its runs settles, it did before)
                 }
                 return false;
             };
@@ -2113,15 +2177,30 @@ koki_compact_kernel(const SweepArgs args) {
             }
             xn = (xs + 1) & 3;
             SCB_SWEEP_PHASE(2);
-            // lanes still open: KO and KI of a cell travel together to the cleanup list
-            const uint32_t both = ~frozen0 | ~frozen1;
-            if (both && warp == 0) {
-                const unsigned int k = __popc(both);
-                const unsigned int at0 = atomicAdd(&args.out_count[forced_node], k);
-                int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + at0;  // cap = n_cells: always room
-                for (uint32_t m = both; m; m &= m - 1) *dst++ = cellidx[lane * 32 + (__ffs(m) - 1)];
+            if constexpr (SINGLES) {
+                // runs still open go on alone (to the back of the cleanup arrays)
+                const uint32_t open0 = ~frozen0, open1 = ~frozen1;
+                if ((open0 | open1) && warp == 0 && !args.negate) {
+                    const unsigned int k = __popc(open0) + __popc(open1);
+                    const unsigned int at0 = atomicAdd(&args.out_count1[forced_node], k);
+                    int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + (args.out_cap - 1 - at0);
+                    for (uint32_t m = open0; m; m &= m - 1) *dst-- = cellidx[(2 * lane) * 32 + (__ffs(m) - 1)];
+                    for (uint32_t m = open1; m; m &= m - 1) *dst-- = cellidx[(2 * lane + 1) * 32 + (__ffs(m) - 1)];
+                }
+                cm0 &= ~open0;
+                cm1 &= ~open1;
+            } else {
+                // lanes still open: KO and KI of a cell travel together to the cleanup list
+                const uint32_t both = ~frozen0 | ~frozen1;
+                if (both && warp == 0) {
+                    const unsigned int k = __popc(both);
+                    const unsigned int at0 = atomicAdd(&args.out_count[forced_node], k);
+                    int32_t* dst = args.out_cells + (size_t)forced_node * args.out_cap + at0;  // cap = n_cells: always room
+                    for (uint32_t m = both; m; m &= m - 1) *dst++ = cellidx[lane * 32 + (__ffs(m) - 1)];
+                }
+                cm0 &= ~both;
+                cm1 &= ~both;
             }
-            cellmask &= ~both;
             found0 = frozen0;
             found1 = frozen1;
         }
@@ -2134,7 +2213,7 @@ koki_compact_kernel(const SweepArgs args) {
                 chk[i] = make_uint2(0u, 0u);
             });
             __syncthreads();
-            uint32_t resolved0 = ~cellmask, resolved1 = ~cellmask;
+            uint32_t resolved0 = ~cm0, resolved1 = ~cm1;
             int chk_time = -1;
             int vset = 0;
             const int t1_max = 2 * steps - 1;  // checkpoints at t = 2^k - 1 < steps - 1 and a last one at steps - 1 (see sweep_kernel)
@@ -2231,7 +2310,7 @@ koki_compact_kernel(const SweepArgs args) {
                     kk_sts64(s_own + i * kKcRowBytes, pq[i]);
                 });
                 __syncthreads();
-                const uint32_t has0 = planes_ge(lam0, 1) & cellmask, has1 = planes_ge(lam1, 1) & cellmask;
+                const uint32_t has0 = planes_ge(lam0, 1) & cm0, has1 = planes_ge(lam1, 1) & cm1;
                 int pc = 0;
                 for (int s = 0; s < steps; ++s) {
                     const uint32_t adv0 = planes_gt(lam0, s) & has0, adv1 = planes_gt(lam1, s) & has1;  // lanes that still owe P a step
@@ -2293,67 +2372,89 @@ koki_compact_kernel(const SweepArgs args) {
                 xn = qc ^ 1;
             }
         }
-        found0 &= cellmask;
-        found1 &= cellmask;
+        found0 &= cm0;
+        found1 &= cm1;
         SCB_SWEEP_PHASE(4);
 
         // ------------------------------------------------------------ outputs
         // normal-run info of the batch's cells: one 4-byte record per cell (bits 0..5 lambda, bit 6 found)
-        for (int v = warp; v < 32; v += kKcWarps) {
-            const int c = cellidx[v * 32 + lane];
-            const uint32_t rec = c >= 0 ? __ldg(args.np_info_t + c) : 0u;
+        for (int v = warp; v < NV; v += kKcWarps) {
+            const int e = cellidx[v * 32 + lane];
+            const uint32_t rec = e >= 0 ? __ldg(args.np_info_t + (e & kCellMask)) : 0u;
 #pragma unroll
             for (int b = 0; b <= kLamPlanes; ++b) {
                 const uint32_t bits = __ballot_sync(0xFFFFFFFFu, (rec >> b) & 1u);
-                if (lane == 0) nrm[(b == kLamPlanes ? 0 : 1 + b) * 32 + v] = bits;
+                if (lane == 0) nrm[(b == kLamPlanes ? 0 : 1 + b) * NV + v] = bits;
             }
         }
         __syncthreads();
-        const uint32_t found_n = nrm[lane];
-        uint32_t lamn[kLamPlanes];
+        // (pairs: both slots of a lane hold the same cells; singles: two unrelated words)
+        const int nv0 = SINGLES ? 2 * lane : lane, nv1 = SINGLES ? 2 * lane + 1 : lane;
+        const uint32_t found_n0 = nrm[nv0], found_n1 = nrm[nv1];
+        // "the normal run's cycle is at least t long", per slot, from the planes in shared memory
+        auto lamn_ge = [&](int nv, int t) -> uint32_t {
+            uint32_t l[kLamPlanes];
 #pragma unroll
-        for (int b = 0; b < kLamPlanes; ++b) lamn[b] = nrm[(1 + b) * 32 + lane];
-        // a cell counts only if its KO run AND its KI run repeat (and the normal one)
-        const uint32_t valid = found0 & found1 & found_n;
-        if (warp == 0) {
-            const uint32_t m0 = __popc(~found0 & cellmask), m1 = __popc(~found1 & cellmask);
-            if (m0) atomicAdd(args.out_missing + 1 + 2 * forced_node, (unsigned long long)m0);
-            if (m1) atomicAdd(args.out_missing + 2 + 2 * forced_node, (unsigned long long)m1);
-            const uint32_t bad = __popc(found0 & found1 & ~found_n);
+            for (int b = 0; b < kLamPlanes; ++b) l[b] = nrm[(1 + b) * NV + nv];
+            return planes_ge(l, t);
+        };
+        // a cell counts only if its KO run AND its KI run repeat (and the normal one); a single run's partner has
+        // repeated already, where it settled
+        const uint32_t valid0 = SINGLES ? (found0 & found_n0) : (found0 & found1 & found_n0);
+        const uint32_t valid1 = SINGLES ? (found1 & found_n1) : valid0;
+        if (warp == 0 && !args.negate) {
+            const uint32_t miss0 = ~found0 & cm0, miss1 = ~found1 & cm1;
+            // (pairs: slot 0 is the knock-out, slot 1 the knock-in; singles: kim0 / kim1 say which run is which)
+            const uint32_t m_ko = SINGLES ? __popc(miss0 & ~kim0) + __popc(miss1 & ~kim1) : __popc(miss0);
+            const uint32_t m_ki = SINGLES ? __popc(miss0 & kim0) + __popc(miss1 & kim1) : __popc(miss1);
+            if (m_ko) atomicAdd(args.out_missing + 1 + 2 * forced_node, (unsigned long long)m_ko);
+            if (m_ki) atomicAdd(args.out_missing + 2 + 2 * forced_node, (unsigned long long)m_ki);
+            const uint32_t bad = SINGLES ? __popc(found0 & ~found_n0) + __popc(found1 & ~found_n1) : __popc(found0 & found1 & ~found_n0);
             if (bad) atomicAdd(args.out_keyerror, (unsigned long long)bad);
+            if constexpr (SINGLES) {
+                // a run without a repeat: its partner was scored as if there were one -- the partner goes to the retract list
+                const uint32_t r0 = miss0 & found_n0, r1 = miss1 & found_n1;
+                if (r0 | r1) {
+                    const unsigned int k = __popc(r0) + __popc(r1);
+                    const unsigned int at0 = atomicAdd(&args.rt_count[forced_node], k);
+                    int32_t* dst = args.rt_cells + (size_t)forced_node * args.rt_cap + (args.rt_cap - 1 - at0);
+                    for (uint32_t m = r0; m; m &= m - 1) *dst-- = cellidx[(2 * lane) * 32 + (__ffs(m) - 1)] ^ (1 << kWhichShift);
+                    for (uint32_t m = r1; m; m &= m - 1) *dst-- = cellidx[(2 * lane + 1) * 32 + (__ffs(m) - 1)] ^ (1 << kWhichShift);
+                }
+            }
         }
         unsigned long long score = 0;
-        if (__any_sync(0xFFFFFFFFu, valid != 0)) {
+        if (__any_sync(0xFFFFFFFFu, (valid0 | valid1) != 0)) {
             // offset 0: the frozen states against the normal run's state_mu, gathered into the pair of copies
             // that xs / xn do not use
             gather(args.np_states_t, xs ^ 2, -1, xn ^ 2);
-            const uint32_t ge2_0 = planes_ge(lam0, 2), ge2_1 = planes_ge(lam1, 2), gen2 = planes_ge(lamn, 2);
-            const uint32_t both2_0 = valid & ge2_0 & gen2, both2_1 = valid & ge2_1 & gen2;
+            const uint32_t ge2_0 = planes_ge(lam0, 2), ge2_1 = planes_ge(lam1, 2);
+            const uint32_t gen2_0 = lamn_ge(nv0, 2), gen2_1 = SINGLES ? lamn_ge(nv1, 2) : gen2_0;
+            const uint32_t both2_0 = valid0 & ge2_0 & gen2_0, both2_1 = valid1 & ge2_1 & gen2_1;
             uint32_t sc = 0, sc_both2 = 0;
             kc_for_own<BASE>(extra, [&](int i) {
-                if (n0 + i < N) {
-                    const uint32_t ref = kk_lds64(s_own + i * kKcRowBytes + (xs ^ 2) * kKcCopyBytes).x;
-                    const uint2 s = kk_lds64(s_own + i * kKcRowBytes + xs * kKcCopyBytes);
-                    const uint32_t x0 = (s.x ^ ref) & valid, x1 = (s.y ^ ref) & valid;
-                    sc += __popc(x0) + __popc(x1);
-                    sc_both2 += __popc(x0 & both2_0) + __popc(x1 & both2_1);
-                }
+                const uint2 ref = kk_lds64(s_own + i * kKcRowBytes + (xs ^ 2) * kKcCopyBytes);
+                const uint2 s = kk_lds64(s_own + i * kKcRowBytes + xs * kKcCopyBytes);
+                const uint32_t x0 = (s.x ^ ref.x) & valid0, x1 = (s.y ^ ref.y) & valid1;
+                sc += __popc(x0) + __popc(x1);
+                sc_both2 += __popc(x0 & both2_0) + __popc(x1 & both2_1);
             });
             score = sc;
-            if (!__any_sync(0xFFFFFFFFu, (valid & (ge2_0 | ge2_1 | gen2)) != 0)) {
+            if (!__any_sync(0xFFFFFFFFu, ((valid0 & (ge2_0 | gen2_0)) | (valid1 & (ge2_1 | gen2_1))) != 0)) {
                 score *= 2;  // every counted cell: fixed point vs fixed point, offset 1 repeats offset 0
             } else {
                 // offsets 1..min(lambda_x, lambda_n): step, and compare the new state while it is made.  With no
                 // period above 2 in the batch, offset 2 is offset 0 again for the period-2 pairs: one step suffices.
-                const bool short_cycles = !__any_sync(0xFFFFFFFFu, (valid & (planes_ge(lam0, 3) | planes_ge(lam1, 3) | planes_ge(lamn, 3))) != 0);
+                const uint32_t gen3_0 = lamn_ge(nv0, 3), gen3_1 = SINGLES ? lamn_ge(nv1, 3) : gen3_0;
+                const bool short_cycles = !__any_sync(0xFFFFFFFFu, ((valid0 & (planes_ge(lam0, 3) | gen3_0)) | (valid1 & (planes_ge(lam1, 3) | gen3_1))) != 0);
                 __syncthreads();  // (offset 0 read the reference copy; the next gather parks words in its partner)
                 for (int t = 1; t < steps; ++t) {
                     if (short_cycles && t == 2) {
                         score += sc_both2;
                         break;
                     }
-                    const uint32_t gn = planes_ge(lamn, t);
-                    const uint32_t act0 = valid & planes_ge(lam0, t) & gn, act1 = valid & planes_ge(lam1, t) & gn;
+                    const uint32_t gn0 = lamn_ge(nv0, t), gn1 = SINGLES ? lamn_ge(nv1, t) : gn0;
+                    const uint32_t act0 = valid0 & planes_ge(lam0, t) & gn0, act1 = valid1 & planes_ge(lam1, t) & gn1;
                     if (!__any_sync(0xFFFFFFFFu, (act0 | act1) != 0)) break;
                     gather(args.np_states_t + (size_t)t * args.wpad * 32 * args.nwp, xs ^ 2, -1, xn ^ 2);
                     const uint32_t srd = s_lane + xs * kKcCopyBytes;
@@ -2363,9 +2464,9 @@ koki_compact_kernel(const SweepArgs args) {
                         const uint2 e = e_next;
                         e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
                         const uint2 f = kk_eval<kKcRowBytes>(e, s_tab + i * kKkEntryBytes, srd);
-                        const uint32_t ref = kk_lds64(s_own + i * kKcRowBytes + (xs ^ 2) * kKcCopyBytes).x;
+                        const uint2 ref = kk_lds64(s_own + i * kKcRowBytes + (xs ^ 2) * kKcCopyBytes);
                         kk_sts64(s_own + i * kKcRowBytes + xn * kKcCopyBytes, f);
-                        sct += __popc((f.x ^ ref) & act0) + __popc((f.y ^ ref) & act1);
+                        sct += __popc((f.x ^ ref.x) & act0) + __popc((f.y ^ ref.y) & act1);
                     });
                     score += sct;
                     __syncthreads();
@@ -2375,6 +2476,7 @@ koki_compact_kernel(const SweepArgs args) {
                 }
             }
         }
+        if (args.negate) score = 0ull - score;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) score += __shfl_xor_sync(0xFFFFFFFFu, score, off);
         if (lane == 0 && score) atomicAdd(args.out_raw + forced_node, score);
@@ -2471,6 +2573,9 @@ struct SweepLists {
     int32_t* cells_b;
     int64_t cap_b;
     unsigned int* count_b;
+    unsigned int* count_a1;  // single runs in list A / list B (filled from the back), retract list (in list A's arrays)
+    unsigned int* count_b1;
+    unsigned int* count_r;
 };
 
 template <int SLOTS>
@@ -2485,8 +2590,8 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
         for (int k = 0; k < 4; ++k)
             if (int rc = ensure_dynamic_smem(kernels[k], smem, marks[k])) return rc;
     }
-    // settle_hist | key_hist | bucket_fill | count_a | count_b | counters are contiguous
-    SCB_CUDA(cudaMemsetAsync(args.settle_hist, 0, 3 * 64 * 4 + (size_t)args.n_nodes * 8 + 16, stream));
+    // count_a1 | count_b1 | count_r | settle_hist | key_hist | bucket_fill | count_a | count_b | counters are contiguous
+    SCB_CUDA(cudaMemsetAsync(lists.count_a1, 0, (size_t)args.n_nodes * 12 + 3 * 64 * 4 + (size_t)args.n_nodes * 8 + 16, stream));
     args.in_cells = nullptr;
     args.in_cap = 0;
     args.in_count = nullptr;
@@ -2552,6 +2657,9 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
     args.out_cells = two_level ? lists.cells_a : lists.cells_b;
     args.out_cap = two_level ? lists.cap_a : lists.cap_b;
     args.out_count = two_level ? lists.count_a : lists.count_b;
+    args.out_count1 = lists.count_a1;
+    args.singles = 0;
+    args.negate = 0;
     const int64_t n_koki = ((n_words + HALF - 1) / HALF) * args.n_nodes;
     if (n_koki >= ((int64_t)1 << 31)) {
         set_error("ko_ki_sweep: %lld (word block, node) pairs exceed one grid; shard the cells", (long long)n_koki);
@@ -2563,6 +2671,15 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
     const char* koki_env = getenv("SCB_SWEEP_KOKI");
     const bool plane2 = SLOTS == 64 && two_level && args.n_nodes <= kKkWarps * 13 && !(koki_env && koki_env[0] == 'o') &&
                         koki_plane_smem_bytes(args.n_nodes) <= kMaxDynSmem;
+    {
+        // single runs need all three new kernels (the sweep_kernel modes know pairs only) and 30-bit cell indices
+        const char* rc_e = getenv("SCB_SWEEP_RECHECK");
+        const char* cl_e = getenv("SCB_SWEEP_CLEANUP");
+        const char* sg_e = getenv("SCB_SWEEP_SINGLES");  // =0: every open cell travels as a pair
+        args.singles = plane2 && !(rc_e && rc_e[0] == 'o') && !(cl_e && cl_e[0] == 'o') && !(sg_e && sg_e[0] == '0') &&
+                       args.n_nodes / kKcWarps <= 8 && koki_cleanup_smem_bytes(args.n_nodes) <= kMaxDynSmem &&
+                       args.wpad * 32 < ((int64_t)1 << kWhichShift);
+    }
     if (plane2) {
         static const void* const kk[13] = {
             (const void*)koki_plane_kernel<1>, (const void*)koki_plane_kernel<2>, (const void*)koki_plane_kernel<3>,
@@ -2584,53 +2701,81 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
         SCB_LAUNCH_CHECK("sweep_kernel<koki>");
     }
     int per_sm = smem <= kMaxDynSmem / 2 ? 2 : 1;
+    // the compacted passes: koki_compact_kernel<BASE, RECHECK, SINGLES> whenever the nodes fit
+    // (SCB_SWEEP_RECHECK=old / SCB_SWEEP_CLEANUP=old keep the sweep_kernel modes; they know pairs only)
+    const int kc_base = args.n_nodes / kKcWarps;
+    const bool compact_fits = SLOTS == 64 && kc_base <= 8 && koki_cleanup_smem_bytes(args.n_nodes) <= kMaxDynSmem;
+    auto launch_compact = [&](bool recheck, bool single_runs, const char* what) -> int {
+        static const void* const table[2][2][9] = {
+            {{(const void*)koki_compact_kernel<0, false, false>, (const void*)koki_compact_kernel<1, false, false>, (const void*)koki_compact_kernel<2, false, false>,
+              (const void*)koki_compact_kernel<3, false, false>, (const void*)koki_compact_kernel<4, false, false>, (const void*)koki_compact_kernel<5, false, false>,
+              (const void*)koki_compact_kernel<6, false, false>, (const void*)koki_compact_kernel<7, false, false>, (const void*)koki_compact_kernel<8, false, false>},
+             {(const void*)koki_compact_kernel<0, false, true>, (const void*)koki_compact_kernel<1, false, true>, (const void*)koki_compact_kernel<2, false, true>,
+              (const void*)koki_compact_kernel<3, false, true>, (const void*)koki_compact_kernel<4, false, true>, (const void*)koki_compact_kernel<5, false, true>,
+              (const void*)koki_compact_kernel<6, false, true>, (const void*)koki_compact_kernel<7, false, true>, (const void*)koki_compact_kernel<8, false, true>}},
+            {{(const void*)koki_compact_kernel<0, true, false>, (const void*)koki_compact_kernel<1, true, false>, (const void*)koki_compact_kernel<2, true, false>,
+              (const void*)koki_compact_kernel<3, true, false>, (const void*)koki_compact_kernel<4, true, false>, (const void*)koki_compact_kernel<5, true, false>,
+              (const void*)koki_compact_kernel<6, true, false>, (const void*)koki_compact_kernel<7, true, false>, (const void*)koki_compact_kernel<8, true, false>},
+             {(const void*)koki_compact_kernel<0, true, true>, (const void*)koki_compact_kernel<1, true, true>, (const void*)koki_compact_kernel<2, true, true>,
+              (const void*)koki_compact_kernel<3, true, true>, (const void*)koki_compact_kernel<4, true, true>, (const void*)koki_compact_kernel<5, true, true>,
+              (const void*)koki_compact_kernel<6, true, true>, (const void*)koki_compact_kernel<7, true, true>, (const void*)koki_compact_kernel<8, true, true>}}};
+        static thread_local SmemMarks marks[2][2][9];
+        const void* kernel = table[recheck ? 1 : 0][single_runs ? 1 : 0][kc_base];
+        const size_t kc_smem = koki_cleanup_smem_bytes(args.n_nodes);
+        if (int rc = ensure_dynamic_smem(kernel, kc_smem, marks[recheck ? 1 : 0][single_runs ? 1 : 0][kc_base])) return rc;
+        void* kargs[1] = {(void*)&args};
+        SCB_CUDA(cudaLaunchKernel(kernel, dim3((unsigned)sm_count()), dim3(kKcThreads), kargs, kc_smem, stream));
+        SCB_LAUNCH_CHECK(what);
+        return SCB_OK;
+    };
+    const char* rc_env = getenv("SCB_SWEEP_RECHECK");
+    const char* cl_env = getenv("SCB_SWEEP_CLEANUP");
+    const bool new_recheck = compact_fits && !(rc_env && rc_env[0] == 'o');
+    const bool new_cleanup = compact_fits && !(cl_env && cl_env[0] == 'o');
+    args.negate = 0;
     if (two_level) {
-        // slow convergers, compacted: a persistent grid runs the full-length ring on list A
+        // slow convergers, compacted: a persistent grid runs the full-length ring on list A (pairs, then single runs)
         args.in_cells = lists.cells_a;
         args.in_cap = lists.cap_a;
         args.in_count = lists.count_a;
+        args.in_count1 = lists.count_a1;
         args.out_cells = lists.cells_b;
         args.out_cap = lists.cap_b;
         args.out_count = lists.count_b;
-        const char* rc_env = getenv("SCB_SWEEP_RECHECK");  // =old keeps sweep_kernel<SLOTS, MODE_RECHECK>
-        const int rc_base = args.n_nodes / kKcWarps;
-        if (SLOTS == 64 && rc_base <= 8 && !(rc_env && rc_env[0] == 'o') && koki_cleanup_smem_bytes(args.n_nodes) <= kMaxDynSmem) {
-            static const void* const kr[9] = {
-                (const void*)koki_compact_kernel<0, true>, (const void*)koki_compact_kernel<1, true>, (const void*)koki_compact_kernel<2, true>,
-                (const void*)koki_compact_kernel<3, true>, (const void*)koki_compact_kernel<4, true>, (const void*)koki_compact_kernel<5, true>,
-                (const void*)koki_compact_kernel<6, true>, (const void*)koki_compact_kernel<7, true>, (const void*)koki_compact_kernel<8, true>};
-            static thread_local SmemMarks kr_marks[9];
-            const size_t kr_smem = koki_cleanup_smem_bytes(args.n_nodes);
-            if (int rc = ensure_dynamic_smem(kr[rc_base], kr_smem, kr_marks[rc_base])) return rc;
-            void* kargs[1] = {(void*)&args};
-            SCB_CUDA(cudaLaunchKernel(kr[rc_base], dim3((unsigned)sm_count()), dim3(kKcThreads), kargs, kr_smem, stream));
-            SCB_LAUNCH_CHECK("koki_compact_kernel<recheck>");
+        args.out_count1 = lists.count_b1;
+        if (new_recheck) {
+            if (int rc = launch_compact(true, false, "koki_compact_kernel<recheck>")) return rc;
+            if (args.singles)
+                if (int rc = launch_compact(true, true, "koki_compact_kernel<recheck, singles>")) return rc;
         } else {
             sweep_kernel<SLOTS, MODE_RECHECK><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
             SCB_LAUNCH_CHECK("sweep_kernel<recheck>");
         }
     }
-    // stragglers, compacted: the general slow path on list B
+    // stragglers, compacted: the general slow path on list B (pairs, then single runs, then the retract list)
     args.in_cells = lists.cells_b;
     args.in_cap = lists.cap_b;
     args.in_count = lists.count_b;
+    args.in_count1 = lists.count_b1;
     args.out_cells = nullptr;
     args.out_cap = 0;
     args.out_count = nullptr;
-    // the 768-thread kernel whenever the nodes fit (SCB_SWEEP_CLEANUP=old keeps sweep_kernel<SLOTS, MODE_CLEANUP>)
-    const char* cl_env = getenv("SCB_SWEEP_CLEANUP");
-    const int cl_base = args.n_nodes / kKcWarps;
-    if (SLOTS == 64 && cl_base <= 8 && !(cl_env && cl_env[0] == 'o') && koki_cleanup_smem_bytes(args.n_nodes) <= kMaxDynSmem) {
-        static const void* const kc[9] = {
-            (const void*)koki_compact_kernel<0, false>, (const void*)koki_compact_kernel<1, false>, (const void*)koki_compact_kernel<2, false>,
-            (const void*)koki_compact_kernel<3, false>, (const void*)koki_compact_kernel<4, false>, (const void*)koki_compact_kernel<5, false>,
-            (const void*)koki_compact_kernel<6, false>, (const void*)koki_compact_kernel<7, false>, (const void*)koki_compact_kernel<8, false>};
-        static thread_local SmemMarks kc_marks[9];
-        const size_t kc_smem = koki_cleanup_smem_bytes(args.n_nodes);
-        if (int rc = ensure_dynamic_smem(kc[cl_base], kc_smem, kc_marks[cl_base])) return rc;
-        void* kargs[1] = {(void*)&args};
-        SCB_CUDA(cudaLaunchKernel(kc[cl_base], dim3((unsigned)sm_count()), dim3(kKcThreads), kargs, kc_smem, stream));
-        SCB_LAUNCH_CHECK("koki_compact_kernel<cleanup>");
+    args.out_count1 = nullptr;
+    args.rt_cells = lists.cells_a;  // (list A is spent by now)
+    args.rt_cap = lists.cap_a;
+    args.rt_count = lists.count_r;
+    if (new_cleanup) {
+        if (int rc = launch_compact(false, false, "koki_compact_kernel<cleanup>")) return rc;
+        if (args.singles) {
+            if (int rc = launch_compact(false, true, "koki_compact_kernel<cleanup, singles>")) return rc;
+            // runs whose partner did not repeat after all: simulate them once more and take their scores back
+            args.in_cells = lists.cells_a;
+            args.in_cap = lists.cap_a;
+            args.in_count1 = lists.count_r;
+            args.negate = 1;
+            if (int rc = launch_compact(true, true, "koki_compact_kernel<retract>")) return rc;
+            args.negate = 0;
+        }
     } else {
         sweep_kernel<SLOTS, MODE_CLEANUP><<<(unsigned)(sm_count() * per_sm), kSweepThreads, smem, stream>>>(args);
         SCB_LAUNCH_CHECK("sweep_kernel<cleanup>");
@@ -2663,7 +2808,7 @@ extern "C" int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int 
            (int64_t)(steps + 1) * wpad * 32 * record_words(n_nodes) * 4 + wpad * 32 * 4 +
            (int64_t)n_nodes * (sweep_list_capacity(wpad * 32, kListDivA) + sweep_list_capacity(wpad * 32, kListDivB)) * 4 +
            ((int64_t)n_nodes + 6) * wpad * 4 +
-           3 * 64 * 4 + (int64_t)n_nodes * 8 + 16;
+           (int64_t)n_nodes * 12 + 3 * 64 * 4 + (int64_t)n_nodes * 8 + 16;
 }
 
 extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
@@ -2705,7 +2850,10 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     lists.cells_b = lists.cells_a + (size_t)n_nodes * lists.cap_a;
     uint32_t* planes_sorted = reinterpret_cast<uint32_t*>(lists.cells_b + (size_t)n_nodes * lists.cap_b);
     args.key_planes = planes_sorted + (size_t)n_nodes * wpad;
-    args.settle_hist = reinterpret_cast<unsigned int*>(args.key_planes + (size_t)6 * wpad);
+    lists.count_a1 = reinterpret_cast<unsigned int*>(args.key_planes + (size_t)6 * wpad);
+    lists.count_b1 = lists.count_a1 + n_nodes;
+    lists.count_r = lists.count_b1 + n_nodes;
+    args.settle_hist = lists.count_r + n_nodes;
     args.key_hist = args.settle_hist + 64;
     unsigned int* bucket_fill = args.key_hist + 64;
     lists.count_a = bucket_fill + 64;
