@@ -1743,6 +1743,8 @@ koki_plane_kernel(const SweepArgs args) {
             kk_sts64(s_own + i * kKkRowBytes + WR * kKkCopyBytes, w);
         }
         uint32_t* v = votes + vset * 2 * kKkSlots;
+        q1x &= ~frozen0; q2x &= ~frozen0;  // only open lanes matter: a word whose lanes have all settled votes nothing
+        q1y &= ~frozen1; q2y &= ~frozen1;
         if (q1x) atomicOr(v + 2 * lane, q1x);
         if (q1y) atomicOr(v + 2 * lane + 1, q1y);
         if (q2x) atomicOr(v + kKkSlots + 2 * lane, q2x);
@@ -2870,7 +2872,7 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     // SCB_SWEEP_SORT=0 keeps the caller's cell order (experiments, tests of both paths)
     bool sort_cells = true;
     if (const char* e = getenv("SCB_SWEEP_SORT")) sort_cells = e[0] != '0';
-    args.stop_open = 24;
+    args.stop_open = 64;  // (24 before single runs made a deferred run half as expensive; flat between 64 and 160)
     args.stop_stall = 4;
     if (const char* e = getenv("SCB_SWEEP_STOP_OPEN")) args.stop_open = atoi(e) >= 0 ? atoi(e) : 0;
     if (const char* e = getenv("SCB_SWEEP_STOP_STALL")) args.stop_stall = atoi(e) > 0 ? atoi(e) : (1 << 30);

@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python tools/run_k50.py 2>&1 | tail -1 | cut -c90-330
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_sweep_launches_d.csv python tools/time_sweep.py > gpurun_out/ncu_kk_l4.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_sweep.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -2
+for i in 1 2 3; do ITERS=3 python tools/time_sweep.py | tail -1 | cut -c1-40; done
