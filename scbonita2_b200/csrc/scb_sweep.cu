@@ -163,6 +163,7 @@ struct SweepArgs {
     int64_t rt_cap;
     unsigned int* rt_count;         // [N]
     int negate;                     // compacted singles pass: subtract the scores (the retract pass), nothing else
+    int brent_mid;                  // cleanup pass: keep the permanent mid-window checkpoint (SCB_SWEEP_BRENT_MID=0: off)
     unsigned long long* out_raw;
     unsigned long long* out_missing;
     unsigned long long* out_keyerror;
@@ -1556,6 +1557,9 @@ sweep_kernel(const SweepArgs args) {
 // Scoring needs at most one more step: a lane frozen by this ring has period 1 or 2, so its states at
 // offsets 0, 1, 2 are s, step(s), s (align_attractors, importance_scores.py:325-340).
 // ---------------------------------------------------------------------------------------
+#ifndef SCB_KK_REG_NODES
+#define SCB_KK_REG_NODES 10  // measured on imp-1M: 58.6 / 58.0 / 58.1 / 57.2 / 58.8 ms for 0 / 4 / 6 / 10 / 13
+#endif
 constexpr int kKkThreads = 512, kKkWarps = 16, kKkSlots = 64;
 constexpr int kKkRow = 2 * kKkSlots;  // words per node: [copy][slot]
 constexpr int kKkRowBytes = kKkRow * 4, kKkCopyBytes = kKkSlots * 4;
@@ -1700,12 +1704,15 @@ koki_plane_kernel(const SweepArgs args) {
     const uint32_t s_own = s_lane + n0 * kKkRowBytes;
     const uint32_t s_tab = shared_addr(table) + n0 * kKkEntryBytes;
     // ---- data -> copy 1 (both slots of a word start from the same state); padding rows: zero in both copies
+    constexpr int KR = CNT < SCB_KK_REG_NODES ? CNT : SCB_KK_REG_NODES;
+    uint2 cur[KR > 0 ? KR : 1];
 #pragma unroll
     for (int i = 0; i < CNT; ++i) {
         const bool real = n0 + i < N;
         const uint32_t v = (real && word_ok) ? __ldg(args.planes + (size_t)(n0 + i) * wpad + word) : 0u;
         kk_sts64(s_own + i * kKkRowBytes + kKkCopyBytes, make_uint2(v, v));
         if (!real) kk_sts64(s_own + i * kKkRowBytes, make_uint2(0u, 0u));
+        if (i < KR) cur[i < KR ? i : 0] = make_uint2(v, v);
     }
     __syncthreads();
 
@@ -1731,7 +1738,8 @@ koki_plane_kernel(const SweepArgs args) {
             const uint2 e = e_next;
             if (i + 1 < CNT) e_next = kk_lds64(s_tab + (i + 1) * kKkEntryBytes);
             const uint2 old2 = kk_lds64(s_own + i * kKkRowBytes + WR * kKkCopyBytes);
-            const uint2 c1 = kk_lds64(s_own + i * kKkRowBytes + RD * kKkCopyBytes);
+            // state_{t-1} of the first KR own nodes stays in registers (the ones the 64-register budget has room for)
+            const uint2 c1 = i < KR ? cur[i < KR ? i : 0] : kk_lds64(s_own + i * kKkRowBytes + RD * kKkCopyBytes);
             const uint2 f = kk_eval(e, s_tab + i * kKkEntryBytes, srd);
             q1x |= f.x ^ c1.x;
             q1y |= f.y ^ c1.y;
@@ -1741,6 +1749,7 @@ koki_plane_kernel(const SweepArgs args) {
             w.x = (f.x & ~frozen0) | (c1.x & frozen0);
             w.y = (f.y & ~frozen1) | (c1.y & frozen1);
             kk_sts64(s_own + i * kKkRowBytes + WR * kKkCopyBytes, w);
+            if (i < KR) cur[i < KR ? i : 0] = w;
         }
         uint32_t* v = votes + vset * 2 * kKkSlots;
         q1x &= ~frozen0; q2x &= ~frozen0;  // only open lanes matter: a word whose lanes have all settled votes nothing
@@ -2218,11 +2227,19 @@ koki_compact_kernel(const SweepArgs args) {
             uint32_t resolved0 = ~cm0, resolved1 = ~cm1;
             int chk_time = -1;
             int vset = 0;
-            const int t1_max = 2 * steps - 1;  // checkpoints at t = 2^k - 1 < steps - 1 and a last one at steps - 1 (see sweep_kernel)
+            // Checkpoints at t = 2^k - 1 < steps - 1, a last one at steps - 1 (see sweep_kernel), and a PERMANENT one at
+            // p = (steps - 1) / 2 kept in state copy 3 (the staging copy, free after the gather): a cell with a repeat
+            // inside the window (mu + lambda <= steps - 1) is on its cycle at p if mu <= p, and back at that state by
+            // p + lambda <= p + steps - 1; otherwise lambda < steps - 1 - p and the checkpoint at steps - 1 sees it by
+            // 2 (steps - 1) - p.  75 steps settle every cell for steps = 50, where the last checkpoint alone needs 99.
+            // (Any checkpoint that matches gives lambda exactly: it is compared every step from the one after it.)
+            const int p1 = args.brent_mid ? (steps - 1) / 2 : (1 << 20);
+            const int t1_max = args.brent_mid ? (steps - 1) + max(p1, steps - 1 - p1) + 1 : 2 * steps - 1;
             auto brent_step = [&](auto rd_tag, int t) -> bool {
                 constexpr int RD = decltype(rd_tag)::value, WR = RD ^ 1;
                 const uint32_t srd = s_lane + RD * kKcCopyBytes;
-                uint32_t qpx = 0, qpy = 0, qcx = 0, qcy = 0;
+                uint32_t qpx = 0, qpy = 0, qcx = 0, qcy = 0, qfx = 0, qfy = 0;
+                const bool p1_on = t > p1;
                 uint2 e_next = kk_lds64(s_tab);
                 kc_for_own<BASE>(extra, [&](int i) {
                     const uint2 e = e_next;
@@ -2232,19 +2249,30 @@ koki_compact_kernel(const SweepArgs args) {
                     qpy |= f.y ^ cur[i].y;
                     qcx |= f.x ^ chk[i].x;
                     qcy |= f.y ^ chk[i].y;
+                    if (p1_on) {
+                        const uint2 fix = kk_lds64(s_own + i * kKcRowBytes + 3 * kKcCopyBytes);
+                        qfx |= f.x ^ fix.x;
+                        qfy |= f.y ^ fix.y;
+                    }
                     kk_sts64(s_own + i * kKcRowBytes + WR * kKcCopyBytes, f);
+                    if (t == p1) kk_sts64(s_own + i * kKcRowBytes + 3 * kKcCopyBytes, f);
                     cur[i] = f;
                 });
-                uint32_t* v = votes + vset * 2 * kKkSlots;
+                uint32_t* v = votes + vset * 4 * kKkSlots;
                 if (qpx) atomicOr(v + 2 * lane, qpx);
                 if (qpy) atomicOr(v + 2 * lane + 1, qpy);
                 if (chk_time >= 0) {
                     if (qcx) atomicOr(v + kKkSlots + 2 * lane, qcx);
                     if (qcy) atomicOr(v + kKkSlots + 2 * lane + 1, qcy);
                 }
+                if (p1_on) {
+                    if (qfx) atomicOr(v + 2 * kKkSlots + 2 * lane, qfx);
+                    if (qfy) atomicOr(v + 2 * kKkSlots + 2 * lane + 1, qfy);
+                }
                 __syncthreads();
                 const uint2 np = *reinterpret_cast<const uint2*>(v + 2 * lane);
                 const uint2 nc = *reinterpret_cast<const uint2*>(v + kKkSlots + 2 * lane);
+                const uint2 nf = *reinterpret_cast<const uint2*>(v + 2 * kKkSlots + 2 * lane);
                 const int l = t - chk_time;
     #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -2269,13 +2297,24 @@ koki_compact_kernel(const SweepArgs args) {
                             r[6 * kKkSlots] |= newly;  // a period found through a checkpoint
                         }
                     }
+                    if (p1_on) {
+                        const uint32_t newly = ~(h ? nf.y : nf.x) & ~resolved;
+                        const int l1 = t - p1;
+                        resolved |= newly;
+                        if (warp == 0 && newly && l1 <= steps - 1) {
+#pragma unroll
+                            for (int b = 0; b < kLamPlanes; ++b)
+                                if ((l1 >> b) & 1) r[b * kKkSlots] |= newly;
+                            r[6 * kKkSlots] |= newly;
+                        }
+                    }
                 }
                 if ((((t + 1) & t) == 0 && t < steps - 1) || t == steps - 1) {
                     kc_for_own<BASE>(extra, [&](int i) { chk[i] = cur[i]; });
                     chk_time = t;
                 }
                 const int vclear = vset == 0 ? 2 : vset - 1;
-                if (tid < 2 * kKkSlots) votes[vclear * 2 * kKkSlots + tid] = 0u;
+                if (tid < 4 * kKkSlots) votes[vclear * 4 * kKkSlots + tid] = 0u;
                 vset = vset == 2 ? 0 : vset + 1;
                 return __all_sync(0xFFFFFFFFu, (resolved0 & resolved1) == 0xFFFFFFFFu);
             };
@@ -2876,6 +2915,8 @@ extern "C" int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad
     args.stop_stall = 4;
     if (const char* e = getenv("SCB_SWEEP_STOP_OPEN")) args.stop_open = atoi(e) >= 0 ? atoi(e) : 0;
     if (const char* e = getenv("SCB_SWEEP_STOP_STALL")) args.stop_stall = atoi(e) > 0 ? atoi(e) : (1 << 30);
+    args.brent_mid = 1;
+    if (const char* e = getenv("SCB_SWEEP_BRENT_MID")) args.brent_mid = e[0] != '0';
     args.ring_stall = 6;
     if (const char* e = getenv("SCB_SWEEP_RING_STALL")) args.ring_stall = atoi(e) > 0 ? atoi(e) : (1 << 30);
     if (!sort_cells && !getenv("SCB_SWEEP_STOP_OPEN")) {  // unsorted: the global step cap does the stopping
