@@ -433,7 +433,6 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     __syncthreads();
     SCB_TRACE_AT(1, tid == 0);
 
-    unsigned int claim_done = 0u;  // producer lane: how many CTAs had claimed their last tile before this one
     if (warp == kConsumerWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
@@ -494,11 +493,17 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
                     phase ^= 1;
                 }
             }
-            // this CTA has claimed its last tile; the last CTA to say so zeroes the claim counter for the next
-            // launch (which cannot start before this grid has completed: it is at best a programmatic
-            // dependent of the kernel AFTER this one)
-            // (the answer is looked at after the flush below: the round trip hides behind it)
-            claim_done = atomicAdd(cta_ticket + 2, 1u);
+            // this CTA has claimed its last tile; the last CTA to say so zeroes the claim counter for the next launch.
+            // The reset has to be in place before this CTA lets the next kernel of the stream start (the
+            // griddepcontrol.launch_dependents below: a programmatic dependent -- another launch of this kernel,
+            // say -- claims tiles before ITS griddepcontrol.wait), and a dependent only starts once EVERY CTA
+            // has triggered it, the last claimer's included.  The consumers are still a few tiles behind the
+            // producer here, so the round trip costs nothing.
+            if (atomicAdd(cta_ticket + 2, 1u) == gridDim.x - 1) {
+                atomicExch(cta_ticket + 1, 0u);
+                atomicExch(cta_ticket + 2, 0u);
+                __threadfence();
+            }
         }
         __syncwarp();
     } else {
@@ -609,10 +614,6 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     if (!kDirectRed)
         for (int i = tid; i < n_acc; i += blockDim.x)
             if (cta_acc[i]) atomicAdd(acc + i, (unsigned long long)cta_acc[i]);
-    if (warp == kConsumerWarps && lane == 0 && claim_done == gridDim.x - 1) {
-        cta_ticket[1] = 0u;
-        cta_ticket[2] = 0u;
-    }
     // sums_only on one GPU: that is all -- the consumer (the fitness kernel) is ordered behind this grid by
     // the stream, inverts the sums itself and zeroes the accumulators: no ticket, no last CTA
     if (sums_only && !peer_regions) return;

@@ -508,3 +508,44 @@ def test_peer_timeout_poisons_the_results(cuda):
     finally:
         for ex in group:
             ex.close()
+
+
+def test_counting_kernel_chained_back_to_back_keeps_every_tile(cuda):
+    """``rule_counts_kernel`` claims its tiles from a counter that the last CTA to finish claiming zeroes again.  A
+    launch chained behind another launch of the same plan (programmatic dependent launch: it claims tiles before
+    its ``griddepcontrol.wait``) must find the counter reset: in sums-only mode the subset sums of K chained passes
+    pile up in the scratch, so they must be exactly K times the sums of one pass -- a tile claimed twice or
+    dropped shows in every integer."""
+    import torch
+    from scbonita2_b200 import device
+    n, cells = 120, 700_000
+    specs = synth.random_network(n, 5)
+    planes = device.BitPlanes.from_packed(synth.random_planes(n, cells, 77), cells)
+    targets, parents = [s.index for s in specs], [synth.spec_parent_rows(s) for s in specs]
+    n_acc = n + 11 * n
+
+    def sums_after(k_passes, chained):
+        plan = device.RuleCountsPlan(n, targets, parents)
+        assert plan.fused_supported
+        for _ in range(k_passes):
+            plan.sums_run(planes, chained=chained)
+        torch.cuda.synchronize()
+        return plan.scratch[:8 * n_acc].view(torch.int64).clone()
+
+    one = sums_after(1, False)
+    assert int(one.sum().item()) > 0
+    for k in (2, 37):
+        assert torch.equal(sums_after(k, True), one * k)
+    # and through a CUDA graph, where the chained launches really run back to back
+    plan = device.RuleCountsPlan(n, targets, parents)
+    plan.sums_run(planes, chained=True)
+    torch.cuda.synchronize()
+    plan.scratch.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(25):
+            plan.sums_run(planes, chained=True)
+    for rep in range(1, 4):
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(plan.scratch[:8 * n_acc].view(torch.int64), one * (25 * rep))

@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
-for m in 0 1 0 1; do echo -n "mid=$m "; SCB_SWEEP_BRENT_MID=$m python tools/run_k50.py 2>&1 | tail -1 | cut -c230-290; done
-for m in 0 1; do echo -n "mid=$m "; SCB_SWEEP_BRENT_MID=$m ITERS=3 python tools/time_sweep.py | tail -1 | cut -c1-40; done
+timeout 600 python -m pytest tests/test_gpu_rules.py -x -q -m gpu 2>&1 | tail -3
+python bench.py --steps 40 --warmup 5 --sweep-steps 0 --no-cpu-baseline --no-e2e --no-e2e-dense 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('   step %.2f us  counts alone %.2f us  checksum %d' % (d['ms_per_step']*1e3, d['roofline']['kernel_ms']*1e3, d['config']['fitness_checksum']))"
