@@ -226,7 +226,10 @@ int scb_bitstring_fitness(const int64_t* task_diff /*[T]*/, int64_t n_tasks, int
  * first.  scratch: scb_ko_ki_sweep_scratch_bytes(...) bytes, 16-byte aligned, private to the call
  * while it runs (normal-run states node-major and cell-major, two per-node lists of deferred cells:
  * about (2 * steps * N / 8 + 8 * N) bytes per cell, 4.5 GB for 200 nodes x 1M cells x 50 steps).
- * Environment knobs for experiments only: SCB_SWEEP_FAST_STEPS, SCB_SWEEP_RING, SCB_SWEEP_SLOTS. */
+ * Environment knobs for experiments and tests only (every setting gives the same integers): SCB_SWEEP_FAST_STEPS,
+ * SCB_SWEEP_RING, SCB_SWEEP_SLOTS, SCB_SWEEP_SORT, SCB_SWEEP_STOP_OPEN / _STOP_STALL / _RING_STALL,
+ * SCB_SWEEP_KOKI=old, SCB_SWEEP_RECHECK=old, SCB_SWEEP_CLEANUP=old (the round-1 kernels for a pass),
+ * SCB_SWEEP_SINGLES=0 (open cells always travel as KO/KI pairs), SCB_SWEEP_BRENT_MID=0. */
 int64_t scb_ko_ki_sweep_scratch_bytes(int n_nodes, int64_t wpad, int steps);
 int scb_ko_ki_sweep(const uint32_t* planes, int n_nodes, int64_t wpad, int64_t n_cells,
                     const int32_t* net_parent /*[N][3]*/, const uint8_t* net_lut /*[N]*/,

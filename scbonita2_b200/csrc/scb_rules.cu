@@ -81,6 +81,12 @@ __device__ __forceinline__ unsigned long long peer_timeout_ns(const unsigned cha
 // Launched as a programmatic dependent of the kernel before it in the stream (rule_counts_kernel
 // in the GA step): its launch latency hides behind that kernel's tail; griddepcontrol.wait comes
 // before the first global read.
+#ifdef SCB_TRACE
+__device__ unsigned long long g_fit_phase[16];  // globaltimer of CTA 0 at the phase boundaries of the last launch
+#define SCB_FIT_AT(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_fit_phase[i] = global_timer_ns(); } while (0)
+#else
+#define SCB_FIT_AT(i) do { } while (0)
+#endif
 __global__ void __launch_bounds__(1024)
 population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int64_t n_ind,
                           const uint8_t* __restrict__ lut, const uint8_t* __restrict__ active,
@@ -114,8 +120,10 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
             for (int64_t i = threadIdx.x; i < n_bytes; i += blockDim.x) s_lut[i] = __ldg(src + i);
         }
     }
+    SCB_FIT_AT(0);
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the producers' writes are visible from here on
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    SCB_FIT_AT(1);
     // Sharded cells: the counts are the sum of every rank's slot in the local exchange region, tagged
     // words {epoch + 1 : count}.  The rank's own slot (written earlier in this stream) names the epoch.
     const unsigned long long* slots = nullptr;
@@ -157,6 +165,7 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     const unsigned long long give_up_ns = region ? peer_timeout_ns(region) : 0ull;
     if (c_size > 1) cluster_sync_all();  // every CTA of the cluster is running (and s_wide is cleared) before a peer stores into it
     int wide = 0;
+    unsigned int zero_ticket = 0u;  // thread 0, sums on one GPU: how many CTAs had read the accumulators before this one
     long long* ones = reinterpret_cast<long long*>(nib);
     const int sums_dbg = sums.mode >> 4;   // experiments: 1 = no ticket / zeroing, 2 = no loads
     if ((sums.mode & 15) != 0) {
@@ -188,18 +197,12 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
             }
         }
         __syncthreads();  // (also: s_wide / s_timeout are cleared)
-        if ((sums.mode & 15) == 1 && !(sums_dbg & 1) && threadIdx.x < 32) {
-            // every read of the global accumulators by this CTA is done: warp 0 of the last CTA to get here
-            // zeroes them (and the ticket) for the next pass, while everybody else goes on
-            unsigned int t = 0;
-            if (threadIdx.x == 0)
-                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(sums.ticket) : "memory");
-            t = __shfl_sync(0xFFFFFFFFu, t, 0);
-            if (t == gridDim.x - 1) {
-                for (int i = threadIdx.x; i < n_acc; i += 32) sums.acc[i] = 0ull;
-                if (threadIdx.x == 0) *sums.ticket = 0u;
-            }
-        }
+        SCB_FIT_AT(2);
+        // Every read of the global accumulators by this CTA is done (the values sit in shared memory): the last
+        // CTA to say so zeroes them, and the ticket, for the next pass.  The ticket is a plain relaxed add whose
+        // answer is only looked at after the tables are built (below): an acquire-release add here cost the CTA
+        // ~2.5 us of fence and round trip in front of the inversion (tools/trace_fit.py).
+        if ((sums.mode & 15) == 1 && !(sums_dbg & 1) && threadIdx.x == 0) zero_ticket = atomicAdd(sums.ticket, 1u);
         const int q = threadIdx.x & 15;
         constexpr int kBatch = 4;  // the loads of four rounds fly together (two dependent L2 trips in all)
         const int per_round = blockDim.x >> 4;
@@ -225,6 +228,7 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
 #pragma unroll
                 for (int k = 0; k < kBatch; ++k)
                     if (q == 0 && live[k]) v[k] = sums.n_cells;
+                SCB_FIT_AT(8);
             } else {
                 // (one round at a time: the eight ranks' loads of a word already fly together)
 #pragma unroll 1
@@ -267,6 +271,7 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
                     ones[q * n_groups + g[k]] = y;
                 }
             }
+            SCB_FIT_AT(9);
         }
     } else
     for (int e = threadIdx.x * (int)c_size + (int)c_rank; e < n_groups * 8; e += blockDim.x * (int)c_size) {
@@ -318,6 +323,7 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
     }
     if (c_size > 1) cluster_sync_all();  // release / acquire: the peers' stores are visible from here on
     else __syncthreads();
+    SCB_FIT_AT(3);
     wide |= (int)s_wide;
     const bool poisoned = s_timeout != 0u;
     for (int g = threadIdx.x; g < n_groups; g += blockDim.x) {
@@ -327,6 +333,7 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
         base[g] = b;
     }
     wide = __syncthreads_or(wide);
+    SCB_FIT_AT(4);
     if (!wide) {
         // warp w builds row w of the nibble tables (0..15 low nibble, 16..31 high nibble) from the
         // deltas in shared memory, lanes striding over the groups
@@ -341,6 +348,15 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
             }
         }
         __syncthreads();
+    }
+    SCB_FIT_AT(5);
+    if ((sums.mode & 15) == 1 && !(sums.mode >> 4 & 1) && threadIdx.x < 32) {
+        const unsigned int t = __shfl_sync(0xFFFFFFFFu, zero_ticket, 0);
+        if (t == gridDim.x - 1) {
+            const int n_acc_all = sums.n_rows + kTermsPerGroup * n_groups;
+            for (int i = threadIdx.x; i < n_acc_all; i += 32) sums.acc[i] = 0ull;
+            if (threadIdx.x == 0) *sums.ticket = 0u;
+        }
     }
     if (lut_off > 0) {
         // staged tables (launch_population_fitness only stages when the fast conditions hold)
@@ -363,6 +379,7 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
             for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, off);
             if (lane == 0) out_diff[p] = poisoned ? (long long)0x8000000000000000ull : total;
         }
+        SCB_FIT_AT(6);
         return;
     }
     for (int64_t p = warp0; p < n_ind; p += n_warps) {
@@ -474,6 +491,14 @@ error_table_direct_kernel(const uint32_t* __restrict__ planes, int64_t wpad, int
 }  // namespace scb
 
 using namespace scb;
+
+#ifdef SCB_TRACE
+extern "C" int scb_debug_fit_phases(unsigned long long* out /*HOST [16]*/) {
+    SCB_CUDA(cudaDeviceSynchronize());
+    SCB_CUDA(cudaMemcpyFromSymbol(out, g_fit_phase, sizeof(unsigned long long) * 16));
+    return SCB_OK;
+}
+#endif
 
 extern "C" int scb_rule_error_table(const int64_t* counts, int n_groups, int64_t n_tasks,
                                     const int32_t* task_group, const uint8_t* task_lut,
