@@ -194,14 +194,16 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
 // given) are skipped: the normal run only fills the slices its longest cycle needs.
 __global__ void __launch_bounds__(256)
 cell_major_kernel(const uint32_t* __restrict__ src, int n_rows, int64_t wpad, uint32_t* __restrict__ dst,
-                  int nwp, const unsigned int* __restrict__ last_slice) {
-    if (last_slice && blockIdx.z > *last_slice) return;
+                  int nwp, const unsigned int* __restrict__ last_slice, int n_slices) {
     __shared__ uint32_t tile[32][33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t w0 = (int64_t)blockIdx.x * 32;
     const int j = blockIdx.y;
-    src += (size_t)blockIdx.z * n_rows * wpad;
-    dst += (size_t)blockIdx.z * wpad * 32 * nwp;
+    // (a CTA walks the slices itself: a grid with one z-layer per slice launches 50 x as many CTAs, nearly all of
+    // which find their slice past *last_slice and leave -- 0.4 ms of launch overhead on the 1M-cell sweep)
+    const int z_end = last_slice ? min(n_slices, (int)*last_slice + 1) : n_slices;
+    for (int z = 0; z < z_end; ++z, src += (size_t)n_rows * wpad, dst += (size_t)wpad * 32 * nwp) {
+    if (z) __syncthreads();
     for (int r = warp; r < 32; r += 8) {
         const int row = 32 * j + r;
         tile[r][lane] = (row < n_rows && w0 + lane < wpad) ? __ldg(src + (size_t)row * wpad + w0 + lane) : 0u;
@@ -217,6 +219,7 @@ cell_major_kernel(const uint32_t* __restrict__ src, int n_rows, int64_t wpad, ui
             if (lane == l) mine = bits;
         }
         dst[((size_t)(w0 + wc) * 32 + lane) * nwp + j] = mine;
+    }
     }
 }
 
@@ -2650,7 +2653,7 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
         // of the slowest cell's of the whole data set.  Every output is a sum over cells, so the order is
         // free.  probe (key per cell) -> counting sort of the cell-major records -> back to bitplanes.
         uint32_t* rec0 = args.np_states_t;  // records in the caller's order; dead before np_states_t is written
-        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes, args.n_nodes, args.wpad, rec0, args.nwp, nullptr);
+        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes, args.n_nodes, args.wpad, rec0, args.nwp, nullptr, 1);
         SCB_LAUNCH_CHECK("cell_major_kernel<data>");
         args.probe = 1;
         sweep_kernel<SLOTS, MODE_NORMAL><<<grid_n, kSweepThreads, smem, stream>>>(args);
@@ -2672,16 +2675,15 @@ static int launch_sweep(SweepArgs args, const SweepLists& lists, uint32_t* plane
     // cell-major copies of the data and of the normal-run states for the compacted passes
     {
         if (!sort_cells) {  // (sorted: planes_t is what the sort made)
-            cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes, args.n_nodes, args.wpad, args.planes_t, args.nwp, nullptr);
+            cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.planes, args.n_nodes, args.wpad, args.planes_t, args.nwp, nullptr, 1);
             SCB_LAUNCH_CHECK("cell_major_kernel<data>");
         }
         grid_t.y = 1;   // np_lam[6][wpad] and np_found[wpad] are contiguous: a 7-row matrix, one word per cell
-        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.np_lam, kLamPlanes + 1, args.wpad, args.np_info_t, 1, nullptr);
+        cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.np_lam, kLamPlanes + 1, args.wpad, args.np_info_t, 1, nullptr, 1);
         SCB_LAUNCH_CHECK("cell_major_kernel<normal info>");
         grid_t.y = (unsigned)n_blocks_j;
-        grid_t.z = (unsigned)args.steps;
         cell_major_kernel<<<grid_t, 256, 0, stream>>>(args.np_states, args.n_nodes, args.wpad, args.np_states_t, args.nwp,
-                                                      args.counters + 2);
+                                                      args.counters + 2, args.steps);
         SCB_LAUNCH_CHECK("cell_major_kernel<normal run>");
     }
     if (const char* ring = getenv("SCB_SWEEP_RING")) {  // experiments: force the KO/KI ring depth

@@ -130,3 +130,15 @@ def test_dtw_table_matches_the_restated_fastdtw():
     big = np.zeros((1024, 1024), dtype=np.uint8)
     _lib.check(_lib.lib().scb_dtw_table_build(10, 1, 5, big.ctypes.data), "scb_dtw_table_build")
     assert (big != big.T).any()
+
+
+def test_bind_host_to_device_never_raises():
+    """``device.bind_host_to_device`` (NUMA placement of pinned buffers, used by bench.py) is best effort: without
+    CUDA or NVML it changes nothing and says so."""
+    import os
+    from scbonita2_b200 import device
+    before = os.sched_getaffinity(0)
+    ok = device.bind_host_to_device(0)
+    assert ok in (True, False)
+    if not ok:
+        assert os.sched_getaffinity(0) == before
