@@ -90,6 +90,8 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
 #ifdef SCB_TRACE
 __device__ int g_dbg;  // experiments: bit 0 = consumers skip the arithmetic, bit 1 = producer skips the copies
 __device__ long long g_trace[256][12];
+__device__ unsigned long long g_pdl_a[64][4];  // globaltimer of CTA 0: entry, loop exit, after griddepcontrol.wait
+__device__ unsigned int g_pdl_a_n;
 #define SCB_TRACE_AT(slot, cond) do { if (cond) g_trace[blockIdx.x & 255][slot] = clock64(); } while (0)
 #else
 #define SCB_TRACE_AT(slot, cond) do { } while (0)
@@ -403,6 +405,10 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     const int lane = tid & 31;
     const int warp = tid >> 5;
     SCB_TRACE_AT(0, tid == 0);
+#ifdef SCB_TRACE
+    __shared__ unsigned int s_pdl_i;
+    if (tid == 0 && blockIdx.x == 0) { s_pdl_i = atomicAdd(&g_pdl_a_n, 1u) & 63u; g_pdl_a[s_pdl_i][0] = global_timer_ns(); }
+#endif
 
     // the plan's tables are fetched first thing (the loads fly while the barriers are set up)
     const int n_orphans = reinterpret_cast<const int*>(plan)[2];
@@ -608,8 +614,14 @@ rule_counts_kernel(const __grid_constant__ CUtensorMap tmap, int box_rows, int n
     // fitness kernel) may be scheduled from here on, and everything above may have run while the
     // kernel BEFORE this one (a reader of out_counts from the previous pass) was still draining --
     // nothing above writes global memory.  Both are no-ops for plain launches.
+#ifdef SCB_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_pdl_a[s_pdl_i][1] = global_timer_ns();
+#endif
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef SCB_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_pdl_a[s_pdl_i][2] = global_timer_ns();
+#endif
     // fold this CTA's sums into the global int64 accumulators (integer adds: order-free, exact)
     if (!kDirectRed)
         for (int i = tid; i < n_acc; i += blockDim.x)
@@ -719,6 +731,11 @@ static int make_tensor_map(const uint32_t* planes, int n_rows, int64_t wpad, int
 using namespace scb;
 
 #ifdef SCB_TRACE
+extern "C" int scb_debug_pdl_a(unsigned long long* out /*HOST [64][4]*/) {
+    SCB_CUDA(cudaDeviceSynchronize());
+    SCB_CUDA(cudaMemcpyFromSymbol(out, g_pdl_a, sizeof(unsigned long long) * 64 * 4));
+    return SCB_OK;
+}
 extern "C" int scb_debug_trace_read(long long* out /*HOST [256][12]*/) {
     SCB_CUDA(cudaDeviceSynchronize());
     SCB_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 256 * 12));
@@ -833,8 +850,8 @@ static int counts_run(const uint32_t* planes, int n_rows, int64_t wpad, int64_t 
         auto* acc = static_cast<unsigned long long*>(scratch);
         auto* ticket = reinterpret_cast<unsigned int*>(acc + n_acc);
 #ifdef SCB_TRACE
-        {
-            int dbg = getenv("SCB_COUNTS_DBG") ? atoi(getenv("SCB_COUNTS_DBG")) : 0;
+        if (getenv("SCB_COUNTS_DBG")) {  // (a copy node between two kernels breaks their programmatic edge)
+            int dbg = atoi(getenv("SCB_COUNTS_DBG"));
             SCB_CUDA(cudaMemcpyToSymbolAsync(g_dbg, &dbg, sizeof(int), 0, cudaMemcpyHostToDevice, as_stream(stream)));
         }
 #endif

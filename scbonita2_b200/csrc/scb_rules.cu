@@ -82,6 +82,8 @@ __device__ __forceinline__ unsigned long long peer_timeout_ns(const unsigned cha
 // in the GA step): its launch latency hides behind that kernel's tail; griddepcontrol.wait comes
 // before the first global read.
 #ifdef SCB_TRACE
+__device__ unsigned long long g_pdl_b[64][4];  // globaltimer of CTA 0: entry, after griddepcontrol.wait, end
+__device__ unsigned int g_pdl_b_n;
 __device__ unsigned long long g_fit_phase[16];  // globaltimer of CTA 0 at the phase boundaries of the last launch
 #define SCB_FIT_AT(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_fit_phase[i] = global_timer_ns(); } while (0)
 #else
@@ -121,9 +123,16 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
         }
     }
     SCB_FIT_AT(0);
+#ifdef SCB_TRACE
+    __shared__ unsigned int s_pdl_i;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { s_pdl_i = atomicAdd(&g_pdl_b_n, 1u) & 63u; g_pdl_b[s_pdl_i][0] = global_timer_ns(); }
+#endif
     asm volatile("griddepcontrol.wait;" ::: "memory");       // the producers' writes are visible from here on
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     SCB_FIT_AT(1);
+#ifdef SCB_TRACE
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_pdl_b[s_pdl_i][1] = global_timer_ns();
+#endif
     // Sharded cells: the counts are the sum of every rank's slot in the local exchange region, tagged
     // words {epoch + 1 : count}.  The rank's own slot (written earlier in this stream) names the epoch.
     const unsigned long long* slots = nullptr;
@@ -380,6 +389,9 @@ population_fitness_kernel(const int64_t* __restrict__ counts, int n_groups, int6
             if (lane == 0) out_diff[p] = poisoned ? (long long)0x8000000000000000ull : total;
         }
         SCB_FIT_AT(6);
+#ifdef SCB_TRACE
+        if (threadIdx.x == 0 && blockIdx.x == 0) g_pdl_b[s_pdl_i][2] = global_timer_ns();
+#endif
         return;
     }
     for (int64_t p = warp0; p < n_ind; p += n_warps) {
@@ -493,6 +505,11 @@ error_table_direct_kernel(const uint32_t* __restrict__ planes, int64_t wpad, int
 using namespace scb;
 
 #ifdef SCB_TRACE
+extern "C" int scb_debug_pdl_b(unsigned long long* out /*HOST [64][4]*/) {
+    SCB_CUDA(cudaDeviceSynchronize());
+    SCB_CUDA(cudaMemcpyFromSymbol(out, g_pdl_b, sizeof(unsigned long long) * 64 * 4));
+    return SCB_OK;
+}
 extern "C" int scb_debug_fit_phases(unsigned long long* out /*HOST [16]*/) {
     SCB_CUDA(cudaDeviceSynchronize());
     SCB_CUDA(cudaMemcpyFromSymbol(out, g_fit_phase, sizeof(unsigned long long) * 16));
