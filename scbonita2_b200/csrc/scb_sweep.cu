@@ -1924,6 +1924,7 @@ koki_compact_kernel(const SweepArgs args) {
     constexpr int NV = SINGLES ? 64 : 32;     // virtual words per batch
     constexpr int kBatch = NV * 32;           // list entries per batch
     constexpr int MODE = RECHECK ? MODE_RECHECK : MODE_CLEANUP;  // (trace macros)
+    (void)MODE;
     extern __shared__ __align__(16) uint32_t smem[];
     const int N = args.n_nodes;
     const int steps = args.steps;
@@ -1943,7 +1944,6 @@ koki_compact_kernel(const SweepArgs args) {
     const int rem = N - BASE * kKcWarps;  // 0 <= rem < 24 by the choice of BASE
     const bool extra = warp < rem;
     const int n0 = warp * BASE + min(warp, rem);
-    const int cnt = BASE + (extra ? 1 : 0);
 
     for (int n = tid; n < N + kKkTabPad; n += kKcThreads) {
         KkEntry e = kk_make_entry(0, 0, 0, 0, affine_table(0u, 0));
