@@ -779,8 +779,8 @@ def run_ours(args):
                                      "note": "algorithmic ops = full 50 steps for every condition, one LUT3 per "
                                              "(node, 32 cells, step); the kernels use early exit (a CTA stops when its "
                                              "cells have repeated), cycle detection and deferral are not counted; what binds "
-                                             "the dominant kernel (koki_plane_kernel, ncu, profiles/r2_sweep_plane_ncu.txt): "
-                                             "shared-memory wavefronts 74 %, ALU pipe 71 %, issue slots 76 % of peak"}
+                                             "the dominant kernel (koki_plane_kernel, ncu, profiles/r2_sweep_final_ncu.txt): "
+                                             "issue slots 77 %, ALU pipe 72 %, shared-memory wavefronts 75 % of peak"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
