@@ -1,9 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke()"
-python bench.py > gpurun_out/bench_r2j.json 2> gpurun_out/bench_r2j.err; tail -1 gpurun_out/bench_r2j.err | cut -c1-200
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_r2j.json').read().strip().splitlines()[-1])
-print('step', d['ms_per_step']*1e3, 'e2e', d['e2e']['ms_per_step'], 'sweep', d['sweep']['seconds'], 'frac', d['roofline']['frac'], d['clocks'])
-PY
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e-dense > gpurun_out/plain_final2.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e-dense > gpurun_out/ncu_final_l2.log 2>&1
+tail -c 300 gpurun_out/plain_final2.log
